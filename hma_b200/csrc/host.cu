@@ -1,0 +1,84 @@
+// Host-side plumbing shared by every entry point: error string, TMA descriptor encoding
+// (through the driver entry point, so the library does not link libcuda), SM count.
+#include "common.cuh"
+#include "../../include/hma_b200.h"
+
+#include <cstdarg>
+#include <cstdio>
+#include <mutex>
+
+namespace hma_host {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+const char* last_error() { return g_err; }
+
+using EncodeFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                              const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                              CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                              CUtensorMapFloatOOBfill);
+
+static EncodeFn get_encode() {
+  static EncodeFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess) {
+      fn = reinterpret_cast<EncodeFn>(p);
+    }
+  });
+  return fn;
+}
+
+int make_tmap_bf16_2d(CUtensorMap* map, const void* base, uint64_t inner, uint64_t outer,
+                      uint64_t row_stride_bytes, uint32_t box_inner, uint32_t box_outer) {
+  EncodeFn enc = get_encode();
+  HMA_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled not available from the driver");
+  HMA_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "TMA base must be 16-byte aligned");
+  HMA_REQUIRE((row_stride_bytes & 15) == 0, "TMA row stride must be a multiple of 16 bytes");
+  HMA_REQUIRE(box_inner * 2 == 128, "128-byte swizzle needs a 64-element bf16 inner box");
+  HMA_REQUIRE(box_outer >= 1 && box_outer <= 256, "TMA box rows out of range");
+  cuuint64_t gdim[2] = {inner, outer};
+  cuuint64_t gstr[1] = {row_stride_bytes};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr, box,
+                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  HMA_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return 0;
+}
+
+int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) n = 148;
+  }
+  return n;
+}
+
+}  // namespace hma_host
+
+extern "C" {
+int hma_abi_version(void) { return HMA_B200_ABI_VERSION; }
+const char* hma_last_error(void) { return hma_host::last_error(); }
+int hma_device_check(void) {
+  int dev = 0;
+  HMA_CHECK_CUDA(cudaGetDevice(&dev));
+  int major = 0, minor = 0;
+  HMA_CHECK_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+  HMA_CHECK_CUDA(cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev));
+  HMA_REQUIRE(major == 10, "hma_b200 kernels are sm_100a only; device is sm_%d%d", major, minor);
+  return 0;
+}
+}

@@ -1,0 +1,109 @@
+"""tcgen05 contractions vs fp32 torch matmul on the same bf16-rounded inputs (GPU only)."""
+import pytest
+import torch
+
+from hma_b200 import _lib
+
+pytestmark = pytest.mark.gpu
+
+EPI_BF16, EPI_GELU, EPI_DGELU, EPI_RESID = 0, 1, 2, 3
+
+
+def _report(name, got, ref):
+    err = (got.float() - ref.float()).abs()
+    denom = ref.float().abs().max().clamp_min(1e-6)
+    rel = (err.max() / denom).item()
+    if rel > 2e-2:
+        # error structure by 32-row / 32-col blocks helps to localise descriptor / swizzle bugs
+        M, N = err.shape
+        rb = err[: M // 32 * 32].reshape(M // 32, 32, N).amax(dim=(1, 2))
+        cb = err[:, : N // 32 * 32].reshape(M, N // 32, 32).amax(dim=(0, 2))
+        print(f"[{name}] rel={rel:.3e} rowblocks={rb[:16].tolist()} colblocks={cb[:16].tolist()}")
+    return rel
+
+
+def gemm_nt(A, B, epi, bias=None, resid=None, aux=None, alpha=1.0, want_z=False):
+    M, K = A.shape
+    N = B.shape[0]
+    out_dtype = torch.float32 if epi == EPI_RESID else torch.bfloat16
+    out = torch.empty(M, N, device=A.device, dtype=out_dtype)
+    out2 = torch.empty(M, N, device=A.device, dtype=torch.bfloat16) if want_z else None
+    _lib.call(
+        "hma_gemm_nt", A.data_ptr(), A.stride(0), B.data_ptr(), B.stride(0), M, N, K, epi, out.data_ptr(),
+        out.stride(0), _lib.ptr(out2), N, _lib.ptr(bias), _lib.ptr(resid), N, _lib.ptr(aux), N, alpha,
+        _lib.current_stream(),
+    )
+    return out, out2
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (256, 256, 256), (1000, 768, 256), (4096, 1024, 256),
+                                   (640, 256, 1024), (333, 256, 768), (40960, 256, 256)])
+def test_gemm_nt_bf16(M, N, K):
+    torch.manual_seed(0)
+    A = torch.randn(M, K, device="cuda").bfloat16()
+    B = (torch.randn(N, K, device="cuda") * 0.1).bfloat16()
+    bias = torch.randn(N, device="cuda")
+    out, _ = gemm_nt(A, B, EPI_BF16, bias=bias)
+    torch.cuda.synchronize()
+    ref = A.float() @ B.float().t() + bias
+    assert _report(f"nt {M}x{N}x{K}", out, ref) < 1e-2
+
+
+def test_gemm_nt_epilogues():
+    torch.manual_seed(1)
+    M, N, K = 777, 1024, 256
+    A = torch.randn(M, K, device="cuda").bfloat16()
+    B = (torch.randn(N, K, device="cuda") * 0.08).bfloat16()
+    bias = torch.randn(N, device="cuda") * 0.5
+    z_ref = A.float() @ B.float().t() + bias
+    h, z = gemm_nt(A, B, EPI_GELU, bias=bias, want_z=True)
+    torch.cuda.synchronize()
+    assert _report("gelu.z", z, z_ref) < 1e-2
+    assert _report("gelu.h", h, torch.nn.functional.gelu(z_ref)) < 1e-2
+
+    # dGELU: out = acc * gelu'(aux)
+    aux = torch.randn(M, N, device="cuda").bfloat16()
+    g, _ = gemm_nt(A, B, EPI_DGELU, aux=aux)
+    torch.cuda.synchronize()
+    zz = aux.float().requires_grad_(True)
+    torch.nn.functional.gelu(zz).sum().backward()
+    assert _report("dgelu", g, (A.float() @ B.float().t()) * zz.grad) < 1e-2
+
+    # fp32 residual
+    resid = torch.randn(M, N, device="cuda")
+    o, _ = gemm_nt(A, B, EPI_RESID, bias=bias, resid=resid, alpha=0.5)
+    torch.cuda.synchronize()
+    ref = resid + 0.5 * (A.float() @ B.float().t()) + bias
+    assert _report("resid", o, ref) < 2e-3
+    o2, _ = gemm_nt(A, B, EPI_RESID)
+    torch.cuda.synchronize()
+    assert _report("f32", o2, A.float() @ B.float().t()) < 2e-3
+
+
+@pytest.mark.parametrize("tokens,Mw,Nw", [(64, 128, 128), (4096, 256, 256), (5000, 768, 256), (3000, 256, 1024),
+                                          (40960, 1024, 256)])
+def test_gemm_wgrad(tokens, Mw, Nw):
+    torch.manual_seed(2)
+    G = (torch.randn(tokens, Mw, device="cuda") * 0.1).bfloat16()
+    X = torch.randn(tokens, Nw, device="cuda").bfloat16()
+    dW = torch.zeros(Mw, Nw, device="cuda")
+    for _ in range(2):  # accumulates
+        _lib.call("hma_gemm_wgrad", G.data_ptr(), Mw, X.data_ptr(), Nw, tokens, Mw, Nw, dW.data_ptr(), Nw,
+                  _lib.current_stream())
+    torch.cuda.synchronize()
+    ref = 2 * (G.float().t() @ X.float())
+    assert _report(f"wgrad {tokens}x{Mw}x{Nw}", dW, ref) < 2e-3
+
+
+def test_gemm_wgrad_strided_views():
+    """Operands that are column slices of wider matrices (as qkv / grad buffers are)."""
+    torch.manual_seed(3)
+    tokens = 2000
+    Gfull = (torch.randn(tokens, 768, device="cuda") * 0.1).bfloat16()
+    X = torch.randn(tokens, 256, device="cuda").bfloat16()
+    G = Gfull[:, 256:512]
+    dW = torch.zeros(256, 256, device="cuda")
+    _lib.call("hma_gemm_wgrad", G.data_ptr(), 768, X.data_ptr(), 256, tokens, 256, 256, dW.data_ptr(), 256,
+              _lib.current_stream())
+    torch.cuda.synchronize()
+    assert _report("wgrad-view", dW, G.float().t() @ X.float()) < 2e-3
