@@ -30,6 +30,35 @@ _SIGNATURES = {
     "hma_device_check": [],
     "hma_gemm_nt": [c_void_p, c_ll, c_void_p, c_ll, c_int, c_int, c_int, c_int, c_void_p, c_ll, c_void_p, c_ll,
                     c_fp, c_fp, c_ll, c_void_p, c_ll, c_float, c_void_p],
+    "hma_attn_spatial_fwd": [c_void_p, c_ll, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p, c_ll, c_fp,
+                             c_void_p],
+    "hma_attn_spatial_bwd": [c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_ll, c_fp, c_int, c_int, c_int, c_int, c_int,
+                             c_int, c_float, c_void_p, c_ll, c_void_p],
+    "hma_attn_temporal_fwd": [c_void_p, c_ll, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p,
+                              c_ll, c_void_p],
+    "hma_attn_temporal_bwd": [c_void_p, c_ll, c_void_p, c_ll, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                              c_float, c_void_p, c_ll, c_void_p],
+    "hma_ln_fwd": [c_fp, c_ll, c_int, c_int, c_fp, c_fp, c_fp, c_int, c_float, c_void_p, c_ll, c_fp, c_void_p],
+    "hma_ln_bwd": [c_void_p, c_ll, c_fp, c_ll, c_fp, c_int, c_int, c_fp, c_fp, c_int, c_fp, c_ll, c_fp, c_fp, c_fp,
+                   c_void_p],
+    "hma_colsum_bf16": [c_void_p, c_ll, c_int, c_int, c_fp, c_void_p],
+    "hma_colsum_f32": [c_fp, c_ll, c_int, c_int, c_fp, c_void_p],
+    "hma_cast_transpose": [c_fp, c_int, c_int, c_void_p, c_void_p, c_float, c_void_p],
+    "hma_cast_bf16": [c_fp, c_void_p, c_ll, c_void_p],
+    "hma_action_prep": [c_fp, c_int, c_int, c_fp, c_fp, c_int, c_void_p, c_int, c_void_p],
+    "hma_ln_relu_fwd": [c_fp, c_int, c_fp, c_fp, c_float, c_void_p, c_fp, c_void_p],
+    "hma_ln_relu_bwd": [c_fp, c_fp, c_fp, c_int, c_fp, c_fp, c_fp, c_fp, c_fp, c_void_p],
+    "hma_embed_fwd": [c_void_p, c_fp, c_fp, c_fp, c_fp, c_fp, c_int, c_int, c_int, c_int, c_int, c_int, c_ll, c_fp,
+                      c_void_p],
+    "hma_embed_bwd": [c_void_p, c_fp, c_int, c_int, c_int, c_int, c_int, c_int, c_ll, c_fp, c_fp, c_fp, c_fp, c_fp,
+                      c_void_p],
+    "hma_ce_fwd": [c_fp, c_ll, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_ll, c_float, c_fp, c_fp, c_fp,
+                   c_void_p],
+    "hma_ce_bwd": [c_fp, c_ll, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_ll, c_float, c_fp, c_fp, c_fp,
+                   c_void_p, c_ll, c_void_p],
+    "hma_sample_tokens": [c_fp, c_ll, c_ll, c_int, c_int, c_int, c_int, c_fp, c_void_p, c_fp, c_void_p],
+    "hma_rank_remask": [c_fp, c_void_p, c_void_p, c_void_p, c_ll, c_int, c_int, c_int, c_ll, c_void_p, c_void_p],
+    "hma_umma_probe": [c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_fp, c_void_p],
     "hma_gemm_wgrad": [c_void_p, c_ll, c_void_p, c_ll, c_int, c_int, c_int, c_fp, c_ll, c_void_p],
 }
 _RESTYPES = {"hma_last_error": ctypes.c_char_p}

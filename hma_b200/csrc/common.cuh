@@ -236,6 +236,12 @@ __device__ __forceinline__ float dgelu_erf(float z) {
   return cdf + z * pdf;
 }
 
+__device__ __forceinline__ float silu(float z) { return z / (1.0f + __expf(-z)); }
+__device__ __forceinline__ float dsilu(float z) {
+  const float s = 1.0f / (1.0f + __expf(-z));
+  return s * (1.0f + z * (1.0f - s));
+}
+
 }  // namespace hma
 
 // ------------------------------------------------------------------------------------------
@@ -250,6 +256,9 @@ const char* last_error();
 // box_inner must be 64 (= 128 bytes); out-of-bounds elements read as zero.
 int make_tmap_bf16_2d(CUtensorMap* map, const void* base, uint64_t inner, uint64_t outer,
                       uint64_t row_stride_bytes, uint32_t box_inner, uint32_t box_outer);
+
+int make_tmap_bf16_2d_sw(CUtensorMap* map, const void* base, uint64_t inner, uint64_t outer,
+                         uint64_t row_stride_bytes, uint32_t box_inner, uint32_t box_outer, int swizzle_bytes);
 
 int sm_count();
 

@@ -57,7 +57,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmNtParams& p, const uint
     for (int j = 0; j < 4; ++j)
       dst[j] = make_uint4(pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
                           pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
-  } else if constexpr (EPI == HMA_EPI_GELU_BF16) {
+  } else if constexpr (EPI == HMA_EPI_GELU_BF16 || EPI == HMA_EPI_SILU_BF16) {
     if (p.out2 != nullptr) {
       uint4* dz = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out2) + (size_t)row * p.ldo2 + n0);
 #pragma unroll
@@ -66,13 +66,13 @@ __device__ __forceinline__ void epilogue_chunk(const GemmNtParams& p, const uint
                            pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
     }
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+    for (int j = 0; j < 32; ++j) v[j] = (EPI == HMA_EPI_GELU_BF16) ? gelu_erf(v[j]) : silu(v[j]);
     uint4* dst = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + (size_t)row * p.ldo + n0);
 #pragma unroll
     for (int j = 0; j < 4; ++j)
       dst[j] = make_uint4(pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
                           pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
-  } else if constexpr (EPI == HMA_EPI_DGELU_BF16) {
+  } else if constexpr (EPI == HMA_EPI_DGELU_BF16 || EPI == HMA_EPI_DSILU_BF16) {
     const uint4* z = reinterpret_cast<const uint4*>(p.aux + (size_t)row * p.ldaux + n0);
     uint4* dst = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + (size_t)row * p.ldo + n0);
 #pragma unroll
@@ -82,8 +82,10 @@ __device__ __forceinline__ void epilogue_chunk(const GemmNtParams& p, const uint
       uint32_t o[4];
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        const float g0 = v[8 * j + 2 * q] * dgelu_erf(bf16_lo(zw[q]));
-        const float g1 = v[8 * j + 2 * q + 1] * dgelu_erf(bf16_hi(zw[q]));
+        const float d0 = (EPI == HMA_EPI_DGELU_BF16) ? dgelu_erf(bf16_lo(zw[q])) : dsilu(bf16_lo(zw[q]));
+        const float d1 = (EPI == HMA_EPI_DGELU_BF16) ? dgelu_erf(bf16_hi(zw[q])) : dsilu(bf16_hi(zw[q]));
+        const float g0 = v[8 * j + 2 * q] * d0;
+        const float g1 = v[8 * j + 2 * q + 1] * d1;
         o[q] = pack_bf16(g0, g1);
       }
       dst[j] = make_uint4(o[0], o[1], o[2], o[3]);
@@ -306,6 +308,10 @@ extern "C" int hma_gemm_nt(const void* A, long long lda, const void* B, long lon
       HMA_REQUIRE(aux != nullptr, "gemm_nt: dGELU epilogue needs the saved pre-activation");
       return dispatch_nt<HMA_EPI_DGELU_BF16>(tmA, tmB, p, bn, stream);
     case HMA_EPI_RESID_F32: return dispatch_nt<HMA_EPI_RESID_F32>(tmA, tmB, p, bn, stream);
+    case HMA_EPI_SILU_BF16: return dispatch_nt<HMA_EPI_SILU_BF16>(tmA, tmB, p, bn, stream);
+    case HMA_EPI_DSILU_BF16:
+      HMA_REQUIRE(aux != nullptr, "gemm_nt: dSiLU epilogue needs the saved pre-activation");
+      return dispatch_nt<HMA_EPI_DSILU_BF16>(tmA, tmB, p, bn, stream);
     default: break;
   }
   HMA_REQUIRE(false, "gemm_nt: unknown epilogue %d", epi);

@@ -40,18 +40,25 @@ static EncodeFn get_encode() {
 
 int make_tmap_bf16_2d(CUtensorMap* map, const void* base, uint64_t inner, uint64_t outer,
                       uint64_t row_stride_bytes, uint32_t box_inner, uint32_t box_outer) {
+  return make_tmap_bf16_2d_sw(map, base, inner, outer, row_stride_bytes, box_inner, box_outer, 128);
+}
+
+int make_tmap_bf16_2d_sw(CUtensorMap* map, const void* base, uint64_t inner, uint64_t outer,
+                         uint64_t row_stride_bytes, uint32_t box_inner, uint32_t box_outer, int swizzle_bytes) {
   EncodeFn enc = get_encode();
   HMA_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled not available from the driver");
   HMA_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "TMA base must be 16-byte aligned");
   HMA_REQUIRE((row_stride_bytes & 15) == 0, "TMA row stride must be a multiple of 16 bytes");
-  HMA_REQUIRE(box_inner * 2 == 128, "128-byte swizzle needs a 64-element bf16 inner box");
+  HMA_REQUIRE(swizzle_bytes == 128 || swizzle_bytes == 64, "unsupported swizzle %d", swizzle_bytes);
+  HMA_REQUIRE((int)box_inner * 2 == swizzle_bytes, "inner box must span exactly one swizzle row");
   HMA_REQUIRE(box_outer >= 1 && box_outer <= 256, "TMA box rows out of range");
   cuuint64_t gdim[2] = {inner, outer};
   cuuint64_t gstr[1] = {row_stride_bytes};
   cuuint32_t box[2] = {box_inner, box_outer};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr, box,
-                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   HMA_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
   return 0;

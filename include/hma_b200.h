@@ -41,6 +41,8 @@ int hma_device_check(void);
 #define HMA_EPI_GELU_BF16 1  /* z = alpha*acc + bias; out2(bf16) = z (optional); out = gelu(z) */
 #define HMA_EPI_DGELU_BF16 2 /* out(bf16)  = (alpha*acc) * gelu'(aux)                          */
 #define HMA_EPI_RESID_F32 3  /* out(fp32)  = resid(fp32, optional) + alpha*acc + bias          */
+#define HMA_EPI_SILU_BF16 4  /* as GELU_BF16 with SiLU (adaLN_modulation, st_mask_git.py:61-63) */
+#define HMA_EPI_DSILU_BF16 5 /* out(bf16)  = (alpha*acc) * silu'(aux)                          */
 
 /* out[M,N] = epi(A[M,K] . B[N,K]^T). A, B bf16 row-major. Replaces nn.Linear forward
  * (attention.py:141,154; st_transformer.py:24-27; st_mask_git.py:70-75,681-683) and, with B a
@@ -53,6 +55,96 @@ int hma_gemm_nt(const void* A, long long lda, const void* B, long long ldb, int 
  * the same Linears. Mw % 128 == 0, Nw % 128 == 0. Accumulates (caller zeroes dW). */
 int hma_gemm_wgrad(const void* G, long long ldg, const void* X, long long ldx, int tokens, int Mw, int Nw,
                    float* dW, long long ldw, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Attention
+ * ------------------------------------------------------------------------------------------- */
+
+/* Bidirectional attention over the n tokens of each frame (attention.py:37-61 / 139-155,
+ * st_transformer.py:85-86). qkv: bf16 [frames*n, ld_qkv]; head h of q/k/v starts at column
+ * q_col/k_col/v_col + 32*h. out: bf16 [frames*n, ldo], head h at column 32*h. lse (optional):
+ * fp32 [frames, heads, n], log2-domain log-sum-exp for the backward. head_dim is 32;
+ * n % 16 == 0, n <= 320. */
+int hma_attn_spatial_fwd(const void* qkv, long long ld_qkv, int frames, int n, int heads, int q_col, int k_col,
+                         int v_col, float scale, void* out, long long ldo, float* lse, void* stream);
+
+/* dqkv (bf16, same layout as qkv) from dout (bf16 [frames*n, ld_dout]), out and lse of the forward. */
+int hma_attn_spatial_bwd(const void* qkv, long long ld_qkv, const void* out, long long ldo, const void* dout,
+                         long long ld_dout, const float* lse, int frames, int n, int heads, int q_col, int k_col,
+                         int v_col, float scale, void* dqkv, long long ld_dqkv, void* stream);
+
+/* Causal attention over the T frames of each of the n slots of each sample (attention.py:37-61 with
+ * causal=True, st_transformer.py:111), reading the (B,T,n,·) layout in place. */
+int hma_attn_temporal_fwd(const void* qkv, long long ld_qkv, int B, int T, int n, int heads, int q_col, int k_col,
+                          int v_col, float scale, void* out, long long ldo, void* stream);
+int hma_attn_temporal_bwd(const void* qkv, long long ld_qkv, const void* dout, long long ld_dout, int B, int T, int n,
+                          int heads, int q_col, int k_col, int v_col, float scale, void* dqkv, long long ld_dqkv,
+                          void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Row-wise stages (d_model = 256): fp32 residual stream -> bf16 operand
+ * ------------------------------------------------------------------------------------------- */
+
+/* mode 0: cast; 1: affine LayerNorm (st_transformer.py:50,75); 2: LayerNorm without affine then
+ * x*(1+scale)+shift with mod = [groups, 512] = shift|scale, group = row / rows_per_group
+ * (ModulateLayer, st_mask_git.py:66-76). stats (optional): fp32 [rows,2] = mean, rstd. */
+int hma_ln_fwd(const float* x, long long ldx, int rows, int mode, const float* gamma, const float* beta,
+               const float* mod, int rows_per_group, float eps, void* y, long long ldy, float* stats, void* stream);
+/* dx (fp32, accumulated in place) += LayerNorm backward of dy (bf16). mode 1 accumulates dgamma/dbeta,
+ * mode 2 accumulates dmod [groups, 512] = dshift|dscale. */
+int hma_ln_bwd(const void* dy, long long lddy, const float* x, long long ldx, const float* stats, int rows, int mode,
+               const float* gamma, const float* mod, int rows_per_group, float* dx, long long lddx, float* dgamma,
+               float* dbeta, float* dmod, void* stream);
+/* out[C] (fp32) += column sums of G (bias gradients). */
+int hma_colsum_bf16(const void* G, long long ld, int rows, int C, float* out, void* stream);
+int hma_colsum_f32(const float* G, long long ld, int rows, int C, float* out, void* stream);
+/* W fp32 [R,C] * alpha -> Wb bf16 [R,C] (optional) and Wt bf16 [C,R] (optional). */
+int hma_cast_transpose(const float* W, int R, int C, void* Wb, void* Wt, float alpha, void* stream);
+int hma_cast_bf16(const float* x, void* y, long long count, void* stream);
+
+/* Action stem pieces (st_mask_git.py:134-138 ActionStat, :90-102 BasicMLP). */
+int hma_action_prep(const float* a, int rows, int da, const float* mean, const float* stdv, int adim, void* y,
+                    int kpad, void* stream);
+int hma_ln_relu_fwd(const float* x, int rows, const float* gamma, const float* beta, float eps, void* y, float* stats,
+                    void* stream);
+int hma_ln_relu_bwd(const float* dy, const float* x, const float* stats, int rows, const float* gamma,
+                    const float* beta, float* dx, float* dgamma, float* dbeta, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Embedding (factorization_utils.py:31-54; st_mask_git.py:651-661,670-672)
+ * ------------------------------------------------------------------------------------------- */
+int hma_embed_fwd(const long long* ids, const float* E0, const float* E1, const float* mask_embed, const float* act,
+                  const float* pos, int pos_n, int B, int T, int S, int A, int vs, long long mask_id, float* x,
+                  void* stream);
+int hma_embed_bwd(const long long* ids, const float* dx, int pos_n, int B, int T, int S, int A, int vs,
+                  long long mask_id, float* dE0, float* dE1, float* dmask, float* dact, float* dpos, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Factorised cross-entropy (st_mask_git.py:603-630)
+ * ------------------------------------------------------------------------------------------- */
+/* sums[3] = sum(mask*loss), sum(mask*acc), sum(mask); loss_acc[2] = loss, acc; lse: [rows, nv]. */
+int hma_ce_fwd(const float* logits, long long ld, const long long* labels, const long long* input_ids, int B, int T,
+               int S, int nv, int vs, long long mask_id, float smoothing, float* lse, float* sums, float* loss_acc,
+               void* stream);
+/* dlogits (bf16 [rows, ldd]) = dloss/sum(mask) * mask * (softmax - smoothed one-hot); dloss is a device scalar. */
+int hma_ce_bwd(const float* logits, long long ld, const long long* labels, const long long* input_ids, int B, int T,
+               int S, int nv, int vs, long long mask_id, float smoothing, const float* lse, const float* sums,
+               const float* dloss, void* dlogits, long long ldd, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * MaskGIT sampling (st_mask_git.py:397-453)
+ * ------------------------------------------------------------------------------------------- */
+/* exp_noise: fp32 [nv][B*S, vs] Exp(1) draws, HIGH vocabulary half first (null = greedy). */
+int hma_sample_tokens(const float* logits, long long stride_b, long long ld, int B, int S, int nv, int vs,
+                      const float* exp_noise, long long* samples, float* conf, void* stream);
+/* n_mask < 0: last step (no ranking). frame: prompt[:, out_t] (token (b,s) at frame + b*stride_b + s). */
+int hma_rank_remask(const float* keys, unsigned char* unmasked, const long long* samples, long long* frame,
+                    long long stride_b, int B, int S, int n_mask, long long mask_id, long long* out_samples,
+                    void* stream);
+
+/* Test-only: single-CTA tcgen05 descriptor probe (see csrc/probe.cu; params is a HOST int[18]). */
+int hma_umma_probe(const void* A, long long lda, const void* B, long long ldb, const int* params, float* out,
+                   void* stream);
 
 #ifdef __cplusplus
 }
