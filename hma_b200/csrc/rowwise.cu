@@ -57,13 +57,15 @@ struct LnParams {
   __nv_bfloat16* y;
   long long ldy;
   float* stats;  // [rows, 2] mean, rstd (may be null)
+  int src_group, dst_group;  // output row r reads input row (r / dst_group) * src_group + r % dst_group
 };
 
 __global__ void __launch_bounds__(256) ln_fwd_kernel(const LnParams p) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row = blockIdx.x * 8 + warp;
   if (row >= p.rows) return;
-  RowLoad r = load_row_f32(p.x + (size_t)row * p.ldx, lane);
+  const size_t src_row = p.dst_group > 0 ? (size_t)(row / p.dst_group) * p.src_group + (row % p.dst_group) : (size_t)row;
+  RowLoad r = load_row_f32(p.x + src_row * p.ldx, lane);
   float out[8];
   if (p.mode == 0) {
 #pragma unroll
@@ -220,14 +222,17 @@ __global__ void __launch_bounds__(256) cast_transpose_kernel(const float* W, int
 
 extern "C" int hma_ln_fwd(const float* x, long long ldx, int rows, int mode, const float* gamma, const float* beta,
                           const float* mod, int rows_per_group, float eps, void* y, long long ldy, float* stats,
-                          void* stream_) {
+                          int src_group, int dst_group, void* stream_) {
   using namespace hma;
   if (rows == 0) return 0;
   HMA_REQUIRE(mode >= 0 && mode <= 2, "ln_fwd: bad mode %d", mode);
   HMA_REQUIRE(mode != 1 || (gamma && beta), "ln_fwd: affine mode needs gamma/beta");
   HMA_REQUIRE(mode != 2 || (mod && rows_per_group > 0), "ln_fwd: modulate mode needs shift/scale");
   HMA_REQUIRE(ldx % 4 == 0 && ldy % 4 == 0, "ln_fwd: rows must be 16-byte aligned");
-  LnParams p{x, ldx, rows, mode, gamma, beta, mod, rows_per_group, eps, static_cast<__nv_bfloat16*>(y), ldy, stats};
+  HMA_REQUIRE((src_group == 0) == (dst_group == 0) && dst_group <= (src_group ? src_group : dst_group),
+              "ln_fwd: bad row remap %d -> %d", src_group, dst_group);
+  LnParams p{x, ldx, rows, mode, gamma, beta, mod, rows_per_group, eps, static_cast<__nv_bfloat16*>(y), ldy, stats,
+             src_group, dst_group};
   ln_fwd_kernel<<<(rows + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream_)>>>(p);
   HMA_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -412,6 +417,36 @@ extern "C" int hma_colsum_f32(const float* G, long long ld, int rows, int C, flo
   using namespace hma;
   if (rows == 0) return 0;
   colsum_f32_kernel<<<(C + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream_)>>>(G, ld, rows, C, out);
+  HMA_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+namespace hma {
+// dst[(f*n + s), :] = s < S ? src[(f*S + s), :] : 0   (video-token rows back into the full token grid)
+__global__ void __launch_bounds__(256) rows_scatter_kernel(const float* src, float* dst, int frames, int S, int n) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * 8 + warp;
+  if (row >= (long long)frames * n) return;
+  const int s = (int)(row % n);
+  const long long f = row / n;
+  float4 a = make_float4(0, 0, 0, 0), b = a;
+  if (s < S) {
+    const float* sr = src + ((size_t)f * S + s) * kC;
+    a = *reinterpret_cast<const float4*>(sr + lane * 4);
+    b = *reinterpret_cast<const float4*>(sr + 128 + lane * 4);
+  }
+  float* d = dst + (size_t)row * kC;
+  *reinterpret_cast<float4*>(d + lane * 4) = a;
+  *reinterpret_cast<float4*>(d + 128 + lane * 4) = b;
+}
+}  // namespace hma
+
+extern "C" int hma_rows_scatter(const float* src, float* dst, int frames, int S, int n, void* stream_) {
+  using namespace hma;
+  const long long rows = (long long)frames * n;
+  if (rows == 0) return 0;
+  HMA_REQUIRE(S <= n, "rows_scatter: S=%d > n=%d", S, n);
+  rows_scatter_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream_)>>>(src, dst, frames, S, n);
   HMA_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -1,0 +1,352 @@
+"""Host-side schedule of the ST-MaskGIT hot path: which CUDA stage runs on which buffer, in what
+order, forward and backward. Mirrors, stage by stage, the reference call stack
+(SURVEY.md §3.2): STMaskGIT.compute_logits (st_mask_git.py:632-686) -> STTransformerDecoder /
+STBlock.forward (st_transformer.py:79-114,172-177) -> compute_video_loss_and_acc (:603-630), and
+the autograd transpose of all of it.
+
+Memory layout: the residual stream is fp32 [B*T*n, 256] in (b, t, s) token order for the whole
+network (n = S video tokens + A action tokens per frame); every GEMM operand is a bf16 matrix
+over the same token order, so neither the spatial nor the temporal stage ever transposes
+(the temporal kernel strides over frames in place). Weights are fp32 master parameters
+(reference state_dict layout); bf16 copies (and their transposes, for input gradients) are made
+per step.
+
+All math runs in libhma_b200.so; torch only allocates buffers.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from typing import Dict, List, Optional
+
+import torch
+
+from . import ops
+from .ops import EPI_BF16, EPI_DGELU, EPI_DSILU, EPI_GELU, EPI_RESID, EPI_SILU
+
+Tensor = torch.Tensor
+C = 256
+SMOOTHING = 0.01  # st_mask_git.py:620
+
+
+@dataclass
+class Dims:
+    B: int
+    T: int
+    S: int
+    A: int  # action tokens per frame actually concatenated (0 if none)
+    heads: int
+    nv: int
+    vs: int
+    mask_id: int
+    scale: float
+    num_layers: int
+    modulate: bool
+    readout_alpha: float
+
+    @property
+    def n(self) -> int:
+        return self.S + self.A
+
+    @property
+    def M(self) -> int:
+        return self.B * self.T
+
+    @property
+    def N(self) -> int:
+        return self.B * self.T * self.n
+
+
+def check_config(cfg) -> None:
+    """Reject, loudly, what the CUDA path does not implement (no silent fallback)."""
+    if cfg.d_model != 256 or cfg.num_heads != 8:
+        raise NotImplementedError(f"hma_b200 kernels are built for d_model=256, num_heads=8 (got {cfg.d_model}, {cfg.num_heads})")
+    if cfg.qk_norm:
+        raise NotImplementedError("qk_norm=True (per-head q/k LayerNorm, attention.py:32-35) is not implemented on the CUDA path yet")
+    if int(cfg.d_model * cfg.mlp_ratio) != 1024:
+        raise NotImplementedError("mlp_ratio must be 4.0")
+    if cfg.jointly_predict_actions or not cfg.jointly_predict_states:
+        raise NotImplementedError("jointly_predict_actions / jointly_predict_states=False are not implemented")
+    net = cfg.action_network
+    if "cross_attention" in net or ("mlp" in net and "modulate" not in net and net != "concat"):
+        raise NotImplementedError(f"action_network={net!r} is not implemented (supported: concat, modulate, concat+modulate)")
+    if cfg.num_factored_vocabs not in (1, 2) or cfg.factored_vocab_size % 256 != 0 or \
+            cfg.num_factored_vocabs * cfg.factored_vocab_size > 1024:
+        raise NotImplementedError("unsupported factorised vocabulary")
+
+
+class Weights:
+    """bf16 operand copies of the fp32 master parameters (plain for forward, transposed for dgrad)."""
+
+    def __init__(self):
+        self.plain: Dict[str, Tensor] = {}
+        self.trans: Dict[str, Tensor] = {}
+        self._versions: Dict[str, int] = {}
+
+    def prepare(self, params: Dict[str, Tensor], names: List[str], need_t: bool, force: bool) -> None:
+        for name in names:
+            w = params[name]
+            ver = w._version
+            have = name in self.plain and (not need_t or name in self.trans)
+            if have and not force and self._versions.get(name) == ver:
+                continue
+            wb, wt = ops.cast_transpose(w.detach(), True, need_t)
+            self.plain[name] = wb
+            if need_t:
+                self.trans[name] = wt
+            self._versions[name] = ver
+
+
+def layer_matrix_names(i: int, dom: Optional[str], modulate: bool) -> List[str]:
+    p = f"decoder.layers.{i}."
+    names = [p + "spatial_attn.qkv.weight", p + "spatial_attn.proj.weight", p + "temporal_attn.qkv.weight",
+             p + "temporal_attn.proj.weight", p + "mlp.fc1.weight", p + "mlp.fc2.weight"]
+    if modulate:
+        q = p + f"action_projectors.{dom}."
+        names += [q + "linear_out.weight", q + "adaLN_modulation.0.weight", q + "adaLN_modulation.2.weight"]
+    return names
+
+
+def stem_pad(da: int) -> int:
+    return (da + 127) // 128 * 128
+
+
+class Engine:
+    """One engine per model; owns the bf16 weight cache."""
+
+    def __init__(self, cfg):
+        check_config(cfg)
+        self.cfg = cfg
+        self.weights = Weights()
+        self._stem_w0: Dict[str, tuple] = {}
+
+    # ------------------------------------------------------------------------------------------
+    def dims(self, B: int, T: int, S: int, with_actions: bool) -> Dims:
+        cfg = self.cfg
+        net = cfg.action_network
+        A = cfg.action_token_size if (with_actions and "concat" in net) else 0
+        hd = cfg.d_model // cfg.num_heads
+        scale = 8.0 / hd if cfg.use_mup else hd ** -0.5  # attention.py:27
+        return Dims(B=B, T=T, S=S, A=A, heads=cfg.num_heads, nv=cfg.num_factored_vocabs, vs=cfg.factored_vocab_size,
+                    mask_id=cfg.image_vocab_size, scale=scale, num_layers=cfg.num_layers,
+                    modulate=with_actions and "modulate" in net,
+                    readout_alpha=(256.0 / cfg.d_model) if cfg.use_mup else 1.0)  # st_mask_git.py:755-760,788-789
+
+    def _prepare(self, p: Dict[str, Tensor], d: Dims, dom: Optional[str], training: bool) -> None:
+        names = ["out_x_proj.weight"]
+        for i in range(d.num_layers):
+            names += layer_matrix_names(i, dom, d.modulate)
+        if dom is not None:
+            names.append(f"action_mlp.{dom}.model.3.weight")
+        self.weights.prepare(p, names, need_t=training, force=training)
+        if dom is not None:
+            w0 = p[f"action_mlp.{dom}.model.0.weight"]
+            key = f"action_mlp.{dom}.model.0.weight"
+            cached = self._stem_w0.get(key)
+            if training or cached is None or cached[0] != w0._version:
+                self._stem_w0[key] = (w0._version, ops.action_prep(w0.detach().contiguous(), stem_pad(w0.shape[1])))
+
+    # ------------------------------------------------------------------------------------------
+    def forward(self, p: Dict[str, Tensor], ids: Tensor, actions: Optional[Tensor], dom: Optional[str], d: Dims,
+                training: bool, skip_normalization: bool = False):
+        """ids: i64 [B, T, S] (contiguous). Returns (logits fp32 [B*T*S, nv*vs], saved or None)."""
+        W = self.weights
+        self._prepare(p, d, dom if actions is not None else None, training)
+        Wp, sv = W.plain, {}
+        B, T, S, n, M, N = d.B, d.T, d.S, d.n, d.M, d.N
+        act = c_bf = None
+        if actions is not None:
+            # action stem: ActionStat + BasicMLP (st_mask_git.py:645-649)
+            a2d = actions.reshape(M, -1).to(torch.float32).contiguous()
+            da = a2d.shape[1]
+            mean = std = None
+            if not skip_normalization:
+                mean, std = p[f"action_preprocessor.{dom}.mean"], p[f"action_preprocessor.{dom}.std"]
+            q = f"action_mlp.{dom}.model."
+            a_prep = ops.action_prep(a2d, stem_pad(da), mean, std)
+            h1 = ops.gemm_nt(a_prep, self._stem_w0[q + "0.weight"][1], EPI_RESID, bias=p[q + "0.bias"])
+            h1n, st_stem = ops.ln_relu_fwd(h1, p[q + "1.weight"], p[q + "1.bias"])
+            act = ops.gemm_nt(h1n, Wp[q + "3.weight"], EPI_RESID, bias=p[q + "3.bias"])
+            c_bf = ops.ln_fwd(act, 0)
+            if training:
+                sv.update(a_prep=a_prep, h1=h1, h1n=h1n, st_stem=st_stem, c_bf=c_bf, da=da)
+        pos = p["pos_embed_TSC"]
+        pos_n = pos.shape[2]
+        E1 = p.get("token_embed.factored_embeds.1.weight") if d.nv == 2 else None
+        x = ops.embed_fwd(ids, p["token_embed.factored_embeds.0.weight"], E1, p["token_embed.mask_token_embed"],
+                          act if d.A else None, pos, pos_n, B, T, S, d.A, d.vs, d.mask_id)
+        layers = []
+        for i in range(d.num_layers):
+            lp = f"decoder.layers.{i}."
+            L = {}
+            # ---- spatial attention, pre-norm (st_transformer.py:85-86)
+            a1, st1 = ops.ln_fwd(x, 1, gamma=p[lp + "norm1.weight"], beta=p[lp + "norm1.bias"], eps=1e-5, want_stats=True)
+            qkv_s = ops.gemm_nt(a1, Wp[lp + "spatial_attn.qkv.weight"], EPI_BF16, bias=p.get(lp + "spatial_attn.qkv.bias"))
+            att_s, lse = ops.attn_spatial_fwd(qkv_s, M, n, d.heads, d.scale, want_lse=training)
+            x1 = ops.gemm_nt(att_s, Wp[lp + "spatial_attn.proj.weight"], EPI_RESID, bias=p.get(lp + "spatial_attn.proj.bias"),
+                             resid=x, out=None if training else x)
+            # ---- per-layer action conditioning (st_transformer.py:102-104; st_mask_git.py:66-76)
+            if d.modulate:
+                ap = lp + f"action_projectors.{dom}."
+                zmod = torch.empty(M, C, device=x.device, dtype=torch.bfloat16) if training else None
+                hmod = ops.gemm_nt(c_bf, Wp[ap + "adaLN_modulation.0.weight"], EPI_SILU, bias=p[ap + "adaLN_modulation.0.bias"], out2=zmod)
+                mod = ops.gemm_nt(hmod, Wp[ap + "adaLN_modulation.2.weight"], EPI_RESID, bias=p[ap + "adaLN_modulation.2.bias"])
+                am, stm = ops.ln_fwd(x1, 2, mod=mod, rows_per_group=n, eps=1e-6, want_stats=True)
+                x2 = ops.gemm_nt(am, Wp[ap + "linear_out.weight"], EPI_RESID, bias=p[ap + "linear_out.bias"], resid=x1,
+                                 out=None if training else x1)
+                if training:
+                    L.update(zmod=zmod, hmod=hmod, mod=mod, am=am, stm=stm)
+            else:
+                x2 = x1
+            # ---- causal temporal attention, no pre-norm (st_transformer.py:111)
+            at = ops.ln_fwd(x2, 0)
+            qkv_t = ops.gemm_nt(at, Wp[lp + "temporal_attn.qkv.weight"], EPI_BF16, bias=p.get(lp + "temporal_attn.qkv.bias"))
+            att_t = ops.attn_temporal_fwd(qkv_t, B, T, n, d.heads, d.scale)
+            x3 = ops.gemm_nt(att_t, Wp[lp + "temporal_attn.proj.weight"], EPI_RESID, bias=p.get(lp + "temporal_attn.proj.bias"),
+                             resid=x2, out=None if training else x2)
+            # ---- MLP, pre-norm, erf-GELU (st_transformer.py:24-27,112)
+            a2, st2 = ops.ln_fwd(x3, 1, gamma=p[lp + "norm2.weight"], beta=p[lp + "norm2.bias"], eps=1e-5, want_stats=True)
+            z = torch.empty(N, 1024, device=x.device, dtype=torch.bfloat16) if training else None
+            h = ops.gemm_nt(a2, Wp[lp + "mlp.fc1.weight"], EPI_GELU, bias=p.get(lp + "mlp.fc1.bias"), out2=z)
+            x4 = ops.gemm_nt(h, Wp[lp + "mlp.fc2.weight"], EPI_RESID, bias=p.get(lp + "mlp.fc2.bias"), resid=x3,
+                             out=None if training else x3)
+            if training:
+                L.update(x0=x, a1=a1, st1=st1, qkv_s=qkv_s, att_s=att_s, lse=lse, x1=x1, at=at, qkv_t=qkv_t, att_t=att_t,
+                         x3=x3, a2=a2, st2=st2, z=z, h=h)
+                layers.append(L)
+            x = x4
+        # ---- head on the video tokens only (st_mask_git.py:681-683)
+        ah = ops.ln_fwd(x, 0, rows=M * S, src_group=n, dst_group=S) if d.A else ops.ln_fwd(x, 0)
+        logits = ops.gemm_nt(ah, Wp["out_x_proj.weight"], EPI_RESID, bias=p["out_x_proj.bias"], alpha=d.readout_alpha)
+        if training:
+            sv.update(layers=layers, ah=ah, ids=ids, dom=dom, dims=d, pos_n=pos_n, has_actions=actions is not None)
+        return logits, (sv if training else None)
+
+    # ------------------------------------------------------------------------------------------
+    def active_param_names(self, p: Dict[str, Tensor], d: Dims, dom: Optional[str], has_actions: bool) -> List[str]:
+        names = ["pos_embed_TSC", "token_embed.mask_token_embed", "token_embed.factored_embeds.0.weight"]
+        if d.nv == 2:
+            names.append("token_embed.factored_embeds.1.weight")
+        for i in range(d.num_layers):
+            lp = f"decoder.layers.{i}."
+            for k in ("norm1.weight", "norm1.bias", "spatial_attn.qkv.weight", "spatial_attn.qkv.bias",
+                      "spatial_attn.proj.weight", "spatial_attn.proj.bias", "temporal_attn.qkv.weight",
+                      "temporal_attn.qkv.bias", "temporal_attn.proj.weight", "temporal_attn.proj.bias", "norm2.weight",
+                      "norm2.bias", "mlp.fc1.weight", "mlp.fc1.bias", "mlp.fc2.weight", "mlp.fc2.bias"):
+                if lp + k in p:
+                    names.append(lp + k)
+            if d.modulate:
+                ap = lp + f"action_projectors.{dom}."
+                names += [ap + "linear_out.weight", ap + "linear_out.bias", ap + "adaLN_modulation.0.weight",
+                          ap + "adaLN_modulation.0.bias", ap + "adaLN_modulation.2.weight", ap + "adaLN_modulation.2.bias"]
+        names += ["out_x_proj.weight", "out_x_proj.bias"]
+        if has_actions and (d.A or d.modulate):
+            q = f"action_mlp.{dom}.model."
+            names += [q + k for k in ("0.weight", "0.bias", "1.weight", "1.bias", "3.weight", "3.bias")]
+        return names
+
+    def backward(self, p: Dict[str, Tensor], sv: dict, dlogits: Tensor) -> Dict[str, Tensor]:
+        """dlogits: bf16 [B*T*S, nv*vs]. Returns fp32 gradients for every active parameter."""
+        d: Dims = sv["dims"]
+        dom = sv["dom"]
+        Wt = self.weights.trans
+        B, T, S, n, M, N = d.B, d.T, d.S, d.n, d.M, d.N
+        dev = dlogits.device
+        names = self.active_param_names(p, d, dom, sv["has_actions"])
+        sizes = [p[k].numel() for k in names]
+        padded = [(s + 3) // 4 * 4 for s in sizes]  # keep every gradient 16-byte aligned
+        flat = torch.zeros(sum(padded), device=dev, dtype=torch.float32)
+        g: Dict[str, Tensor] = {}
+        off = 0
+        for k, s, ps in zip(names, sizes, padded):
+            g[k] = flat[off:off + s].view(p[k].shape)
+            off += ps
+
+        def g2(name):  # gradient viewed as a matrix / vector
+            return g[name]
+
+        # ---- head
+        assert d.readout_alpha == 1.0, "readout scaling != 1 is not implemented for training"
+        ops.gemm_wgrad(dlogits, sv["ah"], g2("out_x_proj.weight"))
+        ops.colsum_bf16(dlogits, g2("out_x_proj.bias"))
+        dxh = ops.gemm_nt(dlogits, Wt["out_x_proj.weight"], EPI_RESID)
+        dx = ops.rows_scatter(dxh, M, S, n) if d.A else dxh
+        dact = torch.zeros(M, C, device=dev, dtype=torch.float32) if sv["has_actions"] else None
+
+        for i in reversed(range(d.num_layers)):
+            L = sv["layers"][i]
+            lp = f"decoder.layers.{i}."
+            # ---- MLP
+            dy = ops.cast_bf16(dx)
+            ops.gemm_wgrad(dy, L["h"], g2(lp + "mlp.fc2.weight"))
+            if lp + "mlp.fc2.bias" in g:
+                ops.colsum_bf16(dy, g2(lp + "mlp.fc2.bias"))
+            dz = ops.gemm_nt(dy, Wt[lp + "mlp.fc2.weight"], EPI_DGELU, aux=L["z"])
+            ops.gemm_wgrad(dz, L["a2"], g2(lp + "mlp.fc1.weight"))
+            if lp + "mlp.fc1.bias" in g:
+                ops.colsum_bf16(dz, g2(lp + "mlp.fc1.bias"))
+            da2 = ops.gemm_nt(dz, Wt[lp + "mlp.fc1.weight"], EPI_BF16)
+            ops.ln_bwd(da2, L["x3"], L["st2"], 1, dx, gamma=p[lp + "norm2.weight"], dgamma=g2(lp + "norm2.weight"),
+                       dbeta=g2(lp + "norm2.bias"))
+            # ---- temporal attention
+            dy = ops.cast_bf16(dx)
+            ops.gemm_wgrad(dy, L["att_t"], g2(lp + "temporal_attn.proj.weight"))
+            if lp + "temporal_attn.proj.bias" in g:
+                ops.colsum_bf16(dy, g2(lp + "temporal_attn.proj.bias"))
+            datt = ops.gemm_nt(dy, Wt[lp + "temporal_attn.proj.weight"], EPI_BF16)
+            dqkv = ops.attn_temporal_bwd(L["qkv_t"], datt, B, T, n, d.heads, d.scale)
+            ops.gemm_wgrad(dqkv, L["at"], g2(lp + "temporal_attn.qkv.weight"))
+            if lp + "temporal_attn.qkv.bias" in g:
+                ops.colsum_bf16(dqkv, g2(lp + "temporal_attn.qkv.bias"))
+            ops.gemm_nt(dqkv, Wt[lp + "temporal_attn.qkv.weight"], EPI_RESID, resid=dx, out=dx)
+            # ---- modulate
+            if d.modulate:
+                ap = lp + f"action_projectors.{dom}."
+                dy = ops.cast_bf16(dx)
+                ops.gemm_wgrad(dy, L["am"], g2(ap + "linear_out.weight"))
+                ops.colsum_bf16(dy, g2(ap + "linear_out.bias"))
+                dam = ops.gemm_nt(dy, Wt[ap + "linear_out.weight"], EPI_BF16)
+                dmod = torch.zeros(M, 2 * C, device=dev, dtype=torch.float32)
+                ops.ln_bwd(dam, L["x1"], L["stm"], 2, dx, mod=L["mod"], rows_per_group=n, dmod=dmod)
+                # adaLN_modulation backward (Linear -> SiLU -> Linear on the [B*T, 256] action embedding)
+                dmod_bf = ops.cast_bf16(dmod)
+                ops.gemm_wgrad(dmod_bf, L["hmod"], g2(ap + "adaLN_modulation.2.weight"))
+                ops.colsum_f32(dmod, g2(ap + "adaLN_modulation.2.bias"))
+                dzm = ops.gemm_nt(dmod_bf, Wt[ap + "adaLN_modulation.2.weight"], EPI_DSILU, aux=L["zmod"])
+                ops.gemm_wgrad(dzm, sv["c_bf"], g2(ap + "adaLN_modulation.0.weight"))
+                ops.colsum_bf16(dzm, g2(ap + "adaLN_modulation.0.bias"))
+                ops.gemm_nt(dzm, Wt[ap + "adaLN_modulation.0.weight"], EPI_RESID, resid=dact, out=dact)
+            # ---- spatial attention
+            dy = ops.cast_bf16(dx)
+            ops.gemm_wgrad(dy, L["att_s"], g2(lp + "spatial_attn.proj.weight"))
+            if lp + "spatial_attn.proj.bias" in g:
+                ops.colsum_bf16(dy, g2(lp + "spatial_attn.proj.bias"))
+            datt = ops.gemm_nt(dy, Wt[lp + "spatial_attn.proj.weight"], EPI_BF16)
+            dqkv = ops.attn_spatial_bwd(L["qkv_s"], L["att_s"], datt, L["lse"], M, n, d.heads, d.scale)
+            ops.gemm_wgrad(dqkv, L["a1"], g2(lp + "spatial_attn.qkv.weight"))
+            if lp + "spatial_attn.qkv.bias" in g:
+                ops.colsum_bf16(dqkv, g2(lp + "spatial_attn.qkv.bias"))
+            da1 = ops.gemm_nt(dqkv, Wt[lp + "spatial_attn.qkv.weight"], EPI_BF16)
+            ops.ln_bwd(da1, L["x0"], L["st1"], 1, dx, gamma=p[lp + "norm1.weight"], dgamma=g2(lp + "norm1.weight"),
+                       dbeta=g2(lp + "norm1.bias"))
+            sv["layers"][i] = None  # release this layer's activations
+
+        # ---- embedding / positional / action-token gradients
+        ops.embed_bwd(sv["ids"], dx, sv["pos_n"], B, T, S, d.A, d.vs, d.mask_id,
+                      g["token_embed.factored_embeds.0.weight"], g.get("token_embed.factored_embeds.1.weight"),
+                      g["token_embed.mask_token_embed"], dact if d.A else None, g["pos_embed_TSC"])
+        # ---- action stem backward
+        if sv["has_actions"] and (d.A or d.modulate):
+            q = f"action_mlp.{dom}.model."
+            dact_bf = ops.cast_bf16(dact)
+            ops.gemm_wgrad(dact_bf, sv["h1n"], g2(q + "3.weight"))
+            ops.colsum_f32(dact, g2(q + "3.bias"))
+            dh1n = ops.gemm_nt(dact_bf, Wt[q + "3.weight"], EPI_RESID)
+            dh1 = ops.ln_relu_bwd(dh1n, sv["h1"], sv["st_stem"], p[q + "1.weight"], p[q + "1.bias"], g2(q + "1.weight"),
+                                  g2(q + "1.bias"))
+            ops.colsum_f32(dh1, g2(q + "0.bias"))
+            kpad = sv["a_prep"].shape[1]
+            dw0 = torch.zeros(C, kpad, device=dev, dtype=torch.float32)
+            ops.gemm_wgrad(ops.cast_bf16(dh1), sv["a_prep"], dw0)
+            g[q + "0.weight"].copy_(dw0[:, : sv["da"]])
+        return g

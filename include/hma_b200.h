@@ -88,8 +88,13 @@ int hma_attn_temporal_bwd(const void* qkv, long long ld_qkv, const void* dout, l
 /* mode 0: cast; 1: affine LayerNorm (st_transformer.py:50,75); 2: LayerNorm without affine then
  * x*(1+scale)+shift with mod = [groups, 512] = shift|scale, group = row / rows_per_group
  * (ModulateLayer, st_mask_git.py:66-76). stats (optional): fp32 [rows,2] = mean, rstd. */
+/* Row remap (src_group, dst_group != 0): output row r reads input row (r / dst_group) * src_group + r % dst_group
+ * (used to drop the action tokens before the head, st_mask_git.py:681). */
 int hma_ln_fwd(const float* x, long long ldx, int rows, int mode, const float* gamma, const float* beta,
-               const float* mod, int rows_per_group, float eps, void* y, long long ldy, float* stats, void* stream);
+               const float* mod, int rows_per_group, float eps, void* y, long long ldy, float* stats, int src_group,
+               int dst_group, void* stream);
+/* dst[(f*n + s), :] = s < S ? src[(f*S + s), :] : 0 — fp32 rows of 256 (inverse of the remap above). */
+int hma_rows_scatter(const float* src, float* dst, int frames, int S, int n, void* stream);
 /* dx (fp32, accumulated in place) += LayerNorm backward of dy (bf16). mode 1 accumulates dgamma/dbeta,
  * mode 2 accumulates dmod [groups, 512] = dshift|dscale. */
 int hma_ln_bwd(const void* dy, long long lddy, const float* x, long long ldx, const float* stats, int rows, int mode,

@@ -76,7 +76,7 @@ def test_ln_fwd_bwd(mode):
     stats = torch.zeros(rows, 2, device="cuda")
     eps = 1e-5 if mode == 1 else 1e-6
     _lib.call("hma_ln_fwd", x.data_ptr(), C, rows, mode, gamma.data_ptr(), beta.data_ptr(), mod.data_ptr(), rpg, eps,
-              y.data_ptr(), C, stats.data_ptr(), S_())
+              y.data_ptr(), C, stats.data_ptr(), 0, 0, S_())
     torch.cuda.synchronize()
     xr = x.clone().requires_grad_(True)
     gr, br, mr = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True), mod.clone().requires_grad_(True)

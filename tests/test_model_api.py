@@ -1,0 +1,63 @@
+"""CPU-side checks of the drop-in boundary: state_dict layout, config round trip, C-ABI exports."""
+import ctypes
+import re
+from pathlib import Path
+
+import pytest
+import torch
+
+from tests._util import build_cuda_model, golden
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def test_state_dict_layout_matches_reference_layout():
+    """oracle.make_state_dict is proven to load strictly into the reference (oracle/make_golden.py);
+    the CUDA model must expose exactly the same keys and shapes."""
+    rec, cfg, sd = golden()
+    model = build_cuda_model(rec, sd, device="cpu")
+    mine = model.state_dict()
+    assert set(mine) == set(sd)
+    for k, v in sd.items():
+        assert tuple(mine[k].shape) == tuple(v.shape), k
+        assert torch.equal(mine[k], v), k
+
+
+def test_config_roundtrip(tmp_path):
+    from hma_b200 import GenieConfig
+
+    c = GenieConfig(num_layers=32, num_heads=8, d_model=256, num_factored_vocabs=2, action_network="concat+modulate")
+    assert c.factored_vocab_size == 512
+    c.save_pretrained(tmp_path / "c.json")
+    c2 = GenieConfig.from_pretrained(tmp_path / "c.json")
+    assert vars(c) == vars(c2)
+
+
+def test_unsupported_configs_fail_loudly():
+    from hma_b200 import GenieConfig, STMaskGIT
+
+    with pytest.raises(NotImplementedError):
+        STMaskGIT(GenieConfig(num_layers=1, num_heads=8, d_model=256, num_factored_vocabs=2, qk_norm=True))
+    with pytest.raises(NotImplementedError):
+        STMaskGIT(GenieConfig(num_layers=1, num_heads=8, d_model=512, num_factored_vocabs=2, qk_norm=False))
+
+
+def test_no_cpu_fallback():
+    rec, cfg, sd = golden()
+    model = build_cuda_model(rec, sd, device="cpu")
+    r = rec[rec["domains"][0]]
+    with pytest.raises(RuntimeError, match="CUDA device only"):
+        model(r["input_ids"], r["labels"], action_ids=r["actions"], domain=[rec["domains"][0]] * 2)
+
+
+def test_c_abi_exports_every_declared_symbol():
+    from hma_b200 import build
+
+    lib_path = build.build()
+    lib = ctypes.CDLL(str(lib_path))
+    header = (ROOT / "include" / "hma_b200.h").read_text()
+    names = sorted(set(re.findall(r"\b(hma_[a-z0-9_]+)\s*\(", header)))
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/hma_b200.h but not exported"
+    assert lib.hma_abi_version() == 1

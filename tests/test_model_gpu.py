@@ -1,0 +1,168 @@
+"""End-to-end parity of the CUDA model (through the public nn.Module API and the C ABI) against
+(a) fixtures produced by the real reference and (b) the CPU oracle on the same seeded inputs.
+
+Tolerances (stated, bf16 tensor-core operands with fp32 accumulation and an fp32 residual stream):
+  loss            |d| <= 1e-2 * |ref|          (north_star: "<= 1e-2 relative")
+  logits          max|d| <= 1e-2 * max|ref|  and  rms(d) <= 1e-2 * rms(ref)
+  gradients       per-tensor norm within 5 % (measured: 0.25 %), sampled entries within 15 % of the tensor's max
+                  (measured: <= 2 % except two action-stem biases at 11 %, where a ReLU gate flips on one of the
+                  8 stem rows of this tiny batch)
+  tokens / masks  bit-exact given identical logits and noise
+"""
+import math
+
+import pytest
+import torch
+
+from oracle import stmaskgit_oracle as O
+from tests._util import build_cuda_model, golden
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def setup():
+    rec, cfg, sd = golden()
+    model = build_cuda_model(rec, sd)
+    return rec, cfg, sd, model
+
+
+def test_forward_loss_logits_vs_reference_fixture(setup):
+    rec, cfg, sd, model = setup
+    for dom in rec["domains"]:
+        r = rec[dom]
+        with torch.no_grad():
+            out = model(r["input_ids"].cuda(), r["labels"].cuda(), action_ids=r["actions"].cuda(), domain=[dom, dom])
+        loss, ref = out.loss.item(), r["loss"].item()
+        assert abs(loss - ref) <= 1e-2 * abs(ref), (loss, ref)
+        assert abs(out.acc.item() - r["acc"].item()) <= 2e-3
+        lg = out.logits.float().cpu()
+        assert lg.shape == (2, 1024, cfg.T, 16, 16)
+        d = lg[:, :, :, ::4, ::4] - r["logits_sub"]
+        assert d.abs().max() <= 1e-2 * r["logits_sub"].abs().max(), d.abs().max()
+        assert d.pow(2).mean().sqrt() <= 1e-2 * r["logits_sub"].pow(2).mean().sqrt()
+
+
+def test_backward_vs_reference_fixture(setup):
+    rec, cfg, sd, model = setup
+    dom = rec["domains"][0]
+    r = rec[dom]
+    model.zero_grad(set_to_none=True)
+    out = model(r["input_ids"].cuda(), r["labels"].cuda(), action_ids=r["actions"].cuda(), domain=[dom, dom])
+    out.loss.backward()
+    torch.cuda.synchronize()
+    named = dict(model.named_parameters())
+    worst = []
+    for k, gn in r["grad_norms"].items():
+        g = named[k].grad
+        assert g is not None, f"no gradient for {k}"
+        rel = abs(g.norm().item() - gn) / max(gn, 1e-12)
+        sl = g.reshape(-1)[:: max(1, g.numel() // 64)][:64].float().cpu()
+        ref_sl = r["grad_slices"][k]
+        e = (sl - ref_sl).abs().max().item() / max(ref_sl.abs().max().item(), gn / math.sqrt(g.numel()), 1e-12)
+        worst.append((rel, e, k))
+    # parameters the reference leaves without a gradient (other domain, unused heads) stay untouched
+    for k, p in named.items():
+        if k not in r["grad_norms"]:
+            assert p.grad is None or p.grad.abs().max().item() == 0.0, k
+    for rel, e, k in sorted(worst, reverse=True)[:6]:
+        print(f"grad-norm rel err {rel:.4f} entry err {e:.4f} {k}")
+    for rel, e, k in sorted(worst, key=lambda t: -t[1])[:6]:
+        print(f"entry err {e:.4f} grad-norm rel err {rel:.4f} {k}")
+    for rel, e, k in worst:
+        assert rel < 5e-2, (k, rel)
+        assert e < 1.5e-1, (k, e)
+
+
+def test_forward_matches_oracle_other_shapes(setup):
+    """Same weights, different shapes: no actions (n = 256), and T shorter than config.T for decode."""
+    rec, cfg, sd, model = setup
+    g = torch.Generator().manual_seed(11)
+    for T, with_actions in ((3, True), (4, False)):
+        x = torch.randint(0, 262144, (1, T, 16, 16), generator=g)
+        x[:, -1] = cfg.mask_token_id
+        a = torch.randn(1, T, rec["d_actions"][1], generator=g) if with_actions else None
+        dom = [rec["domains"][1]] if with_actions else None
+        with torch.no_grad():
+            ref = O.compute_logits(x, a, dom, sd, cfg)
+            got, _ = model.compute_logits(x.cuda(), action_ids=a.cuda() if a is not None else None, domain=dom)
+        d = got.float().cpu() - ref
+        assert d.abs().max() <= 1e-2 * ref.abs().max()
+
+
+def test_maskgit_decode_bit_exact_given_identical_logits_and_noise(setup):
+    """Drive the sampling kernels with the ORACLE's fp32 logits and injected noise: tokens, the unmask
+    bookkeeping and the in-place prompt update must match the oracle exactly."""
+    from hma_b200 import ops
+    rec, cfg, sd, model = setup
+    dom = rec["domains"][0]
+    r = rec[dom]
+    B, T, S, nv, vs = 2, cfg.T, 256, 2, 512
+    steps = 3
+    for temperature, mode in ((0.0, "greedy"), (1.0, "random"), (0.0, "random")):
+        g = torch.Generator().manual_seed(5)
+        noise = {"exp": [[torch.empty(B * S, vs).exponential_(1, generator=g) for _ in range(nv)] for _ in range(steps)],
+                 "rand": [torch.rand(B, 16, 16, generator=g) for _ in range(steps)]}
+        prompt = r["labels"].reshape(B, T, 16, 16).clone()
+        prompt[:, -1] = cfg.mask_token_id
+        # record the oracle's per-step logits by re-running it step by step
+        logits_steps = []
+        orig = O.compute_logits
+
+        def spy(*a, **k):
+            out = orig(*a, **k)
+            logits_steps.append(out)
+            return out
+
+        O.compute_logits = spy
+        try:
+            ref_prompt = prompt.clone()
+            ref_s, _ = O.maskgit_generate(ref_prompt, T - 1, sd, cfg, steps, temperature, mode, r["actions"], [dom, dom],
+                                          noise=noise)
+        finally:
+            O.compute_logits = orig
+        cu_prompt = prompt.clone().cuda()
+        frame = cu_prompt[:, T - 1].view(B, S)
+        unmasked = torch.zeros(B, S, dtype=torch.uint8, device="cuda")
+        out = None
+        for step in range(steps):
+            lg = logits_steps[step].permute(0, 2, 3, 4, 1).reshape(B, T, S, nv * vs)[:, T - 1].contiguous().cuda()
+            nz = torch.stack(noise["exp"][step]).cuda() if temperature > 1e-8 else None
+            new, conf = ops.sample_tokens(lg, nv, vs, nz)
+            if step != steps - 1:
+                n = math.ceil(O.cosine_schedule((step + 1) / steps) * S)
+                keys = conf if mode == "greedy" else noise["rand"][step].reshape(B, S).cuda()
+                out = ops.rank_remask(keys, unmasked, new, frame, n, cfg.mask_token_id)
+            else:
+                out = ops.rank_remask(None, unmasked, new, frame, -1, cfg.mask_token_id)
+        assert torch.equal(out.cpu().view(B, 16, 16), ref_s), (temperature, mode)
+        assert torch.equal(cu_prompt.cpu(), ref_prompt)
+
+
+def test_maskgit_generate_api(setup):
+    rec, cfg, sd, model = setup
+    dom = rec["domains"][0]
+    r = rec[dom]
+    B, T = 2, cfg.T
+    prompt = r["labels"].reshape(B, T, 16, 16).clone().cuda()
+    prompt[:, -1] = cfg.mask_token_id
+    torch.manual_seed(0)
+    s, fl, _ = model.maskgit_generate(prompt, T - 1, maskgit_steps=4, temperature=1.0, action_ids=r["actions"].cuda(),
+                                      domain=[dom, dom])
+    assert s.shape == (B, 16, 16) and fl.shape == (B, 512, 2, 16, 16)
+    assert (s != cfg.mask_token_id).all() and torch.equal(prompt[:, -1], s)  # in-place update, nothing left masked
+    # greedy single step: tokens agree with the reference's greedy decode wherever logits are not near-tied
+    prompt = r["labels"].reshape(B, T, 16, 16).clone().cuda()
+    prompt[:, -1] = cfg.mask_token_id
+    s1, fl1, _ = model.maskgit_generate(prompt, T - 1, maskgit_steps=1, temperature=0.0, action_ids=r["actions"].cuda(),
+                                        domain=[dom, dom])
+    agree = (s1.cpu() == r["gen_greedy1_samples"]).float().mean().item()
+    assert agree > 0.9, agree
+    d = fl1.float().cpu()[:, :, :, ::4, ::4] - r["gen_greedy1_logits_sub"]
+    assert d.abs().max() <= 1e-2 * r["gen_greedy1_logits_sub"].abs().max()
+    with pytest.raises(AssertionError):
+        model.maskgit_generate(r["labels"].reshape(B, T, 16, 16).cuda(), T - 1)  # future frame not masked
+    toks = model.generate(r["labels"][:, : 2 * 256].cuda(), None, 2 * 256, maskgit_steps=2, temperature=0.0,
+                          action_ids=r["actions"].cuda(), domain=[dom, dom], h=[16], w=[16])
+    assert toks.shape == (B, 4 * 256) and (toks != cfg.mask_token_id).all()
+    assert torch.equal(toks[:, : 2 * 256].cpu(), r["labels"][:, : 2 * 256])
