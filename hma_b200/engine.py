@@ -223,7 +223,8 @@ class Engine:
         return logits, (sv if training else None)
 
     # ------------------------------------------------------------------------------------------
-    def active_param_names(self, p: Dict[str, Tensor], d: Dims, dom: Optional[str], has_actions: bool) -> List[str]:
+    def shared_param_names(self, p: Dict[str, Tensor], d: Dims) -> List[str]:
+        """Parameters every batch touches (embeddings, trunk, head), in gradient-buffer order."""
         names = ["pos_embed_TSC", "token_embed.mask_token_embed", "token_embed.factored_embeds.0.weight"]
         if d.nv == 2:
             names.append("token_embed.factored_embeds.1.weight")
@@ -235,18 +236,33 @@ class Engine:
                       "norm2.bias", "mlp.fc1.weight", "mlp.fc1.bias", "mlp.fc2.weight", "mlp.fc2.bias"):
                 if lp + k in p:
                     names.append(lp + k)
-            if d.modulate:
-                ap = lp + f"action_projectors.{dom}."
-                names += [ap + "linear_out.weight", ap + "linear_out.bias", ap + "adaLN_modulation.0.weight",
-                          ap + "adaLN_modulation.0.bias", ap + "adaLN_modulation.2.weight", ap + "adaLN_modulation.2.bias"]
         names += ["out_x_proj.weight", "out_x_proj.bias"]
-        if has_actions and (d.A or d.modulate):
-            q = f"action_mlp.{dom}.model."
-            names += [q + k for k in ("0.weight", "0.bias", "1.weight", "1.bias", "3.weight", "3.bias")]
         return names
 
-    def backward(self, p: Dict[str, Tensor], sv: dict, dlogits: Tensor) -> Dict[str, Tensor]:
-        """dlogits: bf16 [B*T*S, nv*vs]. Returns fp32 gradients for every active parameter."""
+    def domain_param_names(self, p: Dict[str, Tensor], d: Dims, dom: Optional[str], has_actions: bool) -> List[str]:
+        """Parameters only batches of domain `dom` touch (action stem + per-layer ModulateLayers)."""
+        names: List[str] = []
+        if not has_actions or dom is None or not (d.A or d.modulate):
+            return names
+        q = f"action_mlp.{dom}.model."
+        names += [q + k for k in ("0.weight", "0.bias", "1.weight", "1.bias", "3.weight", "3.bias")]
+        if d.modulate:
+            for i in range(d.num_layers):
+                ap = f"decoder.layers.{i}.action_projectors.{dom}."
+                names += [ap + "linear_out.weight", ap + "linear_out.bias", ap + "adaLN_modulation.0.weight",
+                          ap + "adaLN_modulation.0.bias", ap + "adaLN_modulation.2.weight", ap + "adaLN_modulation.2.bias"]
+        return names
+
+    def active_param_names(self, p: Dict[str, Tensor], d: Dims, dom: Optional[str], has_actions: bool) -> List[str]:
+        return self.shared_param_names(p, d) + self.domain_param_names(p, d, dom, has_actions)
+
+    @staticmethod
+    def padded_numel(t: Tensor) -> int:
+        return (t.numel() + 3) // 4 * 4  # keep every tensor 16-byte aligned inside flat buffers
+
+    def backward(self, p: Dict[str, Tensor], sv: dict, dlogits: Tensor, flat: Optional[Tensor] = None) -> Dict[str, Tensor]:
+        """dlogits: bf16 [B*T*S, nv*vs]. Returns fp32 gradients for every active parameter, as views of one
+        flat buffer laid out [shared | domain] (`flat`, if given, must be zeroed and large enough)."""
         d: Dims = sv["dims"]
         dom = sv["dom"]
         Wt = self.weights.trans
@@ -254,8 +270,10 @@ class Engine:
         dev = dlogits.device
         names = self.active_param_names(p, d, dom, sv["has_actions"])
         sizes = [p[k].numel() for k in names]
-        padded = [(s + 3) // 4 * 4 for s in sizes]  # keep every gradient 16-byte aligned
-        flat = torch.zeros(sum(padded), device=dev, dtype=torch.float32)
+        padded = [self.padded_numel(p[k]) for k in names]
+        if flat is None:
+            flat = torch.zeros(sum(padded), device=dev, dtype=torch.float32)
+        assert flat.numel() >= sum(padded)
         g: Dict[str, Tensor] = {}
         off = 0
         for k, s, ps in zip(names, sizes, padded):

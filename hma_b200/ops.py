@@ -19,6 +19,45 @@ def _s() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
+class Profiler:
+    """CUDA-event timing of individual stage launches on the launching stream (bench.py / tools)."""
+
+    def __init__(self, kinds=None):
+        self.kinds = kinds  # None = every stage; else a set of kind prefixes
+        self.records = {}
+
+    def want(self, kind: str) -> bool:
+        return self.kinds is None or any(kind.startswith(k) for k in self.kinds)
+
+    def summary(self):
+        torch.cuda.synchronize()
+        out = {}
+        for kind, recs in self.records.items():
+            ms = [a.elapsed_time(b) for a, b, _ in recs]
+            out[kind] = {"launches": len(ms), "total_ms": sum(ms), "work": sum(w for _, _, w in recs)}
+        return out
+
+
+PROFILER: Optional[Profiler] = None
+LAUNCHES = 0
+
+
+def _call(kind: str, work: float, name: str, *args) -> None:
+    """One C-ABI launch; `work` = algorithmic FLOPs (tensor kernels) or bytes (HBM-bound kernels)."""
+    global LAUNCHES
+    LAUNCHES += 1
+    prof = PROFILER
+    if prof is not None and prof.want(kind):
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        _lib.call(name, *args)
+        e1.record()
+        prof.records.setdefault(kind, []).append((e0, e1, work))
+    else:
+        _lib.call(name, *args)
+
+
 def _p(t: Optional[torch.Tensor]):
     return None if t is None else t.data_ptr()
 
@@ -32,7 +71,7 @@ def gemm_nt(A: torch.Tensor, B: torch.Tensor, epi: int, *, out: Optional[torch.T
     assert B.shape[1] == K and A.dtype == BF16 and B.dtype == BF16 and A.stride(1) == 1 and B.stride(1) == 1
     if out is None:
         out = torch.empty(M, N, device=A.device, dtype=F32 if epi == EPI_RESID else BF16)
-    _lib.call("hma_gemm_nt", A.data_ptr(), A.stride(0), B.data_ptr(), B.stride(0), M, N, K, epi, out.data_ptr(),
+    _call(f"gemm_nt[N={N},K={K},epi={epi}]", 2.0 * M * N * K, "hma_gemm_nt", A.data_ptr(), A.stride(0), B.data_ptr(), B.stride(0), M, N, K, epi, out.data_ptr(),
               out.stride(0), _p(out2), out2.stride(0) if out2 is not None else 0, _p(bias), _p(resid),
               resid.stride(0) if resid is not None else 0, _p(aux), aux.stride(0) if aux is not None else 0,
               float(alpha), _s())
@@ -44,7 +83,7 @@ def gemm_wgrad(G: torch.Tensor, X: torch.Tensor, dW: torch.Tensor) -> None:
     tokens, Mw = G.shape
     Nw = X.shape[1]
     assert X.shape[0] == tokens and dW.shape == (Mw, Nw) and dW.dtype == F32 and dW.stride(1) == 1
-    _lib.call("hma_gemm_wgrad", G.data_ptr(), G.stride(0), X.data_ptr(), X.stride(0), tokens, Mw, Nw, dW.data_ptr(),
+    _call(f"gemm_wgrad[{Mw}x{Nw}]", 2.0 * tokens * Mw * Nw, "hma_gemm_wgrad", G.data_ptr(), G.stride(0), X.data_ptr(), X.stride(0), tokens, Mw, Nw, dW.data_ptr(),
               dW.stride(0), _s())
 
 
@@ -57,23 +96,23 @@ def ln_fwd(x: torch.Tensor, mode: int, *, gamma=None, beta=None, mod=None, rows_
     if out is None:
         out = torch.empty(n_rows, 256, device=x.device, dtype=BF16)
     stats = torch.empty(n_rows, 2, device=x.device, dtype=F32) if want_stats else None
-    _lib.call("hma_ln_fwd", x.data_ptr(), x.stride(0), n_rows, mode, _p(gamma), _p(beta), _p(mod), rows_per_group,
+    _call(f"ln_fwd[mode={mode}]", n_rows * 256 * 6.0, "hma_ln_fwd", x.data_ptr(), x.stride(0), n_rows, mode, _p(gamma), _p(beta), _p(mod), rows_per_group,
               float(eps), out.data_ptr(), out.stride(0), _p(stats), src_group, dst_group, _s())
     return (out, stats) if want_stats else out
 
 
 def ln_bwd(dy: torch.Tensor, x: torch.Tensor, stats: torch.Tensor, mode: int, dx: torch.Tensor, *, gamma=None,
            mod=None, rows_per_group: int = 0, dgamma=None, dbeta=None, dmod=None) -> None:
-    _lib.call("hma_ln_bwd", dy.data_ptr(), dy.stride(0), x.data_ptr(), x.stride(0), stats.data_ptr(), x.shape[0], mode,
+    _call(f"ln_bwd[mode={mode}]", x.shape[0] * 256 * 14.0, "hma_ln_bwd", dy.data_ptr(), dy.stride(0), x.data_ptr(), x.stride(0), stats.data_ptr(), x.shape[0], mode,
               _p(gamma), _p(mod), rows_per_group, dx.data_ptr(), dx.stride(0), _p(dgamma), _p(dbeta), _p(dmod), _s())
 
 
 def colsum_bf16(G: torch.Tensor, out: torch.Tensor) -> None:
-    _lib.call("hma_colsum_bf16", G.data_ptr(), G.stride(0), G.shape[0], G.shape[1], out.data_ptr(), _s())
+    _call("colsum_bf16", G.numel() * 2.0, "hma_colsum_bf16", G.data_ptr(), G.stride(0), G.shape[0], G.shape[1], out.data_ptr(), _s())
 
 
 def colsum_f32(G: torch.Tensor, out: torch.Tensor) -> None:
-    _lib.call("hma_colsum_f32", G.data_ptr(), G.stride(0), G.shape[0], G.shape[1], out.data_ptr(), _s())
+    _call("small", 0.0, "hma_colsum_f32", G.data_ptr(), G.stride(0), G.shape[0], G.shape[1], out.data_ptr(), _s())
 
 
 def cast_transpose(W: torch.Tensor, want_plain: bool = True, want_t: bool = True, alpha: float = 1.0):
@@ -82,14 +121,14 @@ def cast_transpose(W: torch.Tensor, want_plain: bool = True, want_t: bool = True
     R, C = W.shape
     Wb = torch.empty(R, C, device=W.device, dtype=BF16) if want_plain else None
     Wt = torch.empty(C, R, device=W.device, dtype=BF16) if want_t else None
-    _lib.call("hma_cast_transpose", W.data_ptr(), R, C, _p(Wb), _p(Wt), float(alpha), _s())
+    _call("cast_transpose", W.numel() * 8.0, "hma_cast_transpose", W.data_ptr(), R, C, _p(Wb), _p(Wt), float(alpha), _s())
     return Wb, Wt
 
 
 def cast_bf16(x: torch.Tensor) -> torch.Tensor:
     assert x.dtype == F32 and x.is_contiguous()
     y = torch.empty(x.shape, device=x.device, dtype=BF16)
-    _lib.call("hma_cast_bf16", x.data_ptr(), y.data_ptr(), x.numel(), _s())
+    _call("cast_bf16", x.numel() * 6.0, "hma_cast_bf16", x.data_ptr(), y.data_ptr(), x.numel(), _s())
     return y
 
 
@@ -98,7 +137,7 @@ def action_prep(a: torch.Tensor, kpad: int, mean=None, std=None) -> torch.Tensor
     assert a.dtype == F32 and a.dim() == 2 and a.is_contiguous()
     rows, da = a.shape
     y = torch.empty(rows, kpad, device=a.device, dtype=BF16)
-    _lib.call("hma_action_prep", a.data_ptr(), rows, da, _p(mean), _p(std), mean.numel() if mean is not None else 0,
+    _call("small", 0.0, "hma_action_prep", a.data_ptr(), rows, da, _p(mean), _p(std), mean.numel() if mean is not None else 0,
               y.data_ptr(), kpad, _s())
     return y
 
@@ -107,21 +146,21 @@ def ln_relu_fwd(x: torch.Tensor, gamma, beta, eps: float = 1e-5):
     rows = x.shape[0]
     y = torch.empty(rows, 256, device=x.device, dtype=BF16)
     stats = torch.empty(rows, 2, device=x.device, dtype=F32)
-    _lib.call("hma_ln_relu_fwd", x.data_ptr(), rows, gamma.data_ptr(), beta.data_ptr(), float(eps), y.data_ptr(),
+    _call("small", 0.0, "hma_ln_relu_fwd", x.data_ptr(), rows, gamma.data_ptr(), beta.data_ptr(), float(eps), y.data_ptr(),
               stats.data_ptr(), _s())
     return y, stats
 
 
 def ln_relu_bwd(dy, x, stats, gamma, beta, dgamma, dbeta) -> torch.Tensor:
     dx = torch.empty_like(x)
-    _lib.call("hma_ln_relu_bwd", dy.data_ptr(), x.data_ptr(), stats.data_ptr(), x.shape[0], gamma.data_ptr(),
+    _call("small", 0.0, "hma_ln_relu_bwd", dy.data_ptr(), x.data_ptr(), stats.data_ptr(), x.shape[0], gamma.data_ptr(),
               beta.data_ptr(), dx.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(), _s())
     return dx
 
 
 def rows_scatter(src: torch.Tensor, frames: int, S: int, n: int) -> torch.Tensor:
     dst = torch.empty(frames * n, 256, device=src.device, dtype=F32)
-    _lib.call("hma_rows_scatter", src.data_ptr(), dst.data_ptr(), frames, S, n, _s())
+    _call("rows_scatter", frames * n * 256 * 8.0, "hma_rows_scatter", src.data_ptr(), dst.data_ptr(), frames, S, n, _s())
     return dst
 
 
@@ -129,7 +168,7 @@ def attn_spatial_fwd(qkv: torch.Tensor, frames: int, n: int, heads: int, scale: 
     C = heads * 32
     out = torch.empty(frames * n, C, device=qkv.device, dtype=BF16)
     lse = torch.empty(frames, heads, n, device=qkv.device, dtype=F32) if want_lse else None
-    _lib.call("hma_attn_spatial_fwd", qkv.data_ptr(), qkv.stride(0), frames, n, heads, 0, C, 2 * C, float(scale),
+    _call("attn_spatial_fwd", 4.0 * frames * heads * n * n * 32, "hma_attn_spatial_fwd", qkv.data_ptr(), qkv.stride(0), frames, n, heads, 0, C, 2 * C, float(scale),
               out.data_ptr(), C, _p(lse), _s())
     return out, lse
 
@@ -137,7 +176,7 @@ def attn_spatial_fwd(qkv: torch.Tensor, frames: int, n: int, heads: int, scale: 
 def attn_spatial_bwd(qkv, out, dout, lse, frames: int, n: int, heads: int, scale: float) -> torch.Tensor:
     C = heads * 32
     dqkv = torch.empty_like(qkv)
-    _lib.call("hma_attn_spatial_bwd", qkv.data_ptr(), qkv.stride(0), out.data_ptr(), out.stride(0), dout.data_ptr(),
+    _call("attn_spatial_bwd", 10.0 * frames * heads * n * n * 32, "hma_attn_spatial_bwd", qkv.data_ptr(), qkv.stride(0), out.data_ptr(), out.stride(0), dout.data_ptr(),
               dout.stride(0), lse.data_ptr(), frames, n, heads, 0, C, 2 * C, float(scale), dqkv.data_ptr(),
               dqkv.stride(0), _s())
     return dqkv
@@ -146,7 +185,7 @@ def attn_spatial_bwd(qkv, out, dout, lse, frames: int, n: int, heads: int, scale
 def attn_temporal_fwd(qkv: torch.Tensor, B: int, T: int, n: int, heads: int, scale: float) -> torch.Tensor:
     C = heads * 32
     out = torch.empty(B * T * n, C, device=qkv.device, dtype=BF16)
-    _lib.call("hma_attn_temporal_fwd", qkv.data_ptr(), qkv.stride(0), B, T, n, heads, 0, C, 2 * C, float(scale),
+    _call("attn_temporal_fwd", B * T * n * C * 8.0, "hma_attn_temporal_fwd", qkv.data_ptr(), qkv.stride(0), B, T, n, heads, 0, C, 2 * C, float(scale),
               out.data_ptr(), C, _s())
     return out
 
@@ -154,20 +193,20 @@ def attn_temporal_fwd(qkv: torch.Tensor, B: int, T: int, n: int, heads: int, sca
 def attn_temporal_bwd(qkv, dout, B: int, T: int, n: int, heads: int, scale: float) -> torch.Tensor:
     C = heads * 32
     dqkv = torch.empty_like(qkv)
-    _lib.call("hma_attn_temporal_bwd", qkv.data_ptr(), qkv.stride(0), dout.data_ptr(), dout.stride(0), B, T, n, heads,
+    _call("attn_temporal_bwd", B * T * n * C * 16.0, "hma_attn_temporal_bwd", qkv.data_ptr(), qkv.stride(0), dout.data_ptr(), dout.stride(0), B, T, n, heads,
               0, C, 2 * C, float(scale), dqkv.data_ptr(), dqkv.stride(0), _s())
     return dqkv
 
 
 def embed_fwd(ids, E0, E1, mask_embed, act, pos, pos_n: int, B: int, T: int, S: int, A: int, vs: int, mask_id: int):
     x = torch.empty(B * T * (S + A), 256, device=ids.device, dtype=F32)
-    _lib.call("hma_embed_fwd", ids.data_ptr(), E0.data_ptr(), _p(E1), mask_embed.data_ptr(), _p(act), pos.data_ptr(),
+    _call("embed_fwd", B * T * (S + A) * 256 * 8.0, "hma_embed_fwd", ids.data_ptr(), E0.data_ptr(), _p(E1), mask_embed.data_ptr(), _p(act), pos.data_ptr(),
               pos_n, B, T, S, A, vs, mask_id, x.data_ptr(), _s())
     return x
 
 
 def embed_bwd(ids, dx, pos_n, B, T, S, A, vs, mask_id, dE0, dE1, dmask, dact, dpos) -> None:
-    _lib.call("hma_embed_bwd", ids.data_ptr(), dx.data_ptr(), pos_n, B, T, S, A, vs, mask_id, dE0.data_ptr(), _p(dE1),
+    _call("embed_bwd", B * T * (S + A) * 256 * 8.0, "hma_embed_bwd", ids.data_ptr(), dx.data_ptr(), pos_n, B, T, S, A, vs, mask_id, dE0.data_ptr(), _p(dE1),
               dmask.data_ptr(), _p(dact), dpos.data_ptr(), _s())
 
 
@@ -176,14 +215,14 @@ def ce_fwd(logits, labels, input_ids, B, T, S, nv, vs, mask_id, smoothing):
     lse = torch.empty(rows, nv, device=logits.device, dtype=F32)
     sums = torch.empty(3, device=logits.device, dtype=F32)
     loss_acc = torch.empty(2, device=logits.device, dtype=F32)
-    _lib.call("hma_ce_fwd", logits.data_ptr(), logits.stride(0), labels.data_ptr(), input_ids.data_ptr(), B, T, S, nv,
+    _call("ce_fwd", logits.numel() * 4.0, "hma_ce_fwd", logits.data_ptr(), logits.stride(0), labels.data_ptr(), input_ids.data_ptr(), B, T, S, nv,
               vs, mask_id, float(smoothing), lse.data_ptr(), sums.data_ptr(), loss_acc.data_ptr(), _s())
     return loss_acc, lse, sums
 
 
 def ce_bwd(logits, labels, input_ids, B, T, S, nv, vs, mask_id, smoothing, lse, sums, dloss) -> torch.Tensor:
     dlogits = torch.empty(B * T * S, nv * vs, device=logits.device, dtype=BF16)
-    _lib.call("hma_ce_bwd", logits.data_ptr(), logits.stride(0), labels.data_ptr(), input_ids.data_ptr(), B, T, S, nv,
+    _call("ce_bwd", logits.numel() * 6.0, "hma_ce_bwd", logits.data_ptr(), logits.stride(0), labels.data_ptr(), input_ids.data_ptr(), B, T, S, nv,
               vs, mask_id, float(smoothing), lse.data_ptr(), sums.data_ptr(), dloss.data_ptr(), dlogits.data_ptr(),
               dlogits.stride(0), _s())
     return dlogits
@@ -194,7 +233,7 @@ def sample_tokens(logits_frame: torch.Tensor, nv: int, vs: int, exp_noise: Optio
     B, S, _ = logits_frame.shape
     samples = torch.empty(B, S, device=logits_frame.device, dtype=torch.long)
     conf = torch.empty(B, S, device=logits_frame.device, dtype=F32)
-    _lib.call("hma_sample_tokens", logits_frame.data_ptr(), logits_frame.stride(0), logits_frame.stride(1), B, S, nv,
+    _call("sample_tokens", B * S * nv * vs * 4.0, "hma_sample_tokens", logits_frame.data_ptr(), logits_frame.stride(0), logits_frame.stride(1), B, S, nv,
               vs, _p(exp_noise), samples.data_ptr(), conf.data_ptr(), _s())
     return samples, conf
 
@@ -204,6 +243,6 @@ def rank_remask(keys, unmasked_u8, samples, frame_view, n_mask: int, mask_id: in
     B, S = samples.shape
     assert frame_view.stride(1) == 1
     out = torch.empty_like(samples)
-    _lib.call("hma_rank_remask", _p(keys), unmasked_u8.data_ptr(), samples.data_ptr(), frame_view.data_ptr(),
+    _call("rank_remask", B * S * 32.0, "hma_rank_remask", _p(keys), unmasked_u8.data_ptr(), samples.data_ptr(), frame_view.data_ptr(),
               frame_view.stride(0), B, S, n_mask, mask_id, out.data_ptr(), _s())
     return out

@@ -1,0 +1,158 @@
+"""Training step over the CUDA engine without autograd in the loop: forward, fused loss, backward,
+gradient synchronisation over NCCL, global-norm clip and AdamW — the device-side content of one
+iteration of the reference trainer (train_multi.py:556-598).
+
+Parameters live in one flat fp32 arena laid out [shared | domain 0 | domain 1 | ...]; the model's
+nn.Parameters are views into it, so state_dict()/load_state_dict() keep the reference key layout.
+A backward writes its gradients as one flat buffer [shared | active domain] with the same intra-range
+layout, which makes the optimizer two streaming kernels and the gradient exchange two collectives:
+  * all-reduce of the shared range (every rank contributes),
+  * all-gather of the per-domain range (each rank trains ONE domain per batch, as the reference's
+    MultiTaskBatchSampler guarantees; the reference instead all-reduces all ~375 M parameters, of
+    which ~330 M are zeros — SURVEY.md §2.2, §8e).
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence
+
+import torch
+import torch.distributed as dist
+
+from . import _lib, ops
+from .engine import SMOOTHING, Engine
+
+
+class ParamArena:
+    def __init__(self, model):
+        eng: Engine = model._engine
+        cfg = model.config
+        named = dict(model.named_parameters())
+        dev = next(iter(named.values())).device
+        d = eng.dims(1, cfg.T, cfg.S, True)
+        domains: List[str] = list(getattr(model, "action_mlp", {}).keys())
+        shared_used = eng.shared_param_names(named, d)
+        dom_used = {dom: eng.domain_param_names(named, d, dom, True) for dom in domains}
+        claimed = set(shared_used)
+        for v in dom_used.values():
+            claimed.update(v)
+        leftovers = [k for k in named if k not in claimed]
+        order: List[str] = list(shared_used)
+        self.shared_size = sum(eng.padded_numel(named[k]) for k in shared_used)
+        self.dom_range: Dict[str, tuple] = {}
+        off = self.shared_size
+        for dom in domains:
+            size = sum(eng.padded_numel(named[k]) for k in dom_used[dom])
+            self.dom_range[dom] = (off, size)
+            off += size
+            order += dom_used[dom]
+        order += leftovers
+        total = sum(eng.padded_numel(named[k]) for k in order)
+        self.flat = torch.zeros(total, device=dev, dtype=torch.float32)
+        self.offsets: Dict[str, int] = {}
+        off = 0
+        with torch.no_grad():
+            for k in order:
+                p = named[k]
+                view = self.flat[off:off + p.numel()].view(p.shape)
+                view.copy_(p.data)
+                p.data = view
+                self.offsets[k] = off
+                off += eng.padded_numel(p)
+        self.max_dom_size = max([s for _, s in self.dom_range.values()], default=0)
+
+
+class TrainStep:
+    def __init__(self, model, lr: float = 1e-4, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.05,
+                 max_grad_norm: Optional[float] = 1.0, process_group=None):
+        self.model = model
+        self.engine: Engine = model._engine
+        self.arena = ParamArena(model)
+        self.lr, self.betas, self.eps, self.wd, self.max_norm = lr, betas, eps, weight_decay, max_grad_norm
+        dev = self.arena.flat.device
+        self.m = torch.zeros_like(self.arena.flat)
+        self.v = torch.zeros_like(self.arena.flat)
+        self.grad = torch.zeros(self.arena.shared_size + self.arena.max_dom_size, device=dev, dtype=torch.float32)
+        self.sumsq = torch.zeros(1, device=dev, dtype=torch.float32)
+        self.ones = torch.ones(1, device=dev, dtype=torch.float32)
+        self.step_count = 0
+        self.pg = process_group
+        self.world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
+        self.rank = dist.get_rank(process_group) if self.world > 1 else 0
+        self.gathered = (torch.zeros(self.world, self.arena.max_dom_size, device=dev, dtype=torch.float32)
+                         if self.world > 1 else None)
+        self._p = None
+
+    def _params(self) -> Dict[str, torch.Tensor]:
+        if self._p is None:
+            p = {k: b for k, b in self.model.named_buffers()}
+            p.update({k: v.data for k, v in self.model.named_parameters()})
+            self._p = p
+        return self._p
+
+    def _adamw(self, lo: int, n: int, g: torch.Tensor, scale: float) -> None:
+        a = self.arena.flat
+        _lib.call("hma_adamw_step", a.data_ptr() + 4 * lo, g.data_ptr(), self.m.data_ptr() + 4 * lo,
+                  self.v.data_ptr() + 4 * lo, n, self.lr, self.betas[0], self.betas[1], self.eps, self.wd,
+                  self.step_count, scale, self.sumsq.data_ptr() if self.max_norm is not None else None,
+                  float(self.max_norm or 0.0), ops._s())
+
+    def __call__(self, input_ids: torch.Tensor, labels: torch.Tensor, action_ids: Optional[torch.Tensor], domain,
+                 rank_domains: Optional[Sequence[str]] = None) -> torch.Tensor:
+        """One optimisation step. Returns a device tensor [loss, acc]. `rank_domains[r]` is the domain rank r
+        trains this step (defaults to an all_gather_object when world_size > 1)."""
+        model, eng, cfg = self.model, self.engine, self.model.config
+        B = input_ids.shape[0]
+        T = cfg.T
+        S = input_ids.numel() // (B * T)
+        ids = input_ids.reshape(B, T, S).contiguous()
+        labels = labels.reshape(B, T * S).contiguous()
+        dom = model._domain0(domain, action_ids)
+        d = eng.dims(B, T, S, action_ids is not None)
+        p = self._params()
+        logits, sv = eng.forward(p, ids, action_ids, dom, d, training=True)
+        loss_acc, lse, sums = ops.ce_fwd(logits, labels, ids, B, T, S, d.nv, d.vs, d.mask_id, SMOOTHING)
+        dlogits = ops.ce_bwd(logits, labels, ids, B, T, S, d.nv, d.vs, d.mask_id, SMOOTHING, lse, sums, self.ones)
+        self.grad.zero_()
+        eng.backward(p, sv, dlogits, flat=self.grad)
+        self.step_count += 1
+        shared = self.arena.shared_size
+        dom_lo, dom_n = self.arena.dom_range.get(dom, (0, 0)) if dom is not None else (0, 0)
+        g_shared = self.grad[:shared]
+        g_dom = self.grad[shared:shared + dom_n]
+        scale = 1.0 / self.world
+        updates = []  # (arena offset, length, gradient tensor)
+        if self.world > 1:
+            if rank_domains is None:
+                gathered: List[Optional[str]] = [None] * self.world
+                dist.all_gather_object(gathered, dom, group=self.pg)
+                rank_domains = gathered
+            dist.all_reduce(g_shared, group=self.pg)
+            if self.arena.max_dom_size:
+                send = self.grad[shared:shared + self.arena.max_dom_size]
+                dist.all_gather_into_tensor(self.gathered.view(-1), send, group=self.pg)
+                first: Dict[str, int] = {}
+                for r, rd in enumerate(rank_domains):
+                    if rd is None:
+                        continue
+                    if rd in first:
+                        n_r = self.arena.dom_range[rd][1]
+                        self.gathered[first[rd], :n_r] += self.gathered[r, :n_r]
+                    else:
+                        first[rd] = r
+                for rd, r in first.items():
+                    lo, n_r = self.arena.dom_range[rd]
+                    updates.append((lo, n_r, self.gathered[r, :n_r]))
+        elif dom_n:
+            updates.append((dom_lo, dom_n, g_dom))
+        if self.max_norm is not None:
+            self.sumsq.zero_()
+            _lib.call("hma_sumsq", g_shared.data_ptr(), shared, self.sumsq.data_ptr(), ops._s())
+            for _, n_r, g in updates:
+                _lib.call("hma_sumsq", g.data_ptr(), n_r, self.sumsq.data_ptr(), ops._s())
+        self._adamw(0, shared, g_shared, scale)
+        for lo, n_r, g in updates:
+            self._adamw(lo, n_r, g, scale)
+        # parameters changed underneath torch's version counters: drop the cached bf16 inference copies
+        eng.weights._versions.clear()
+        eng._stem_w0.clear()
+        return loss_acc

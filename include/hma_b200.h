@@ -147,6 +147,16 @@ int hma_rank_remask(const float* keys, unsigned char* unmasked, const long long*
                     long long stride_b, int B, int S, int n_mask, long long mask_id, long long* out_samples,
                     void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Optimizer over contiguous fp32 ranges (train_multi.py:593-598: clip_grad_norm_ + AdamW)
+ * ------------------------------------------------------------------------------------------- */
+/* *out += sum(g^2) */
+int hma_sumsq(const float* g, long long n, float* out, void* stream);
+/* AdamW with decoupled weight decay; gradient = g * grad_scale * clip where
+ * clip = min(1, max_norm / (sqrt(*sumsq) * grad_scale + 1e-6)) if sumsq != NULL. step counts from 1. */
+int hma_adamw_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
+                   float eps, float wd, int step, float grad_scale, const float* sumsq, float max_norm, void* stream);
+
 /* Test-only: single-CTA tcgen05 descriptor probe (see csrc/probe.cu; params is a HOST int[18]). */
 int hma_umma_probe(const void* A, long long lda, const void* B, long long ldb, const int* params, float* out,
                    void* stream);
