@@ -47,6 +47,8 @@ _SIGNATURES = {
     "hma_colsum_f32": [c_fp, c_ll, c_int, c_int, c_fp, c_void_p],
     "hma_cast_transpose": [c_fp, c_int, c_int, c_void_p, c_void_p, c_float, c_void_p],
     "hma_cast_bf16": [c_fp, c_void_p, c_ll, c_void_p],
+    "hma_cast_colsum": [c_fp, c_void_p, c_int, c_fp, c_void_p],
+    "hma_cast_transpose_batched": [c_void_p, c_int, c_int, c_int, c_void_p],
     "hma_action_prep": [c_fp, c_int, c_int, c_fp, c_fp, c_int, c_void_p, c_int, c_void_p],
     "hma_ln_relu_fwd": [c_fp, c_int, c_fp, c_fp, c_float, c_void_p, c_fp, c_void_p],
     "hma_ln_relu_bwd": [c_fp, c_fp, c_fp, c_int, c_fp, c_fp, c_fp, c_fp, c_fp, c_void_p],

@@ -236,9 +236,19 @@ __device__ __forceinline__ float dgelu_erf(float z) {
   return cdf + z * pdf;
 }
 
-__device__ __forceinline__ float silu(float z) { return z / (1.0f + __expf(-z)); }
+__device__ __forceinline__ float fast_rcp(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float fast_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float silu(float z) { return z * fast_rcp(1.0f + fast_ex2(-1.4426950408889634f * z)); }
 __device__ __forceinline__ float dsilu(float z) {
-  const float s = 1.0f / (1.0f + __expf(-z));
+  const float s = fast_rcp(1.0f + fast_ex2(-1.4426950408889634f * z));
   return s * (1.0f + z * (1.0f - s));
 }
 

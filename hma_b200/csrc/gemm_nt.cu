@@ -3,14 +3,20 @@
 // st_mask_git.py:70-75,681-683 and their autograd transposes).
 //
 // sm_100a design: persistent CTAs, one 128 x BN output tile at a time.
-//   warp 0   TMA producer  (cp.async.bulk.tensor, 128-byte swizzle, 64-wide K panels)
-//   warp 1   UMMA issuer   (tcgen05.mma kind::f16, bf16 x bf16 -> fp32 in TMEM)
-//   warp 2   TMEM allocator
-//   warps 4-7 epilogue     (tcgen05.ld 32x32b: one output row per thread) with the fused
-//                          bias / GELU / dGELU / fp32-residual variants
+//   warp 0     TMA producer  (cp.async.bulk.tensor, 128-byte swizzle, 64-wide K panels)
+//   warp 1     UMMA issuer   (tcgen05.mma kind::f16, bf16 x bf16 -> fp32 in TMEM)
+//   warp 2     TMEM allocator
+//   warps 4-11 epilogue      (tcgen05.ld 32x32b: one accumulator row per thread; two warps per TMEM
+//                            lane quarter, alternating 32-column chunks)
 // The accumulator is double buffered in TMEM (2 x BN columns) so the epilogue of tile i overlaps
 // the MMAs of tile i+1. When the whole B slice (BN x K) fits in shared memory it is loaded once
 // per CTA and kept resident ("stationary"), so only A streams.
+//
+// Epilogue memory access: a thread owns a ROW of the accumulator, which is the worst possible
+// shape for global memory (32 lanes -> 32 different rows). Every chunk is therefore transposed
+// through a per-warp padded shared-memory buffer, and residual / saved-activation reads and all
+// stores are issued in the transposed domain, where a warp instruction touches whole 64/128-byte
+// row segments.
 #include "common.cuh"
 #include "../../include/hma_b200.h"
 
@@ -32,13 +38,118 @@ struct GemmNtParams {
 
 constexpr int kBM = 128;
 constexpr int kBK = 64;
-constexpr int kAStage = kBM * kBK * 2;  // 16 KB
-constexpr int kStages = 4;
+constexpr int kAStage = kBM * kBK * 2;      // 16 KB
+constexpr int kEpiWarps = 8;
+constexpr int kStageF32Row = 144;           // 32 fp32 + 16 B pad: conflict-free 16-byte row writes
+constexpr int kStageBf16Row = 80;           // 32 bf16 + 16 B pad
+constexpr int kStageBytes = 32 * kStageF32Row;  // per epilogue warp
+constexpr int kSmemLimit = 227 * 1024 - 1024;
+
+__device__ __forceinline__ void sts_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ uint4 lds_v4(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+
+// erf to ~2.5e-5 absolute (Abramowitz-Stegun 7.1.25) sharing e = exp(-x^2) with the Gaussian pdf;
+// far below the bf16 resolution of every consumer. x = z / sqrt(2).
+__device__ __forceinline__ void gelu_parts(float z, float& cdf, float& pdf) {
+  const float x = z * 0.70710678118654752f;
+  const float ax = fabsf(x);
+  const float t = fast_rcp(fmaf(0.47047f, ax, 1.0f));
+  const float e = fast_ex2(-1.4426950408889634f * x * x);
+  const float poly = ((0.7478556f * t - 0.0958798f) * t + 0.3480242f) * t;
+  const float erf_abs = fmaf(-poly, e, 1.0f);
+  cdf = 0.5f + 0.5f * copysignf(erf_abs, x);
+  pdf = 0.3989422804014327f * e;
+}
+template <int EPI>
+__device__ __forceinline__ float act_fwd(float z) {
+  if constexpr (EPI == HMA_EPI_GELU_BF16) {
+    float cdf, pdf;
+    gelu_parts(z, cdf, pdf);
+    return z * cdf;
+  } else {
+    return silu(z);
+  }
+}
+template <int EPI>
+__device__ __forceinline__ float act_bwd(float z) {
+  if constexpr (EPI == HMA_EPI_DGELU_BF16) {
+    float cdf, pdf;
+    gelu_parts(z, cdf, pdf);
+    return fmaf(z, pdf, cdf);
+  } else {
+    return dsilu(z);
+  }
+}
+
+// Stage 32 fp32 values of this lane's row, then hand each lane 4 consecutive columns of row
+// (4*i + lane/8), i = 0..7, via `f(row_in_chunk, col_in_chunk, float4)`.
+template <class F>
+__device__ __forceinline__ void transpose_f32(uint32_t stage, int lane, const float (&v)[32], F&& f) {
+#pragma unroll
+  for (int q = 0; q < 8; ++q)
+    sts_v4(stage + lane * kStageF32Row + q * 16, __float_as_uint(v[4 * q]), __float_as_uint(v[4 * q + 1]),
+           __float_as_uint(v[4 * q + 2]), __float_as_uint(v[4 * q + 3]));
+  __syncwarp();
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int rr = 4 * i + (lane >> 3);
+    const int cc = (lane & 7) * 4;
+    const uint4 u = lds_v4(stage + rr * kStageF32Row + cc * 4);
+    f(rr, cc, make_float4(__uint_as_float(u.x), __uint_as_float(u.y), __uint_as_float(u.z), __uint_as_float(u.w)));
+  }
+  __syncwarp();
+}
+
+// Stage 32 bf16 values of this lane's row and store the chunk to `dst` (row-major bf16, leading
+// dimension ld) with 64-byte row segments: lane handles row (8*i + lane/4), 16-byte piece lane%4.
+__device__ __forceinline__ void store_chunk_bf16(uint32_t stage, int lane, const float (&v)[32], __nv_bfloat16* dst,
+                                                 long long ld, int row0, int n0, int M) {
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+    sts_v4(stage + lane * kStageBf16Row + q * 16, pack_bf16(v[8 * q], v[8 * q + 1]), pack_bf16(v[8 * q + 2], v[8 * q + 3]),
+           pack_bf16(v[8 * q + 4], v[8 * q + 5]), pack_bf16(v[8 * q + 6], v[8 * q + 7]));
+  __syncwarp();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int rr = 8 * i + (lane >> 2);
+    const int piece = lane & 3;
+    const uint4 u = lds_v4(stage + rr * kStageBf16Row + piece * 16);
+    if (row0 + rr < M) *reinterpret_cast<uint4*>(dst + (size_t)(row0 + rr) * ld + n0 + piece * 8) = u;
+  }
+  __syncwarp();
+}
+
+// Positions a lane owns in the transposed domain of a 32x32 chunk: row 4*i + lane/8, columns (lane%8)*4..+3.
+template <int EPI>
+__device__ __forceinline__ void prefetch_chunk(const GemmNtParams& p, int row0, int n0, int lane, float4 (&pf)[8]) {
+  // RESID: the fp32 residual; DGELU/DSILU: the saved bf16 pre-activation (in the low 8 bytes)
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int row = row0 + 4 * i + (lane >> 3);
+    const int cc = (lane & 7) * 4;
+    pf[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (row < p.M) {
+      if constexpr (EPI == HMA_EPI_RESID_F32) {
+        if (p.resid != nullptr) pf[i] = *reinterpret_cast<const float4*>(p.resid + (size_t)row * p.ldr + n0 + cc);
+      } else {
+        const uint2 z = *reinterpret_cast<const uint2*>(p.aux + (size_t)row * p.ldaux + n0 + cc);
+        pf[i].x = __uint_as_float(z.x);
+        pf[i].y = __uint_as_float(z.y);
+      }
+    }
+  }
+}
 
 template <int EPI>
-__device__ __forceinline__ void epilogue_chunk(const GemmNtParams& p, const uint32_t (&r)[32], int row,
-                                               int n0) {
-  // r: 32 consecutive fp32 accumulator columns [n0, n0+32) of output row `row`.
+__device__ __forceinline__ void epilogue_chunk(const GemmNtParams& p, const uint32_t (&r)[32], int row0, int n0,
+                                               int lane, uint32_t stage, const float4 (&pf)[8]) {
+  // r: 32 consecutive fp32 accumulator columns [n0, n0+32) of output row (row0 + lane).
   float v[32];
 #pragma unroll
   for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * p.alpha;
@@ -49,67 +160,43 @@ __device__ __forceinline__ void epilogue_chunk(const GemmNtParams& p, const uint
       v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
     }
   }
-  if (row >= p.M) return;
-
   if constexpr (EPI == HMA_EPI_BF16) {
-    uint4* dst = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + (size_t)row * p.ldo + n0);
-#pragma unroll
-    for (int j = 0; j < 4; ++j)
-      dst[j] = make_uint4(pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
-                          pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
+    store_chunk_bf16(stage, lane, v, static_cast<__nv_bfloat16*>(p.out), p.ldo, row0, n0, p.M);
   } else if constexpr (EPI == HMA_EPI_GELU_BF16 || EPI == HMA_EPI_SILU_BF16) {
-    if (p.out2 != nullptr) {
-      uint4* dz = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out2) + (size_t)row * p.ldo2 + n0);
+    if (p.out2 != nullptr) store_chunk_bf16(stage, lane, v, static_cast<__nv_bfloat16*>(p.out2), p.ldo2, row0, n0, p.M);
 #pragma unroll
-      for (int j = 0; j < 4; ++j)
-        dz[j] = make_uint4(pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
-                           pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
-    }
-#pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = (EPI == HMA_EPI_GELU_BF16) ? gelu_erf(v[j]) : silu(v[j]);
-    uint4* dst = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + (size_t)row * p.ldo + n0);
-#pragma unroll
-    for (int j = 0; j < 4; ++j)
-      dst[j] = make_uint4(pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
-                          pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
+    for (int j = 0; j < 32; ++j) v[j] = act_fwd<EPI>(v[j]);
+    store_chunk_bf16(stage, lane, v, static_cast<__nv_bfloat16*>(p.out), p.ldo, row0, n0, p.M);
   } else if constexpr (EPI == HMA_EPI_DGELU_BF16 || EPI == HMA_EPI_DSILU_BF16) {
-    const uint4* z = reinterpret_cast<const uint4*>(p.aux + (size_t)row * p.ldaux + n0);
-    uint4* dst = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + (size_t)row * p.ldo + n0);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const uint4 zz = z[j];
-      const uint32_t zw[4] = {zz.x, zz.y, zz.z, zz.w};
-      uint32_t o[4];
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const float d0 = (EPI == HMA_EPI_DGELU_BF16) ? dgelu_erf(bf16_lo(zw[q])) : dsilu(bf16_lo(zw[q]));
-        const float d1 = (EPI == HMA_EPI_DGELU_BF16) ? dgelu_erf(bf16_hi(zw[q])) : dsilu(bf16_hi(zw[q]));
-        const float g0 = v[8 * j + 2 * q] * d0;
-        const float g1 = v[8 * j + 2 * q + 1] * d1;
-        o[q] = pack_bf16(g0, g1);
+    __nv_bfloat16* out = static_cast<__nv_bfloat16*>(p.out);
+    transpose_f32(stage, lane, v, [&](int rr, int cc, float4 a) {
+      const int row = row0 + rr;
+      if (row < p.M) {
+        const float4 zf = pf[rr >> 2];
+        const uint2 z = make_uint2(__float_as_uint(zf.x), __float_as_uint(zf.y));
+        const float g0 = a.x * act_bwd<EPI>(bf16_lo(z.x)), g1 = a.y * act_bwd<EPI>(bf16_hi(z.x));
+        const float g2 = a.z * act_bwd<EPI>(bf16_lo(z.y)), g3 = a.w * act_bwd<EPI>(bf16_hi(z.y));
+        *reinterpret_cast<uint2*>(out + (size_t)row * p.ldo + n0 + cc) = make_uint2(pack_bf16(g0, g1), pack_bf16(g2, g3));
       }
-      dst[j] = make_uint4(o[0], o[1], o[2], o[3]);
-    }
+    });
   } else if constexpr (EPI == HMA_EPI_RESID_F32) {
-    float4* dst = reinterpret_cast<float4*>(static_cast<float*>(p.out) + (size_t)row * p.ldo + n0);
-    if (p.resid != nullptr) {
-      const float4* src = reinterpret_cast<const float4*>(p.resid + (size_t)row * p.ldr + n0);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float4 x = src[j];
-        dst[j] = make_float4(x.x + v[4 * j], x.y + v[4 * j + 1], x.z + v[4 * j + 2], x.w + v[4 * j + 3]);
+    float* out = static_cast<float*>(p.out);
+    transpose_f32(stage, lane, v, [&](int rr, int cc, float4 a) {
+      const int row = row0 + rr;
+      if (row < p.M) {
+        const float4 x = pf[rr >> 2];
+        a.x += x.x; a.y += x.y; a.z += x.z; a.w += x.w;
+        *reinterpret_cast<float4*>(out + (size_t)row * p.ldo + n0 + cc) = a;
       }
-    } else {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-    }
+    });
   }
 }
 
 template <int BN, int EPI, bool STAT>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(384, 1)
 gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const GemmNtParams p) {
+  constexpr int kStages = (BN == 256) ? 3 : 4;
   constexpr int kBStage = BN * kBK * 2;
   constexpr uint32_t kTmemCols = 2 * BN;
   constexpr uint32_t kIdesc = umma_idesc_bf16(kBM, BN, 0, 0);
@@ -122,13 +209,14 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __shared__ __align__(8) uint64_t bar_tempty[2];
   __shared__ uint32_t tmem_base_slot;
 
+  const int KB = p.K / kBK;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t smemA = smem_base;
   const uint32_t smemB = smem_base + kStages * kAStage;
+  const uint32_t smemStage = smemB + (STAT ? KB : kStages) * kBStage;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int KB = p.K / kBK;
   const int n_tiles = p.N / BN;
   const int m_tiles = (p.M + kBM - 1) / kBM;
   const int n_blk = blockIdx.x % n_tiles;
@@ -147,7 +235,7 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     mbar_init(smem_u32(&bar_bfull), 1);
     for (int s = 0; s < 2; ++s) {
       mbar_init(smem_u32(&bar_tfull[s]), 1);
-      mbar_init(smem_u32(&bar_tempty[s]), 128);
+      mbar_init(smem_u32(&bar_tempty[s]), kEpiWarps * 32);
     }
     fence_barrier_init();
   }
@@ -215,20 +303,33 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else if (warp >= 4) {
     // ---------------------------------------------------------------- epilogue
-    const int ew = warp - 4;  // == warp % 4: the TMEM lane quarter this warp may read
+    const int ew = warp & 3;         // TMEM lane quarter this warp may read
+    const int eh = (warp - 4) >> 2;  // which 32-column chunks (c % 2 == eh)
+    const uint32_t stage_buf = smemStage + (uint32_t)(warp - 4) * kStageBytes;
+    // Global operands of the epilogue (fp32 residual / saved pre-activation) do not depend on the
+    // accumulator: they are fetched one chunk ahead, the first chunk of a tile BEFORE waiting for the
+    // MMAs, so their HBM latency hides behind the tensor-core work.
+    constexpr bool kPrefetch = (EPI == HMA_EPI_RESID_F32 || EPI == HMA_EPI_DGELU_BF16 || EPI == HMA_EPI_DSILU_BF16);
+    constexpr int kChunks = BN / 64;  // chunks per warp and tile
     int it = 0;
     for (int m_blk = m_start; m_blk < m_tiles; m_blk += m_step, ++it) {
       const int as = it & 1;
       const uint32_t aph = (uint32_t)(it >> 1) & 1u;
+      const int row0 = m_blk * kBM + ew * 32;
+      float4 pf[2][8];
+      if constexpr (kPrefetch) prefetch_chunk<EPI>(p, row0, n_blk * BN + eh * 32, lane, pf[0]);
       mbar_wait(smem_u32(&bar_tfull[as]), aph);
       tc_fence_after();
-      const int row = m_blk * kBM + ew * 32 + lane;
-#pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+#pragma unroll
+      for (int j = 0; j < kChunks; ++j) {
+        const int c = eh + 2 * j;
+        if constexpr (kPrefetch) {
+          if (j + 1 < kChunks) prefetch_chunk<EPI>(p, row0, n_blk * BN + (c + 2) * 32, lane, pf[(j + 1) & 1]);
+        }
         uint32_t r[32];
         tmem_ld_x32(tmem_addr(tmem_base, (uint32_t)(ew * 32), (uint32_t)(as * BN + c * 32)), r);
         tmem_ld_wait();
-        epilogue_chunk<EPI>(p, r, row, n_blk * BN + c * 32);
+        epilogue_chunk<EPI>(p, r, row0, n_blk * BN + c * 32, lane, stage_buf, pf[j & 1]);
       }
       tc_fence_before();
       mbar_arrive(smem_u32(&bar_tempty[as]));
@@ -243,25 +344,30 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
 }
 
+template <int BN>
+static size_t smem_need(int KB, bool stat) {
+  constexpr int kStages = (BN == 256) ? 3 : 4;
+  constexpr int kBStage = BN * kBK * 2;
+  return 1024 + (size_t)kStages * kAStage + (size_t)(stat ? KB : kStages) * kBStage + (size_t)kEpiWarps * kStageBytes;
+}
+
 template <int BN, int EPI, bool STAT>
 static int launch_nt(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmNtParams& p, cudaStream_t stream) {
-  constexpr int kBStage = BN * kBK * 2;
-  const int KB = p.K / kBK;
-  const size_t smem = 1024 + (size_t)kStages * kAStage + (STAT ? (size_t)KB * kBStage : (size_t)kStages * kBStage);
+  const size_t smem = smem_need<BN>(p.K / kBK, STAT);
   auto kern = gemm_nt_kernel<BN, EPI, STAT>;
   static bool attr_done = false;  // idempotent; racing threads set the same value
   if (!attr_done) {
-    HMA_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048));
+    HMA_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
     attr_done = true;
   }
-  HMA_REQUIRE(smem <= 227 * 1024 - 2048, "gemm_nt: shared memory request %zu too large", smem);
+  HMA_REQUIRE(smem <= (size_t)kSmemLimit, "gemm_nt: shared memory request %zu too large", smem);
   const int n_tiles = p.N / BN;
   const int m_tiles = (p.M + kBM - 1) / kBM;
   int per_n = hma_host::sm_count() / n_tiles;
   if (per_n < 1) per_n = 1;
   if (per_n > m_tiles) per_n = m_tiles;
   const int grid = per_n * n_tiles;
-  kern<<<grid, 256, smem, stream>>>(tmA, tmB, p);
+  kern<<<grid, 384, smem, stream>>>(tmA, tmB, p);
   HMA_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -269,10 +375,12 @@ static int launch_nt(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmN
 template <int EPI>
 static int dispatch_nt(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmNtParams& p, int bn,
                        cudaStream_t stream) {
-  const bool stat = (size_t)p.K * bn * 2 <= 128 * 1024;
+  const int KB = p.K / kBK;
   if (bn == 256) {
+    const bool stat = smem_need<256>(KB, true) <= (size_t)kSmemLimit;
     return stat ? launch_nt<256, EPI, true>(tmA, tmB, p, stream) : launch_nt<256, EPI, false>(tmA, tmB, p, stream);
   }
+  const bool stat = smem_need<128>(KB, true) <= (size_t)kSmemLimit;
   return stat ? launch_nt<128, EPI, true>(tmA, tmB, p, stream) : launch_nt<128, EPI, false>(tmA, tmB, p, stream);
 }
 
@@ -289,6 +397,7 @@ extern "C" int hma_gemm_nt(const void* A, long long lda, const void* B, long lon
   HMA_REQUIRE(K % kBK == 0, "gemm_nt: K=%d must be a multiple of 64", K);
   HMA_REQUIRE(N % 128 == 0, "gemm_nt: N=%d must be a multiple of 128", N);
   HMA_REQUIRE(out != nullptr, "gemm_nt: out is null");
+  HMA_REQUIRE(ldo % 8 == 0 && ldo2 % 8 == 0 && ldr % 4 == 0 && ldaux % 4 == 0, "gemm_nt: leading dimensions must keep rows 16-byte aligned");
   const int bn = (N % 256 == 0 && N >= 512) ? 256 : 128;
   CUtensorMap tmA, tmB;
   int rc = hma_host::make_tmap_bf16_2d(&tmA, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda * 2, kBK, kBM);

@@ -256,15 +256,7 @@ extern "C" int hma_ln_bwd(const void* dy, long long lddy, const float* x, long l
   return 0;
 }
 
-extern "C" int hma_colsum_bf16(const void* G, long long ld, int rows, int C, float* out, void* stream_) {
-  using namespace hma;
-  if (rows == 0) return 0;
-  HMA_REQUIRE(C % 4 == 0 && C <= 1024 && ld % 4 == 0, "colsum: C=%d must be a multiple of 4, <= 1024", C);
-  colsum_kernel<<<(rows + 127) / 128, 256, 0, static_cast<cudaStream_t>(stream_)>>>(
-      static_cast<const __nv_bfloat16*>(G), ld, rows, C, out);
-  HMA_CHECK_CUDA(cudaGetLastError());
-  return 0;
-}
+extern "C" int hma_colsum_bf16(const void* G, long long ld, int rows, int C, float* out, void* stream_);
 
 extern "C" int hma_cast_transpose(const float* W, int R, int Cc, void* Wb, void* Wt, float alpha, void* stream_) {
   using namespace hma;
@@ -447,6 +439,137 @@ extern "C" int hma_rows_scatter(const float* src, float* dst, int frames, int S,
   if (rows == 0) return 0;
   HMA_REQUIRE(S <= n, "rows_scatter: S=%d > n=%d", S, n);
   rows_scatter_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream_)>>>(src, dst, frames, S, n);
+  HMA_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+namespace hma {
+
+// y = bf16(x) for fp32 rows of 256, plus (optionally) colsum[c] += sum_r x[r, c] of the ROUNDED values:
+// the bias gradient of the projection that consumes y, for free while the row streams by.
+__global__ void __launch_bounds__(256) cast_colsum_kernel(const float* x, __nv_bfloat16* y, int rows, float* colsum) {
+  __shared__ float red[8][kC];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int r0 = blockIdx.x * 64;
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+#pragma unroll 4
+  for (int i = warp; i < 64; i += 8) {
+    const int row = r0 + i;
+    if (row < rows) {
+      const RowLoad r = load_row_f32(x + (size_t)row * kC, lane);
+      const uint2 a = make_uint2(pack_bf16(r.v[0], r.v[1]), pack_bf16(r.v[2], r.v[3]));
+      const uint2 b = make_uint2(pack_bf16(r.v[4], r.v[5]), pack_bf16(r.v[6], r.v[7]));
+      *reinterpret_cast<uint2*>(y + (size_t)row * kC + lane * 4) = a;
+      *reinterpret_cast<uint2*>(y + (size_t)row * kC + 128 + lane * 4) = b;
+      acc[0] += bf16_lo(a.x); acc[1] += bf16_hi(a.x); acc[2] += bf16_lo(a.y); acc[3] += bf16_hi(a.y);
+      acc[4] += bf16_lo(b.x); acc[5] += bf16_hi(b.x); acc[6] += bf16_lo(b.y); acc[7] += bf16_hi(b.y);
+    }
+  }
+  if (colsum == nullptr) return;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) red[warp][col_of(lane, j)] = acc[j];
+  __syncthreads();
+  float s = 0.f;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) s += red[w][threadIdx.x];
+  atomicAdd(colsum + threadIdx.x, s);
+}
+
+// out[c] += sum_r G[r, c], bf16 G with C % 8 == 0, C <= 2048: 16-byte loads, 128-row slabs per CTA.
+__global__ void __launch_bounds__(256) colsum_wide_kernel(const __nv_bfloat16* G, long long ld, int rows, int C,
+                                                          float* out) {
+  extern __shared__ float wred[];  // [groups][C]
+  const int vec_per_row = C / 8;
+  const int groups = 256 / vec_per_row;  // row groups processed concurrently (>= 1)
+  const int g = threadIdx.x / vec_per_row, vcol = threadIdx.x % vec_per_row;
+  const int r0 = blockIdx.x * 128;
+  const int r1 = min(rows, r0 + 128);
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  if (g < groups) {
+#pragma unroll 4
+    for (int r = r0 + g; r < r1; r += groups) {
+      const uint4 v = *reinterpret_cast<const uint4*>(G + (size_t)r * ld + vcol * 8);
+      acc[0] += bf16_lo(v.x); acc[1] += bf16_hi(v.x); acc[2] += bf16_lo(v.y); acc[3] += bf16_hi(v.y);
+      acc[4] += bf16_lo(v.z); acc[5] += bf16_hi(v.z); acc[6] += bf16_lo(v.w); acc[7] += bf16_hi(v.w);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) wred[g * C + vcol * 8 + j] = acc[j];
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += 256) {
+    float s = 0.f;
+    for (int q = 0; q < groups; ++q) s += wred[q * C + c];
+    atomicAdd(out + c, s);
+  }
+}
+
+struct CastDesc {
+  const float* src;
+  __nv_bfloat16* plain;
+  __nv_bfloat16* trans;
+  long long R, C;
+};
+
+// One launch for every weight matrix of a step: blockIdx.z selects the matrix.
+__global__ void __launch_bounds__(256) cast_transpose_batched_kernel(const CastDesc* descs) {
+  __shared__ float tile[32][33];
+  const CastDesc d = descs[blockIdx.z];
+  const int R = (int)d.R, Cc = (int)d.C;
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  if (c0 >= Cc || r0 >= R) return;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int i = ty; i < 32; i += 8) {
+    const int r = r0 + i, c = c0 + tx;
+    float v = 0.f;
+    if (r < R && c < Cc) {
+      v = d.src[(size_t)r * Cc + c];
+      if (d.plain != nullptr) d.plain[(size_t)r * Cc + c] = __float2bfloat16(v);
+    }
+    tile[i][tx] = v;
+  }
+  if (d.trans == nullptr) return;
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    const int c = c0 + i, r = r0 + tx;
+    if (r < R && c < Cc) d.trans[(size_t)c * R + r] = __float2bfloat16(tile[tx][i]);
+  }
+}
+
+}  // namespace hma
+
+extern "C" int hma_cast_colsum(const float* x, void* y, int rows, float* colsum, void* stream_) {
+  using namespace hma;
+  if (rows == 0) return 0;
+  cast_colsum_kernel<<<(rows + 63) / 64, 256, 0, static_cast<cudaStream_t>(stream_)>>>(
+      x, static_cast<__nv_bfloat16*>(y), rows, colsum);
+  HMA_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int hma_cast_transpose_batched(const void* descs, int count, int max_rows, int max_cols, void* stream_) {
+  using namespace hma;
+  if (count == 0) return 0;
+  HMA_REQUIRE(count <= 65535, "cast_transpose_batched: too many matrices");
+  dim3 grid((max_cols + 31) / 32, (max_rows + 31) / 32, count);
+  cast_transpose_batched_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream_)>>>(static_cast<const CastDesc*>(descs));
+  HMA_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int hma_colsum_bf16(const void* G, long long ld, int rows, int C, float* out, void* stream_) {
+  using namespace hma;
+  if (rows == 0) return 0;
+  HMA_REQUIRE(C % 8 == 0 && C <= 2048 && ld % 8 == 0, "colsum: C=%d must be a multiple of 8, <= 2048", C);
+  const int vec_per_row = C / 8;
+  const int groups = 256 / vec_per_row;
+  HMA_REQUIRE(groups >= 1, "colsum: C too wide");
+  const size_t smem = (size_t)groups * C * sizeof(float);
+  colsum_wide_kernel<<<(rows + 127) / 128, 256, smem, static_cast<cudaStream_t>(stream_)>>>(
+      static_cast<const __nv_bfloat16*>(G), ld, rows, C, out);
   HMA_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

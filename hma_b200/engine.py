@@ -76,25 +76,46 @@ def check_config(cfg) -> None:
 
 
 class Weights:
-    """bf16 operand copies of the fp32 master parameters (plain for forward, transposed for dgrad)."""
+    """bf16 operand copies of the fp32 master parameters (plain for forward, transposed for dgrad),
+    refreshed by ONE batched cast/transpose launch per step."""
 
     def __init__(self):
         self.plain: Dict[str, Tensor] = {}
         self.trans: Dict[str, Tensor] = {}
         self._versions: Dict[str, int] = {}
+        self._tables: Dict[tuple, tuple] = {}
 
     def prepare(self, params: Dict[str, Tensor], names: List[str], need_t: bool, force: bool) -> None:
+        todo = []
         for name in names:
             w = params[name]
-            ver = w._version
             have = name in self.plain and (not need_t or name in self.trans)
-            if have and not force and self._versions.get(name) == ver:
+            if have and not force and self._versions.get(name) == w._version:
                 continue
-            wb, wt = ops.cast_transpose(w.detach(), True, need_t)
-            self.plain[name] = wb
-            if need_t:
-                self.trans[name] = wt
-            self._versions[name] = ver
+            todo.append(name)
+        if not todo:
+            return
+        key = (tuple(todo), need_t)
+        srcs = tuple(params[n].data_ptr() for n in todo)
+        cached = self._tables.get(key)
+        if cached is None or cached[0] != srcs:
+            rows = []
+            for n in todo:
+                w = params[n]
+                assert w.dim() == 2 and w.is_contiguous() and w.dtype == torch.float32
+                R, Cc = w.shape
+                if n not in self.plain:
+                    self.plain[n] = torch.empty(R, Cc, device=w.device, dtype=torch.bfloat16)
+                if need_t and n not in self.trans:
+                    self.trans[n] = torch.empty(Cc, R, device=w.device, dtype=torch.bfloat16)
+                rows.append([w.data_ptr(), self.plain[n].data_ptr(), self.trans[n].data_ptr() if need_t else 0, R, Cc])
+            dev = params[todo[0]].device
+            table = torch.tensor(rows, dtype=torch.int64).to(dev)
+            cached = (srcs, table, max(r[3] for r in rows), max(r[4] for r in rows))
+            self._tables[key] = cached
+        ops.cast_transpose_batched(cached[1], len(todo), cached[2], cached[3])
+        for n in todo:
+            self._versions[n] = params[n]._version
 
 
 def layer_matrix_names(i: int, dom: Optional[str], modulate: bool) -> List[str]:
@@ -295,10 +316,8 @@ class Engine:
             L = sv["layers"][i]
             lp = f"decoder.layers.{i}."
             # ---- MLP
-            dy = ops.cast_bf16(dx)
+            dy = ops.cast_colsum(dx, g.get(lp + "mlp.fc2.bias"))
             ops.gemm_wgrad(dy, L["h"], g2(lp + "mlp.fc2.weight"))
-            if lp + "mlp.fc2.bias" in g:
-                ops.colsum_bf16(dy, g2(lp + "mlp.fc2.bias"))
             dz = ops.gemm_nt(dy, Wt[lp + "mlp.fc2.weight"], EPI_DGELU, aux=L["z"])
             ops.gemm_wgrad(dz, L["a2"], g2(lp + "mlp.fc1.weight"))
             if lp + "mlp.fc1.bias" in g:
@@ -307,10 +326,8 @@ class Engine:
             ops.ln_bwd(da2, L["x3"], L["st2"], 1, dx, gamma=p[lp + "norm2.weight"], dgamma=g2(lp + "norm2.weight"),
                        dbeta=g2(lp + "norm2.bias"))
             # ---- temporal attention
-            dy = ops.cast_bf16(dx)
+            dy = ops.cast_colsum(dx, g.get(lp + "temporal_attn.proj.bias"))
             ops.gemm_wgrad(dy, L["att_t"], g2(lp + "temporal_attn.proj.weight"))
-            if lp + "temporal_attn.proj.bias" in g:
-                ops.colsum_bf16(dy, g2(lp + "temporal_attn.proj.bias"))
             datt = ops.gemm_nt(dy, Wt[lp + "temporal_attn.proj.weight"], EPI_BF16)
             dqkv = ops.attn_temporal_bwd(L["qkv_t"], datt, B, T, n, d.heads, d.scale)
             ops.gemm_wgrad(dqkv, L["at"], g2(lp + "temporal_attn.qkv.weight"))
@@ -320,9 +337,8 @@ class Engine:
             # ---- modulate
             if d.modulate:
                 ap = lp + f"action_projectors.{dom}."
-                dy = ops.cast_bf16(dx)
+                dy = ops.cast_colsum(dx, g2(ap + "linear_out.bias"))
                 ops.gemm_wgrad(dy, L["am"], g2(ap + "linear_out.weight"))
-                ops.colsum_bf16(dy, g2(ap + "linear_out.bias"))
                 dam = ops.gemm_nt(dy, Wt[ap + "linear_out.weight"], EPI_BF16)
                 dmod = torch.zeros(M, 2 * C, device=dev, dtype=torch.float32)
                 ops.ln_bwd(dam, L["x1"], L["stm"], 2, dx, mod=L["mod"], rows_per_group=n, dmod=dmod)
@@ -335,10 +351,8 @@ class Engine:
                 ops.colsum_bf16(dzm, g2(ap + "adaLN_modulation.0.bias"))
                 ops.gemm_nt(dzm, Wt[ap + "adaLN_modulation.0.weight"], EPI_RESID, resid=dact, out=dact)
             # ---- spatial attention
-            dy = ops.cast_bf16(dx)
+            dy = ops.cast_colsum(dx, g.get(lp + "spatial_attn.proj.bias"))
             ops.gemm_wgrad(dy, L["att_s"], g2(lp + "spatial_attn.proj.weight"))
-            if lp + "spatial_attn.proj.bias" in g:
-                ops.colsum_bf16(dy, g2(lp + "spatial_attn.proj.bias"))
             datt = ops.gemm_nt(dy, Wt[lp + "spatial_attn.proj.weight"], EPI_BF16)
             dqkv = ops.attn_spatial_bwd(L["qkv_s"], L["att_s"], datt, L["lse"], M, n, d.heads, d.scale)
             ops.gemm_wgrad(dqkv, L["a1"], g2(lp + "spatial_attn.qkv.weight"))

@@ -132,6 +132,18 @@ def cast_bf16(x: torch.Tensor) -> torch.Tensor:
     return y
 
 
+def cast_colsum(x: torch.Tensor, colsum: Optional[torch.Tensor]) -> torch.Tensor:
+    """bf16 copy of fp32 [rows,256] and colsum[256] += its column sums (bias gradient of the consumer)."""
+    assert x.dtype == F32 and x.is_contiguous() and x.shape[1] == 256
+    y = torch.empty(x.shape, device=x.device, dtype=BF16)
+    _call("cast_colsum", x.numel() * 6.0, "hma_cast_colsum", x.data_ptr(), y.data_ptr(), x.shape[0], _p(colsum), _s())
+    return y
+
+
+def cast_transpose_batched(desc: torch.Tensor, count: int, max_rows: int, max_cols: int) -> None:
+    _call("cast_transpose_batched", 0.0, "hma_cast_transpose_batched", desc.data_ptr(), count, max_rows, max_cols, _s())
+
+
 def action_prep(a: torch.Tensor, kpad: int, mean=None, std=None) -> torch.Tensor:
     """(a - mean)/(std + 1e-10) per action-dim chunk, zero-padded to kpad columns, bf16."""
     assert a.dtype == F32 and a.dim() == 2 and a.is_contiguous()

@@ -106,6 +106,10 @@ int hma_colsum_f32(const float* G, long long ld, int rows, int C, float* out, vo
 /* W fp32 [R,C] * alpha -> Wb bf16 [R,C] (optional) and Wt bf16 [C,R] (optional). */
 int hma_cast_transpose(const float* W, int R, int C, void* Wb, void* Wt, float alpha, void* stream);
 int hma_cast_bf16(const float* x, void* y, long long count, void* stream);
+/* y = bf16(x) for fp32 rows of 256 and, if colsum != NULL, colsum[256] += column sums of y. */
+int hma_cast_colsum(const float* x, void* y, int rows, float* colsum, void* stream);
+/* descs: DEVICE array of {const float* src; bf16* plain; bf16* trans; int64 R; int64 C} (40 bytes each). */
+int hma_cast_transpose_batched(const void* descs, int count, int max_rows, int max_cols, void* stream);
 
 /* Action stem pieces (st_mask_git.py:134-138 ActionStat, :90-102 BasicMLP). */
 int hma_action_prep(const float* a, int rows, int da, const float* mean, const float* stdv, int adim, void* y,
