@@ -97,6 +97,15 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst_smem, const CUtensorMap
       : "memory");
 }
 
+__device__ __forceinline__ void tma_load_3d(uint32_t dst_smem, const CUtensorMap* m, uint32_t bar, int c0, int c1,
+                                            int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst_smem), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+
 // ------------------------------------------------------------------------------------------
 // TMEM allocation
 // ------------------------------------------------------------------------------------------
@@ -269,6 +278,9 @@ int make_tmap_bf16_2d(CUtensorMap* map, const void* base, uint64_t inner, uint64
 
 int make_tmap_bf16_2d_sw(CUtensorMap* map, const void* base, uint64_t inner, uint64_t outer,
                          uint64_t row_stride_bytes, uint32_t box_inner, uint32_t box_outer, int swizzle_bytes);
+
+int make_tmap_bf16_3d_sw64(CUtensorMap* map, const void* base, uint64_t d0, uint64_t d1, uint64_t d2,
+                           uint64_t stride1_bytes, uint64_t stride2_bytes, uint32_t b1, uint32_t b2);
 
 int sm_count();
 

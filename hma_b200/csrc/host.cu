@@ -64,6 +64,25 @@ int make_tmap_bf16_2d_sw(CUtensorMap* map, const void* base, uint64_t inner, uin
   return 0;
 }
 
+// 3-D bf16 map with 64-byte swizzle over a row-major [d2][d1][d0] view (d0 contiguous); box {32, b1, b2}.
+int make_tmap_bf16_3d_sw64(CUtensorMap* map, const void* base, uint64_t d0, uint64_t d1, uint64_t d2,
+                           uint64_t stride1_bytes, uint64_t stride2_bytes, uint32_t b1, uint32_t b2) {
+  EncodeFn enc = get_encode();
+  HMA_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled not available from the driver");
+  HMA_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0 && (stride1_bytes & 15) == 0 && (stride2_bytes & 15) == 0,
+              "TMA base/strides must be 16-byte aligned");
+  HMA_REQUIRE(b1 >= 1 && b1 <= 256 && b2 >= 1 && b2 <= 256, "TMA box out of range");
+  cuuint64_t gdim[3] = {d0, d1, d2};
+  cuuint64_t gstr[2] = {stride1_bytes, stride2_bytes};
+  cuuint32_t box[3] = {32, b1, b2};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  HMA_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(3d) failed with CUresult %d", (int)r);
+  return 0;
+}
+
 int sm_count() {
   static int n = 0;
   if (n == 0) {

@@ -222,7 +222,7 @@ class Engine:
             # ---- causal temporal attention, no pre-norm (st_transformer.py:111)
             at = ops.ln_fwd(x2, 0)
             qkv_t = ops.gemm_nt(at, Wp[lp + "temporal_attn.qkv.weight"], EPI_BF16, bias=p.get(lp + "temporal_attn.qkv.bias"))
-            att_t = ops.attn_temporal_fwd(qkv_t, B, T, n, d.heads, d.scale)
+            att_t, lse_t = ops.attn_temporal_fwd(qkv_t, B, T, n, d.heads, d.scale, want_lse=training)
             x3 = ops.gemm_nt(att_t, Wp[lp + "temporal_attn.proj.weight"], EPI_RESID, bias=p.get(lp + "temporal_attn.proj.bias"),
                              resid=x2, out=None if training else x2)
             # ---- MLP, pre-norm, erf-GELU (st_transformer.py:24-27,112)
@@ -233,7 +233,7 @@ class Engine:
                              out=None if training else x3)
             if training:
                 L.update(x0=x, a1=a1, st1=st1, qkv_s=qkv_s, att_s=att_s, lse=lse, x1=x1, at=at, qkv_t=qkv_t, att_t=att_t,
-                         x3=x3, a2=a2, st2=st2, z=z, h=h)
+                         x3=x3, a2=a2, st2=st2, z=z, h=h, lse_t=lse_t)
                 layers.append(L)
             x = x4
         # ---- head on the video tokens only (st_mask_git.py:681-683)
@@ -329,7 +329,7 @@ class Engine:
             dy = ops.cast_colsum(dx, g.get(lp + "temporal_attn.proj.bias"))
             ops.gemm_wgrad(dy, L["att_t"], g2(lp + "temporal_attn.proj.weight"))
             datt = ops.gemm_nt(dy, Wt[lp + "temporal_attn.proj.weight"], EPI_BF16)
-            dqkv = ops.attn_temporal_bwd(L["qkv_t"], datt, B, T, n, d.heads, d.scale)
+            dqkv = ops.attn_temporal_bwd(L["qkv_t"], L["att_t"], datt, L["lse_t"], B, T, n, d.heads, d.scale)
             ops.gemm_wgrad(dqkv, L["at"], g2(lp + "temporal_attn.qkv.weight"))
             if lp + "temporal_attn.qkv.bias" in g:
                 ops.colsum_bf16(dqkv, g2(lp + "temporal_attn.qkv.bias"))

@@ -194,19 +194,21 @@ def attn_spatial_bwd(qkv, out, dout, lse, frames: int, n: int, heads: int, scale
     return dqkv
 
 
-def attn_temporal_fwd(qkv: torch.Tensor, B: int, T: int, n: int, heads: int, scale: float) -> torch.Tensor:
+def attn_temporal_fwd(qkv: torch.Tensor, B: int, T: int, n: int, heads: int, scale: float, want_lse: bool = False):
     C = heads * 32
     out = torch.empty(B * T * n, C, device=qkv.device, dtype=BF16)
-    _call("attn_temporal_fwd", B * T * n * C * 8.0, "hma_attn_temporal_fwd", qkv.data_ptr(), qkv.stride(0), B, T, n, heads, 0, C, 2 * C, float(scale),
-              out.data_ptr(), C, _s())
-    return out
+    lse = torch.empty(B * T * n, heads, device=qkv.device, dtype=F32) if want_lse else None
+    _call("attn_temporal_fwd", B * T * n * C * 8.0, "hma_attn_temporal_fwd", qkv.data_ptr(), qkv.stride(0), B, T, n,
+          heads, 0, C, 2 * C, float(scale), out.data_ptr(), C, _p(lse), _s())
+    return out, lse
 
 
-def attn_temporal_bwd(qkv, dout, B: int, T: int, n: int, heads: int, scale: float) -> torch.Tensor:
+def attn_temporal_bwd(qkv, out, dout, lse, B: int, T: int, n: int, heads: int, scale: float) -> torch.Tensor:
     C = heads * 32
     dqkv = torch.empty_like(qkv)
-    _call("attn_temporal_bwd", B * T * n * C * 16.0, "hma_attn_temporal_bwd", qkv.data_ptr(), qkv.stride(0), dout.data_ptr(), dout.stride(0), B, T, n, heads,
-              0, C, 2 * C, float(scale), dqkv.data_ptr(), dqkv.stride(0), _s())
+    _call("attn_temporal_bwd", B * T * n * C * 18.0, "hma_attn_temporal_bwd", qkv.data_ptr(), qkv.stride(0),
+          out.data_ptr(), out.stride(0), dout.data_ptr(), dout.stride(0), lse.data_ptr(), B, T, n, heads, 0, C, 2 * C,
+          float(scale), dqkv.data_ptr(), dqkv.stride(0), _s())
     return dqkv
 
 

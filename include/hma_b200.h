@@ -74,12 +74,13 @@ int hma_attn_spatial_bwd(const void* qkv, long long ld_qkv, const void* out, lon
                          int v_col, float scale, void* dqkv, long long ld_dqkv, void* stream);
 
 /* Causal attention over the T frames of each of the n slots of each sample (attention.py:37-61 with
- * causal=True, st_transformer.py:111), reading the (B,T,n,·) layout in place. */
+ * causal=True, st_transformer.py:111), reading the (B,T,n,.) layout in place. T <= 128.
+ * lse: fp32 [tokens, heads] (log2 domain), optional in forward, required in backward. */
 int hma_attn_temporal_fwd(const void* qkv, long long ld_qkv, int B, int T, int n, int heads, int q_col, int k_col,
-                          int v_col, float scale, void* out, long long ldo, void* stream);
-int hma_attn_temporal_bwd(const void* qkv, long long ld_qkv, const void* dout, long long ld_dout, int B, int T, int n,
-                          int heads, int q_col, int k_col, int v_col, float scale, void* dqkv, long long ld_dqkv,
-                          void* stream);
+                          int v_col, float scale, void* out, long long ldo, float* lse, void* stream);
+int hma_attn_temporal_bwd(const void* qkv, long long ld_qkv, const void* out, long long ldo, const void* dout,
+                          long long ld_dout, const float* lse, int B, int T, int n, int heads, int q_col, int k_col,
+                          int v_col, float scale, void* dqkv, long long ld_dqkv, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Row-wise stages (d_model = 256): fp32 residual stream -> bf16 operand

@@ -36,7 +36,7 @@ def test_attn_spatial_fwd(frames, n):
     assert (lse - ref_lse).abs().max().item() < 2e-2
 
 
-@pytest.mark.parametrize("B,T,n", [(2, 4, 320), (1, 16, 40), (2, 32, 24), (1, 5, 7)])
+@pytest.mark.parametrize("B,T,n", [(2, 4, 320), (1, 16, 40), (2, 32, 24), (1, 5, 7), (2, 12, 320), (1, 128, 3), (1, 1, 16)])
 def test_attn_temporal_fwd_bwd(B, T, n):
     torch.manual_seed(1)
     H, hd = 8, 32
@@ -47,9 +47,11 @@ def test_attn_temporal_fwd_bwd(B, T, n):
     out = torch.zeros(rows, C, device="cuda", dtype=torch.bfloat16)
     dqkv = torch.zeros(rows, 3 * C, device="cuda", dtype=torch.bfloat16)
     scale = 0.25
-    _lib.call("hma_attn_temporal_fwd", qkv.data_ptr(), 3 * C, B, T, n, H, 0, C, 2 * C, scale, out.data_ptr(), C, S_())
-    _lib.call("hma_attn_temporal_bwd", qkv.data_ptr(), 3 * C, dout.data_ptr(), C, B, T, n, H, 0, C, 2 * C, scale,
-              dqkv.data_ptr(), 3 * C, S_())
+    lse = torch.zeros(rows, H, device="cuda")
+    _lib.call("hma_attn_temporal_fwd", qkv.data_ptr(), 3 * C, B, T, n, H, 0, C, 2 * C, scale, out.data_ptr(), C,
+              lse.data_ptr(), S_())
+    _lib.call("hma_attn_temporal_bwd", qkv.data_ptr(), 3 * C, out.data_ptr(), C, dout.data_ptr(), C, lse.data_ptr(), B,
+              T, n, H, 0, C, 2 * C, scale, dqkv.data_ptr(), 3 * C, S_())
     torch.cuda.synchronize()
     x = qkv.float().reshape(B, T, n, 3, H, hd).requires_grad_(True)
     q, k, v = x.permute(3, 0, 2, 4, 1, 5)  # [B, n, H, T, hd]
