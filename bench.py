@@ -210,11 +210,13 @@ def main() -> None:
     dominant = "gemm_nt[N=1024,K=256,epi=1]"  # fc1 + GELU: see DESIGN.md "roofline kernel"
     ops.PROFILER = ops.Profiler(kinds={dominant})
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.profiler.start()  # no-op unless run as `ncu --profile-from-start off ...` (profiles/ recipes)
     e0.record()
     for i in range(args.warmup, total):
         out = run_resident(i, resident[i])
     e1.record()
     sync_all()
+    torch.cuda.profiler.stop()
     ms_resident = e0.elapsed_time(e1)
     prof = ops.PROFILER.summary()
     ops.PROFILER = None

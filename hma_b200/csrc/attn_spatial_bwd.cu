@@ -10,6 +10,10 @@
 //   dQ           : A = dS K-major, B = K MN-major (reduction over keys)
 // Accumulators live in TMEM (S 128 + dP 128 + dQ 3x32 + dK 32 + dV 32 columns). Eight compute
 // warps turn (S, dP) into (P, dS): warp w owns TMEM lane quarter w%4 and key-column half w/4.
+// Software pipeline: the compute warps first copy their S / dP columns into registers and release
+// TMEM, so the S / dP contractions of the NEXT tile pair run while they do the exp / dS math, and
+// the P / dS tiles are double buffered in shared memory so they never wait for the dV/dK/dQ
+// contractions of the previous pair either.
 #include "common.cuh"
 #include "../../include/hma_b200.h"
 
@@ -58,7 +62,7 @@ __global__ void __launch_bounds__(288, 1)
 attn_spatial_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
                         const AttnBwdParams p) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t bar_load, bar_sdp, bar_pds, bar_kv, bar_epi, bar_final;
+  __shared__ __align__(8) uint64_t bar_load, bar_sdp, bar_tfree, bar_pds[2], bar_mma[2], bar_kv, bar_epi, bar_final;
   __shared__ uint32_t tmem_base_slot;
   __shared__ float s_lse[kBMaxN];
   __shared__ float s_delta[kBMaxN];
@@ -68,8 +72,8 @@ attn_spatial_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
   const uint32_t sK = sQ + kBTile;
   const uint32_t sV = sK + kBTile;
   const uint32_t sDO = sV + kBTile;
-  const uint32_t sP = sDO + kBTile;          // 80 KB offset: 1024-aligned
-  const uint32_t sDS = sP + 2 * kBPanel;
+  const uint32_t sP0 = sDO + kBTile;         // 80 KB offset: 1024-aligned; two {P, dS} buffers of 64 KB
+  constexpr uint32_t kPdsBuf = 4 * kBPanel;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -82,13 +86,30 @@ attn_spatial_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
   if (threadIdx.x == 0) {
     mbar_init(smem_u32(&bar_load), 1);
     mbar_init(smem_u32(&bar_sdp), 1);
-    mbar_init(smem_u32(&bar_pds), kComputeThreads);
+    mbar_init(smem_u32(&bar_tfree), kComputeThreads);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(smem_u32(&bar_pds[i]), kComputeThreads);
+      mbar_init(smem_u32(&bar_mma[i]), 1);
+    }
     mbar_init(smem_u32(&bar_kv), 1);
     mbar_init(smem_u32(&bar_epi), kComputeThreads);
     mbar_init(smem_u32(&bar_final), 1);
     fence_barrier_init();
   }
+  __syncthreads();
   if (warp == 8) {
+    // start the operand loads first: they overlap the per-row statistics below
+    if (elect_one()) {
+      const uint32_t bl = smem_u32(&bar_load);
+      mbar_expect_tx(bl, (uint32_t)(4 * n * kBRowB));
+      for (int r = 0; r < n; r += p.box_rows) {
+        tma_load_2d(sQ + r * kBRowB, &tmQKV, bl, p.q_col + head * 32, row0 + r);
+        tma_load_2d(sK + r * kBRowB, &tmQKV, bl, p.k_col + head * 32, row0 + r);
+        tma_load_2d(sV + r * kBRowB, &tmQKV, bl, p.v_col + head * 32, row0 + r);
+        tma_load_2d(sDO + r * kBRowB, &tmDO, bl, head * 32, row0 + r);
+      }
+    }
+    __syncwarp();
     tmem_alloc(smem_u32(&tmem_base_slot), 512);
     tmem_relinquish();
   }
@@ -116,15 +137,7 @@ attn_spatial_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
 
   if (warp == 8) {
     if (elect_one()) {
-      const uint32_t bl = smem_u32(&bar_load);
-      mbar_expect_tx(bl, (uint32_t)(4 * n * kBRowB));
-      for (int r = 0; r < n; r += p.box_rows) {
-        tma_load_2d(sQ + r * kBRowB, &tmQKV, bl, p.q_col + head * 32, row0 + r);
-        tma_load_2d(sK + r * kBRowB, &tmQKV, bl, p.k_col + head * 32, row0 + r);
-        tma_load_2d(sV + r * kBRowB, &tmQKV, bl, p.v_col + head * 32, row0 + r);
-        tma_load_2d(sDO + r * kBRowB, &tmDO, bl, head * 32, row0 + r);
-      }
-      mbar_wait(bl, 0);
+      mbar_wait(smem_u32(&bar_load), 0);
       tc_fence_after();
 
       auto issue_sdp = [&](int kt, int qt) {
@@ -142,40 +155,43 @@ attn_spatial_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
 
       const uint32_t idesc_t = umma_idesc_bf16(128, 32, 1, 1);   // dV, dK: both operands MN-major
       const uint32_t idesc_q = umma_idesc_bf16(128, 32, 0, 1);   // dQ: A K-major, B MN-major
-      int it = 0;
+      const int NI = ntile * ntile;
       issue_sdp(0, 0);
       umma_commit(smem_u32(&bar_sdp));
-      for (int kt = 0; kt < ntile; ++kt) {
+      for (int it = 0; it < NI; ++it) {
+        const int kt = it / ntile, qt = it % ntile;
         const int nk = min(128, n - kt * 128);
-        for (int qt = 0; qt < ntile; ++qt, ++it) {
-          const int kq = min(128, n - qt * 128);
-          mbar_wait(smem_u32(&bar_pds), (uint32_t)(it & 1));
-          tc_fence_after();
-          if (qt == 0 && kt > 0) {
-            mbar_wait(smem_u32(&bar_epi), (uint32_t)((kt - 1) & 1));
-            tc_fence_after();
-          }
-          const uint32_t q_addr = sQ + (uint32_t)qt * 128 * kBRowB;
-          const uint32_t do_addr = sDO + (uint32_t)qt * 128 * kBRowB;
-          for (int kk = 0; kk < kq / 16; ++kk) {
-            umma_ss(tDV, umma_desc_mnmajor(sP + kk * 2048, kBPanel), bdesc_sw64(do_addr + kk * 1024), idesc_t,
-                    (uint32_t)((qt | kk) != 0));
-            umma_ss(tDK, umma_desc_mnmajor(sDS + kk * 2048, kBPanel), bdesc_sw64(q_addr + kk * 1024), idesc_t,
-                    (uint32_t)((qt | kk) != 0));
-          }
-          for (int kk = 0; kk < nk / 16; ++kk)
-            umma_ss(tDQ + (uint32_t)qt * 32, umma_desc_kmajor(sDS + (uint32_t)(kk >> 2) * kBPanel + (uint32_t)(kk & 3) * 32),
-                    bdesc_sw64(sK + (uint32_t)(kt * 128 + kk * 16) * kBRowB), idesc_q, (uint32_t)((kt | kk) != 0));
-          if (qt == ntile - 1) umma_commit(smem_u32(&bar_kv));
-          int nkt = kt, nqt = qt + 1;
-          if (nqt == ntile) { nqt = 0; nkt = kt + 1; }
-          if (nkt < ntile) {
-            issue_sdp(nkt, nqt);
-            umma_commit(smem_u32(&bar_sdp));
-          } else {
-            umma_commit(smem_u32(&bar_final));
-          }
+        const int kq = min(128, n - qt * 128);
+        const int bsel = it & 1;
+        // S / dP of the next pair as soon as this pair's have been copied out of TMEM
+        mbar_wait(smem_u32(&bar_tfree), (uint32_t)(it & 1));
+        tc_fence_after();
+        if (it + 1 < NI) {
+          issue_sdp((it + 1) / ntile, (it + 1) % ntile);
+          umma_commit(smem_u32(&bar_sdp));
         }
+        mbar_wait(smem_u32(&bar_pds[bsel]), (uint32_t)((it >> 1) & 1));
+        tc_fence_after();
+        if (qt == 0 && kt > 0) {
+          mbar_wait(smem_u32(&bar_epi), (uint32_t)((kt - 1) & 1));
+          tc_fence_after();
+        }
+        const uint32_t sP = sP0 + (uint32_t)bsel * kPdsBuf;
+        const uint32_t sDS = sP + 2 * kBPanel;
+        const uint32_t q_addr = sQ + (uint32_t)qt * 128 * kBRowB;
+        const uint32_t do_addr = sDO + (uint32_t)qt * 128 * kBRowB;
+        for (int kk = 0; kk < kq / 16; ++kk) {
+          umma_ss(tDV, umma_desc_mnmajor(sP + kk * 2048, kBPanel), bdesc_sw64(do_addr + kk * 1024), idesc_t,
+                  (uint32_t)((qt | kk) != 0));
+          umma_ss(tDK, umma_desc_mnmajor(sDS + kk * 2048, kBPanel), bdesc_sw64(q_addr + kk * 1024), idesc_t,
+                  (uint32_t)((qt | kk) != 0));
+        }
+        for (int kk = 0; kk < nk / 16; ++kk)
+          umma_ss(tDQ + (uint32_t)qt * 32, umma_desc_kmajor(sDS + (uint32_t)(kk >> 2) * kBPanel + (uint32_t)(kk & 3) * 32),
+                  bdesc_sw64(sK + (uint32_t)(kt * 128 + kk * 16) * kBRowB), idesc_q, (uint32_t)((kt | kk) != 0));
+        umma_commit(smem_u32(&bar_mma[bsel]));
+        if (qt == ntile - 1) umma_commit(smem_u32(&bar_kv));
+        if (it == NI - 1) umma_commit(smem_u32(&bar_final));
       }
     }
   } else {
@@ -187,26 +203,41 @@ attn_spatial_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
     for (int kt = 0; kt < ntile; ++kt) {
       const int nk = min(128, n - kt * 128);
       for (int qt = 0; qt < ntile; ++qt, ++it) {
+        // (9 warps -> three share one SM sub-partition -> <= 168 registers: do every spin-wait BEFORE the
+        //  128 S/dP registers become live so nothing spills inside a wait loop)
+        const int bsel = it & 1;
+        if (it >= 2) mbar_wait(smem_u32(&bar_mma[bsel]), (uint32_t)(((it - 2) >> 1) & 1));
         mbar_wait(smem_u32(&bar_sdp), (uint32_t)(it & 1));
         tc_fence_after();
         const int qi = qt * 128 + row;
         const float L = qi < n ? s_lse[qi] : 0.f;
         const float delta = qi < n ? s_delta[qi] : 0.f;
-#pragma unroll 1
+        // copy this warp's S / dP columns to registers and hand TMEM back to the tensor core
+        uint32_t s[2][32], dp[2][32];
+        const bool has0 = half * 64 < nk, has1 = half * 64 + 32 < nk;  // warp-uniform
+        if (has0) {
+          tmem_ld_x32(tS + lane_addr + half * 64, s[0]);
+          tmem_ld_x32(tDP + lane_addr + half * 64, dp[0]);
+        }
+        if (has1) {
+          tmem_ld_x32(tS + lane_addr + half * 64 + 32, s[1]);
+          tmem_ld_x32(tDP + lane_addr + half * 64 + 32, dp[1]);
+        }
+        tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive(smem_u32(&bar_tfree));
+        const uint32_t sP = sP0 + (uint32_t)bsel * kPdsBuf;
+        const uint32_t sDS = sP + 2 * kBPanel;
+#pragma unroll
         for (int cc = 0; cc < 2; ++cc) {
-          const int col0 = half * 64 + cc * 32;
-          if (col0 >= nk) break;  // warp-uniform
-          uint32_t s[32], dp[32];
-          tmem_ld_x32(tS + lane_addr + col0, s);
-          tmem_ld_x32(tDP + lane_addr + col0, dp);
-          tmem_ld_wait();
+          if (cc == 0 ? !has0 : !has1) continue;
           uint32_t pk[16], dk[16];
 #pragma unroll
           for (int j = 0; j < 32; j += 2) {
-            const float p0 = exp2f(fmaf(__uint_as_float(s[j]), p.scale_log2, -L));
-            const float p1 = exp2f(fmaf(__uint_as_float(s[j + 1]), p.scale_log2, -L));
-            const float d0 = p0 * (__uint_as_float(dp[j]) - delta) * p.scale;
-            const float d1 = p1 * (__uint_as_float(dp[j + 1]) - delta) * p.scale;
+            const float p0 = fast_ex2(fmaf(__uint_as_float(s[cc][j]), p.scale_log2, -L));
+            const float p1 = fast_ex2(fmaf(__uint_as_float(s[cc][j + 1]), p.scale_log2, -L));
+            const float d0 = p0 * (__uint_as_float(dp[cc][j]) - delta) * p.scale;
+            const float d1 = p1 * (__uint_as_float(dp[cc][j + 1]) - delta) * p.scale;
             pk[j >> 1] = pack_bf16(p0, p1);
             dk[j >> 1] = pack_bf16(d0, d1);
           }
@@ -221,8 +252,7 @@ attn_spatial_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
           }
         }
         fence_proxy_async();
-        tc_fence_before();
-        mbar_arrive(smem_u32(&bar_pds));
+        mbar_arrive(smem_u32(&bar_pds[bsel]));
         if (qt == ntile - 1) {
           // dK / dV of this key tile are complete: warps 0-3 store dK, warps 4-7 store dV
           mbar_wait(smem_u32(&bar_kv), (uint32_t)(kt & 1));
@@ -287,7 +317,7 @@ extern "C" int hma_attn_spatial_bwd(const void* qkv, long long ld_qkv, const voi
   rc = hma_host::make_tmap_bf16_2d_sw(&tmD, dout, (uint64_t)ld_dout, (uint64_t)frames * n, (uint64_t)ld_dout * 2, 32,
                                       (uint32_t)p.box_rows, 64);
   if (rc) return rc;
-  constexpr size_t smem = 1024 + 4 * kBTile + 4 * kBPanel;
+  constexpr size_t smem = 1024 + 4 * kBTile + 8 * kBPanel;
   static bool attr_done = false;
   if (!attr_done) {
     HMA_CHECK_CUDA(cudaFuncSetAttribute(attn_spatial_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -47,9 +47,10 @@ __device__ __forceinline__ uint64_t desc_sw64(uint32_t saddr, uint32_t lbo, uint
   return d;
 }
 
-// one key block: stats + P for the calling thread's row
-__device__ __forceinline__ void softmax_block(uint32_t tmem_row_s, int ncols, float scale_log2, uint32_t p_smem,
-                                              int row, float& m_out, float& l_out) {
+// one key block: stats + P for the calling thread's row. kFull: ncols is a multiple of 32.
+template <bool kFull>
+__device__ __forceinline__ void softmax_block_t(uint32_t tmem_row_s, int ncols, float scale_log2, uint32_t p_smem,
+                                                int row, float& m_out, float& l_out) {
   float m = -INFINITY;
   for (int c = 0; c < ncols; c += 32) {
     uint32_t r[32];
@@ -57,10 +58,10 @@ __device__ __forceinline__ void softmax_block(uint32_t tmem_row_s, int ncols, fl
     tmem_ld_wait();
 #pragma unroll
     for (int j = 0; j < 32; ++j)
-      if (c + j < ncols) m = fmaxf(m, __uint_as_float(r[j]));  // ncols may end inside the last chunk
+      if (kFull || c + j < ncols) m = fmaxf(m, __uint_as_float(r[j]));
   }
   const float mb = m * scale_log2;
-  float l = 0.f;
+  float l0 = 0.f, l1 = 0.f;
   for (int c = 0; c < ncols; c += 32) {
     uint32_t r[32];
     tmem_ld_x32(tmem_row_s + c, r);
@@ -68,13 +69,12 @@ __device__ __forceinline__ void softmax_block(uint32_t tmem_row_s, int ncols, fl
     uint32_t pk[16];
 #pragma unroll
     for (int j = 0; j < 32; j += 2) {
-      float p0 = exp2f(fmaf(__uint_as_float(r[j]), scale_log2, -mb));
-      float p1 = exp2f(fmaf(__uint_as_float(r[j + 1]), scale_log2, -mb));
-      if (c + j >= ncols) { p0 = 0.f; p1 = 0.f; }  // ncols is a multiple of 16, so pairs never straddle
-      // sum what the tensor core will actually multiply (bf16-rounded), as flash kernels do
-      const uint32_t w = pack_bf16(p0, p1);
-      l += bf16_lo(w) + bf16_hi(w);
-      pk[j >> 1] = w;
+      float p0 = fast_ex2(fmaf(__uint_as_float(r[j]), scale_log2, -mb));
+      float p1 = fast_ex2(fmaf(__uint_as_float(r[j + 1]), scale_log2, -mb));
+      if (!kFull && c + j >= ncols) { p0 = 0.f; p1 = 0.f; }  // ncols is a multiple of 16: pairs never straddle
+      l0 += p0;
+      l1 += p1;
+      pk[j >> 1] = pack_bf16(p0, p1);
     }
     const uint32_t panel = p_smem + (uint32_t)(c >> 6) * kPPanel;
     const int col0 = c & 63;
@@ -87,7 +87,12 @@ __device__ __forceinline__ void softmax_block(uint32_t tmem_row_s, int ncols, fl
     }
   }
   m_out = m;
-  l_out = l;
+  l_out = l0 + l1;
+}
+__device__ __forceinline__ void softmax_block(uint32_t tmem_row_s, int ncols, float scale_log2, uint32_t p_smem,
+                                              int row, float& m_out, float& l_out) {
+  if ((ncols & 31) == 0) softmax_block_t<true>(tmem_row_s, ncols, scale_log2, p_smem, row, m_out, l_out);
+  else softmax_block_t<false>(tmem_row_s, ncols, scale_log2, p_smem, row, m_out, l_out);
 }
 
 __global__ void __launch_bounds__(160, 2)
@@ -208,8 +213,8 @@ attn_spatial_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnFwd
       mbar_arrive(smem_u32(&bar_oread));
 
       const float m = fmaxf(ma, mb);
-      const float wa = exp2f((ma - m) * p.scale_log2);
-      const float wb = nb > 0 ? exp2f((mb - m) * p.scale_log2) : 0.f;
+      const float wa = fast_ex2((ma - m) * p.scale_log2);
+      const float wb = nb > 0 ? fast_ex2((mb - m) * p.scale_log2) : 0.f;
       const float l = la * wa + lb * wb;
       const float inv = 1.0f / l;
       const int qi = t * 128 + row;
