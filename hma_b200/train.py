@@ -61,6 +61,37 @@ class ParamArena:
         self.max_dom_size = max([s for _, s in self.dom_range.values()], default=0)
 
 
+def exchange_gradients(grad: torch.Tensor, shared_size: int, max_dom_size: int, dom_range: Dict[str, tuple],
+                       rank_domains: Sequence[Optional[str]], gathered: Optional[torch.Tensor], group=None):
+    """Gradient exchange of one step (device- and backend-agnostic: NCCL on GPUs, gloo in the CPU tests).
+
+    grad = [shared | this rank's domain block] (sums, not means). After the call grad[:shared_size] holds the
+    sum over ranks, and the returned list [(arena_offset, length, tensor)] holds, for every distinct domain
+    trained by some rank this step, the sum of the blocks of the ranks that trained it. Equivalent to the
+    reference's dense all-reduce over all parameters (train_multi.py:579,779-781), whose other entries are zero.
+    """
+    world = dist.get_world_size(group)
+    dist.all_reduce(grad[:shared_size], group=group)
+    updates = []
+    if max_dom_size:
+        send = grad[shared_size:shared_size + max_dom_size]
+        dist.all_gather_into_tensor(gathered.view(-1), send, group=group)
+        first: Dict[str, int] = {}
+        for r, rd in enumerate(rank_domains):
+            if rd is None:
+                continue
+            n_r = dom_range[rd][1]
+            if rd in first:
+                gathered[first[rd], :n_r] += gathered[r, :n_r]
+            else:
+                first[rd] = r
+        for rd, r in first.items():
+            lo, n_r = dom_range[rd]
+            updates.append((lo, n_r, gathered[r, :n_r]))
+    assert len(rank_domains) == world
+    return updates
+
+
 class TrainStep:
     def __init__(self, model, lr: float = 1e-4, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.05,
                  max_grad_norm: Optional[float] = 1.0, process_group=None):
@@ -126,22 +157,8 @@ class TrainStep:
                 gathered: List[Optional[str]] = [None] * self.world
                 dist.all_gather_object(gathered, dom, group=self.pg)
                 rank_domains = gathered
-            dist.all_reduce(g_shared, group=self.pg)
-            if self.arena.max_dom_size:
-                send = self.grad[shared:shared + self.arena.max_dom_size]
-                dist.all_gather_into_tensor(self.gathered.view(-1), send, group=self.pg)
-                first: Dict[str, int] = {}
-                for r, rd in enumerate(rank_domains):
-                    if rd is None:
-                        continue
-                    if rd in first:
-                        n_r = self.arena.dom_range[rd][1]
-                        self.gathered[first[rd], :n_r] += self.gathered[r, :n_r]
-                    else:
-                        first[rd] = r
-                for rd, r in first.items():
-                    lo, n_r = self.arena.dom_range[rd]
-                    updates.append((lo, n_r, self.gathered[r, :n_r]))
+            updates = exchange_gradients(self.grad, shared, self.arena.max_dom_size, self.arena.dom_range, rank_domains,
+                                         self.gathered, self.pg)
         elif dom_n:
             updates.append((dom_lo, dom_n, g_dom))
         if self.max_norm is not None:
