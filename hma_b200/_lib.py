@@ -42,7 +42,7 @@ _SIGNATURES = {
                    c_void_p],
     "hma_rows_scatter": [c_fp, c_fp, c_int, c_int, c_int, c_void_p],
     "hma_ln_bwd": [c_void_p, c_ll, c_fp, c_ll, c_fp, c_int, c_int, c_fp, c_fp, c_int, c_fp, c_ll, c_fp, c_fp, c_fp,
-                   c_void_p],
+                   c_void_p, c_fp, c_void_p],
     "hma_colsum_bf16": [c_void_p, c_ll, c_int, c_int, c_fp, c_void_p],
     "hma_colsum_f32": [c_fp, c_ll, c_int, c_int, c_fp, c_void_p],
     "hma_cast_transpose": [c_fp, c_int, c_int, c_void_p, c_void_p, c_float, c_void_p],

@@ -118,6 +118,8 @@ struct LnBwdParams {
   float* dgamma;  // mode 1: [C] dgamma, [C] dbeta (separate pointers)
   float* dbeta;
   float* dmod;  // mode 2: [groups, 2C] dshift | dscale
+  __nv_bfloat16* dy_next;  // optional: bf16 copy of the updated dx (the next stage's GEMM operand)
+  float* colsum_next;      // optional: += column sums of dy_next (the next stage's bias gradient)
 };
 
 __global__ void __launch_bounds__(256) ln_bwd_kernel(const LnBwdParams p) {
@@ -125,8 +127,9 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const LnBwdParams p) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int r0 = blockIdx.x * p.rows_per_cta;
   float acc_w[8], acc_b[8];  // d(gamma|scale), d(beta|shift) partials for this lane's 8 columns
+  float acc_c[8];            // column sums of the bf16 copy of the new dx
 #pragma unroll
-  for (int j = 0; j < 8; ++j) { acc_w[j] = 0.f; acc_b[j] = 0.f; }
+  for (int j = 0; j < 8; ++j) { acc_w[j] = 0.f; acc_b[j] = 0.f; acc_c[j] = 0.f; }
   float mult[8];
   if (p.mode == 1) {
 #pragma unroll
@@ -161,6 +164,14 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const LnBwdParams p) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) o[j] = dx.v[j] + rstd * (g[j] - s1 - xh[j] * s2);
     store_row_f32(p.dx + (size_t)row * p.lddx, lane, o);
+    if (p.dy_next != nullptr) {
+      const uint2 a = make_uint2(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]));
+      const uint2 b = make_uint2(pack_bf16(o[4], o[5]), pack_bf16(o[6], o[7]));
+      *reinterpret_cast<uint2*>(p.dy_next + (size_t)row * kC + lane * 4) = a;
+      *reinterpret_cast<uint2*>(p.dy_next + (size_t)row * kC + 128 + lane * 4) = b;
+      acc_c[0] += bf16_lo(a.x); acc_c[1] += bf16_hi(a.x); acc_c[2] += bf16_lo(a.y); acc_c[3] += bf16_hi(a.y);
+      acc_c[4] += bf16_lo(b.x); acc_c[5] += bf16_hi(b.x); acc_c[6] += bf16_lo(b.y); acc_c[7] += bf16_hi(b.y);
+    }
   }
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
@@ -177,6 +188,16 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const LnBwdParams p) {
     } else {
       atomicAdd(p.dmod + (size_t)(r0 / p.rows_per_group) * 2 * kC + c, s);
     }
+  }
+  if (p.colsum_next != nullptr) {
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 8; ++j) red[warp][col_of(lane, j)] = acc_c[j];
+    __syncthreads();
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += red[w][threadIdx.x];
+    atomicAdd(p.colsum_next + threadIdx.x, s);
   }
 }
 
@@ -240,7 +261,8 @@ extern "C" int hma_ln_fwd(const float* x, long long ldx, int rows, int mode, con
 
 extern "C" int hma_ln_bwd(const void* dy, long long lddy, const float* x, long long ldx, const float* stats, int rows,
                           int mode, const float* gamma, const float* mod, int rows_per_group, float* dx,
-                          long long lddx, float* dgamma, float* dbeta, float* dmod, void* stream_) {
+                          long long lddx, float* dgamma, float* dbeta, float* dmod, void* dy_next,
+                          float* colsum_next, void* stream_) {
   using namespace hma;
   if (rows == 0) return 0;
   HMA_REQUIRE(mode == 1 || mode == 2, "ln_bwd: bad mode %d", mode);
@@ -250,7 +272,9 @@ extern "C" int hma_ln_bwd(const void* dy, long long lddy, const float* x, long l
   int rpc = 32;
   if (mode == 2 && rows_per_group % 32 != 0) rpc = 16;
   LnBwdParams p{static_cast<const __nv_bfloat16*>(dy), lddy, x, ldx, stats, rows, mode, gamma, mod,
-                rows_per_group > 0 ? rows_per_group : rows, rpc, dx, lddx, dgamma, dbeta, dmod};
+                rows_per_group > 0 ? rows_per_group : rows, rpc, dx, lddx, dgamma, dbeta, dmod,
+                static_cast<__nv_bfloat16*>(dy_next), colsum_next};
+  HMA_REQUIRE(colsum_next == nullptr || dy_next != nullptr, "ln_bwd: colsum_next needs dy_next");
   ln_bwd_kernel<<<(rows + rpc - 1) / rpc, 256, 0, static_cast<cudaStream_t>(stream_)>>>(p);
   HMA_CHECK_CUDA(cudaGetLastError());
   return 0;

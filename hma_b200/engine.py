@@ -140,6 +140,13 @@ class Engine:
         self.cfg = cfg
         self.weights = Weights()
         self._stem_w0: Dict[str, tuple] = {}
+        self._side: Dict[int, torch.cuda.Stream] = {}
+
+    def _side_stream(self, dev) -> "torch.cuda.Stream":
+        idx = dev.index if dev.index is not None else torch.cuda.current_device()
+        if idx not in self._side:
+            self._side[idx] = torch.cuda.Stream(device=idx)
+        return self._side[idx]
 
     # ------------------------------------------------------------------------------------------
     def dims(self, B: int, T: int, S: int, with_actions: bool) -> Dims:
@@ -196,6 +203,31 @@ class Engine:
         E1 = p.get("token_embed.factored_embeds.1.weight") if d.nv == 2 else None
         x = ops.embed_fwd(ids, p["token_embed.factored_embeds.0.weight"], E1, p["token_embed.mask_token_embed"],
                           act if d.A else None, pos, pos_n, B, T, S, d.A, d.vs, d.mask_id)
+        # adaLN_modulation (Linear -> SiLU -> Linear on the [B*T, 256] action embedding) depends only on the
+        # stem output: all layers' shift/scale are produced up-front on a side stream, where these
+        # one-tile GEMMs fill the tails of the main stream's kernels instead of serialising with them.
+        hmods = zmods = mods = None
+        mod_events = []
+        if d.modulate:
+            dev = x.device
+            hmods = torch.empty(d.num_layers, M, C, device=dev, dtype=torch.bfloat16)
+            zmods = torch.empty(d.num_layers, M, C, device=dev, dtype=torch.bfloat16) if training else None
+            mods = torch.empty(d.num_layers, M, 2 * C, device=dev, dtype=torch.float32)
+            main = torch.cuda.current_stream()
+            side = self._side_stream(dev)
+            fork = torch.cuda.Event()
+            fork.record(main)
+            with torch.cuda.stream(side):
+                side.wait_event(fork)
+                for i in range(d.num_layers):
+                    ap = f"decoder.layers.{i}.action_projectors.{dom}."
+                    ops.gemm_nt(c_bf, Wp[ap + "adaLN_modulation.0.weight"], EPI_SILU, bias=p[ap + "adaLN_modulation.0.bias"],
+                                out=hmods[i], out2=zmods[i] if training else None)
+                    ops.gemm_nt(hmods[i], Wp[ap + "adaLN_modulation.2.weight"], EPI_RESID,
+                                bias=p[ap + "adaLN_modulation.2.bias"], out=mods[i])
+                    ev = torch.cuda.Event()
+                    ev.record(side)
+                    mod_events.append(ev)
         layers = []
         for i in range(d.num_layers):
             lp = f"decoder.layers.{i}."
@@ -209,9 +241,9 @@ class Engine:
             # ---- per-layer action conditioning (st_transformer.py:102-104; st_mask_git.py:66-76)
             if d.modulate:
                 ap = lp + f"action_projectors.{dom}."
-                zmod = torch.empty(M, C, device=x.device, dtype=torch.bfloat16) if training else None
-                hmod = ops.gemm_nt(c_bf, Wp[ap + "adaLN_modulation.0.weight"], EPI_SILU, bias=p[ap + "adaLN_modulation.0.bias"], out2=zmod)
-                mod = ops.gemm_nt(hmod, Wp[ap + "adaLN_modulation.2.weight"], EPI_RESID, bias=p[ap + "adaLN_modulation.2.bias"])
+                torch.cuda.current_stream().wait_event(mod_events[i])
+                hmod, mod = hmods[i], mods[i]
+                zmod = zmods[i] if training else None
                 am, stm = ops.ln_fwd(x1, 2, mod=mod, rows_per_group=n, eps=1e-6, want_stats=True)
                 x2 = ops.gemm_nt(am, Wp[ap + "linear_out.weight"], EPI_RESID, bias=p[ap + "linear_out.bias"], resid=x1,
                                  out=None if training else x1)
@@ -312,21 +344,28 @@ class Engine:
         dx = ops.rows_scatter(dxh, M, S, n) if d.A else dxh
         dact = torch.zeros(M, C, device=dev, dtype=torch.float32) if sv["has_actions"] else None
 
+        main = torch.cuda.current_stream()
+        side = self._side_stream(dev)
+        if d.modulate:
+            fork = torch.cuda.Event()
+            fork.record(main)  # dact zero-fill and the gradient buffer memset precede the side-stream chain
+            side.wait_event(fork)
+        dy = None  # bf16 copy of dx whose column sums are already in the consumer's bias gradient
         for i in reversed(range(d.num_layers)):
             L = sv["layers"][i]
             lp = f"decoder.layers.{i}."
             # ---- MLP
-            dy = ops.cast_colsum(dx, g.get(lp + "mlp.fc2.bias"))
+            if dy is None:
+                dy = ops.cast_colsum(dx, g.get(lp + "mlp.fc2.bias"))
             ops.gemm_wgrad(dy, L["h"], g2(lp + "mlp.fc2.weight"))
             dz = ops.gemm_nt(dy, Wt[lp + "mlp.fc2.weight"], EPI_DGELU, aux=L["z"])
             ops.gemm_wgrad(dz, L["a2"], g2(lp + "mlp.fc1.weight"))
             if lp + "mlp.fc1.bias" in g:
                 ops.colsum_bf16(dz, g2(lp + "mlp.fc1.bias"))
             da2 = ops.gemm_nt(dz, Wt[lp + "mlp.fc1.weight"], EPI_BF16)
-            ops.ln_bwd(da2, L["x3"], L["st2"], 1, dx, gamma=p[lp + "norm2.weight"], dgamma=g2(lp + "norm2.weight"),
-                       dbeta=g2(lp + "norm2.bias"))
+            dy = ops.ln_bwd(da2, L["x3"], L["st2"], 1, dx, gamma=p[lp + "norm2.weight"], dgamma=g2(lp + "norm2.weight"),
+                            dbeta=g2(lp + "norm2.bias"), want_next=True, colsum_next=g.get(lp + "temporal_attn.proj.bias"))
             # ---- temporal attention
-            dy = ops.cast_colsum(dx, g.get(lp + "temporal_attn.proj.bias"))
             ops.gemm_wgrad(dy, L["att_t"], g2(lp + "temporal_attn.proj.weight"))
             datt = ops.gemm_nt(dy, Wt[lp + "temporal_attn.proj.weight"], EPI_BF16)
             dqkv = ops.attn_temporal_bwd(L["qkv_t"], L["att_t"], datt, L["lse_t"], B, T, n, d.heads, d.scale)
@@ -341,17 +380,24 @@ class Engine:
                 ops.gemm_wgrad(dy, L["am"], g2(ap + "linear_out.weight"))
                 dam = ops.gemm_nt(dy, Wt[ap + "linear_out.weight"], EPI_BF16)
                 dmod = torch.zeros(M, 2 * C, device=dev, dtype=torch.float32)
-                ops.ln_bwd(dam, L["x1"], L["stm"], 2, dx, mod=L["mod"], rows_per_group=n, dmod=dmod)
-                # adaLN_modulation backward (Linear -> SiLU -> Linear on the [B*T, 256] action embedding)
-                dmod_bf = ops.cast_bf16(dmod)
-                ops.gemm_wgrad(dmod_bf, L["hmod"], g2(ap + "adaLN_modulation.2.weight"))
-                ops.colsum_f32(dmod, g2(ap + "adaLN_modulation.2.bias"))
-                dzm = ops.gemm_nt(dmod_bf, Wt[ap + "adaLN_modulation.2.weight"], EPI_DSILU, aux=L["zmod"])
-                ops.gemm_wgrad(dzm, sv["c_bf"], g2(ap + "adaLN_modulation.0.weight"))
-                ops.colsum_bf16(dzm, g2(ap + "adaLN_modulation.0.bias"))
-                ops.gemm_nt(dzm, Wt[ap + "adaLN_modulation.0.weight"], EPI_RESID, resid=dact, out=dact)
+                dy = ops.ln_bwd(dam, L["x1"], L["stm"], 2, dx, mod=L["mod"], rows_per_group=n, dmod=dmod, want_next=True,
+                                colsum_next=g.get(lp + "spatial_attn.proj.bias"))
+                # adaLN_modulation backward: a chain of one-tile kernels -> side stream
+                ev = torch.cuda.Event()
+                ev.record(main)
+                with torch.cuda.stream(side):
+                    side.wait_event(ev)
+                    dmod_bf = ops.cast_bf16(dmod)
+                    ops.gemm_wgrad(dmod_bf, L["hmod"], g2(ap + "adaLN_modulation.2.weight"))
+                    ops.colsum_f32(dmod, g2(ap + "adaLN_modulation.2.bias"))
+                    dzm = ops.gemm_nt(dmod_bf, Wt[ap + "adaLN_modulation.2.weight"], EPI_DSILU, aux=L["zmod"])
+                    ops.gemm_wgrad(dzm, sv["c_bf"], g2(ap + "adaLN_modulation.0.weight"))
+                    ops.colsum_bf16(dzm, g2(ap + "adaLN_modulation.0.bias"))
+                    ops.gemm_nt(dzm, Wt[ap + "adaLN_modulation.0.weight"], EPI_RESID, resid=dact, out=dact)
+                    dmod.record_stream(side)
+            else:
+                dy = ops.cast_colsum(dx, g.get(lp + "spatial_attn.proj.bias"))
             # ---- spatial attention
-            dy = ops.cast_colsum(dx, g.get(lp + "spatial_attn.proj.bias"))
             ops.gemm_wgrad(dy, L["att_s"], g2(lp + "spatial_attn.proj.weight"))
             datt = ops.gemm_nt(dy, Wt[lp + "spatial_attn.proj.weight"], EPI_BF16)
             dqkv = ops.attn_spatial_bwd(L["qkv_s"], L["att_s"], datt, L["lse"], M, n, d.heads, d.scale)
@@ -359,9 +405,14 @@ class Engine:
             if lp + "spatial_attn.qkv.bias" in g:
                 ops.colsum_bf16(dqkv, g2(lp + "spatial_attn.qkv.bias"))
             da1 = ops.gemm_nt(dqkv, Wt[lp + "spatial_attn.qkv.weight"], EPI_BF16)
-            ops.ln_bwd(da1, L["x0"], L["st1"], 1, dx, gamma=p[lp + "norm1.weight"], dgamma=g2(lp + "norm1.weight"),
-                       dbeta=g2(lp + "norm1.bias"))
+            nxt = f"decoder.layers.{i - 1}.mlp.fc2.bias" if i > 0 else None
+            dy = ops.ln_bwd(da1, L["x0"], L["st1"], 1, dx, gamma=p[lp + "norm1.weight"], dgamma=g2(lp + "norm1.weight"),
+                            dbeta=g2(lp + "norm1.bias"), want_next=i > 0, colsum_next=g.get(nxt) if nxt else None)
             sv["layers"][i] = None  # release this layer's activations
+        if d.modulate:
+            join = torch.cuda.Event()
+            join.record(side)
+            main.wait_event(join)
 
         # ---- embedding / positional / action-token gradients
         ops.embed_bwd(sv["ids"], dx, sv["pos_n"], B, T, S, d.A, d.vs, d.mask_id,

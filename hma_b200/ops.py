@@ -102,9 +102,15 @@ def ln_fwd(x: torch.Tensor, mode: int, *, gamma=None, beta=None, mod=None, rows_
 
 
 def ln_bwd(dy: torch.Tensor, x: torch.Tensor, stats: torch.Tensor, mode: int, dx: torch.Tensor, *, gamma=None,
-           mod=None, rows_per_group: int = 0, dgamma=None, dbeta=None, dmod=None) -> None:
-    _call(f"ln_bwd[mode={mode}]", x.shape[0] * 256 * 14.0, "hma_ln_bwd", dy.data_ptr(), dy.stride(0), x.data_ptr(), x.stride(0), stats.data_ptr(), x.shape[0], mode,
-              _p(gamma), _p(mod), rows_per_group, dx.data_ptr(), dx.stride(0), _p(dgamma), _p(dbeta), _p(dmod), _s())
+           mod=None, rows_per_group: int = 0, dgamma=None, dbeta=None, dmod=None, want_next: bool = False,
+           colsum_next=None):
+    """dx += LN backward; optionally returns bf16(dx) for the next stage and accumulates its column sums."""
+    dy_next = torch.empty(x.shape[0], 256, device=x.device, dtype=BF16) if want_next else None
+    _call(f"ln_bwd[mode={mode}]", x.shape[0] * 256 * (16.0 if want_next else 14.0), "hma_ln_bwd", dy.data_ptr(),
+          dy.stride(0), x.data_ptr(), x.stride(0), stats.data_ptr(), x.shape[0], mode, _p(gamma), _p(mod),
+          rows_per_group, dx.data_ptr(), dx.stride(0), _p(dgamma), _p(dbeta), _p(dmod), _p(dy_next),
+          _p(colsum_next) if want_next else None, _s())
+    return dy_next
 
 
 def colsum_bf16(G: torch.Tensor, out: torch.Tensor) -> None:

@@ -97,10 +97,11 @@ int hma_ln_fwd(const float* x, long long ldx, int rows, int mode, const float* g
 /* dst[(f*n + s), :] = s < S ? src[(f*S + s), :] : 0 — fp32 rows of 256 (inverse of the remap above). */
 int hma_rows_scatter(const float* src, float* dst, int frames, int S, int n, void* stream);
 /* dx (fp32, accumulated in place) += LayerNorm backward of dy (bf16). mode 1 accumulates dgamma/dbeta,
- * mode 2 accumulates dmod [groups, 512] = dshift|dscale. */
+ * mode 2 accumulates dmod [groups, 512] = dshift|dscale. Optionally also writes dy_next = bf16(dx) [rows,256]
+ * and colsum_next[256] += its column sums (operand and bias gradient of the next backward stage). */
 int hma_ln_bwd(const void* dy, long long lddy, const float* x, long long ldx, const float* stats, int rows, int mode,
                const float* gamma, const float* mod, int rows_per_group, float* dx, long long lddx, float* dgamma,
-               float* dbeta, float* dmod, void* stream);
+               float* dbeta, float* dmod, void* dy_next, float* colsum_next, void* stream);
 /* out[C] (fp32) += column sums of G (bias gradients). */
 int hma_colsum_bf16(const void* G, long long ld, int rows, int C, float* out, void* stream);
 int hma_colsum_f32(const float* G, long long ld, int rows, int C, float* out, void* stream);

@@ -98,9 +98,14 @@ def test_ln_fwd_bwd(mode):
     dx0 = dx.clone()
     dgamma, dbeta = torch.zeros(C, device="cuda"), torch.zeros(C, device="cuda")
     dmod = torch.zeros(groups, 2 * C, device="cuda")
+    dyn = torch.zeros(rows, C, device="cuda", dtype=torch.bfloat16)
+    csum = torch.zeros(C, device="cuda")
     _lib.call("hma_ln_bwd", dy.data_ptr(), C, x.data_ptr(), C, stats.data_ptr(), rows, mode, gamma.data_ptr(),
-              mod.data_ptr(), rpg, dx.data_ptr(), C, dgamma.data_ptr(), dbeta.data_ptr(), dmod.data_ptr(), S_())
+              mod.data_ptr(), rpg, dx.data_ptr(), C, dgamma.data_ptr(), dbeta.data_ptr(), dmod.data_ptr(),
+              dyn.data_ptr(), csum.data_ptr(), S_())
     torch.cuda.synchronize()
+    assert torch.equal(dyn, dx.bfloat16())
+    assert relerr(csum, dyn.float().sum(0)) < 1e-3
     ref.backward(dy.float())
     assert relerr(dx - dx0, xr.grad) < 2e-3
     if mode == 1:
