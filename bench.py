@@ -269,6 +269,12 @@ def main() -> None:
         pass
     peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
     peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)"
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_roofline_kernel.json")) as f:
+            traffic = json.load(f).get("traffic_bytes")  # dram read+write of one launch, from the committed ncu capture
+    except Exception:
+        pass
     rec = prof.get(dominant, {"launches": 0, "total_ms": 0.0, "work": 0.0})
     achieved = rec["work"] / (rec["total_ms"] / 1e3) / 1e12 if rec["total_ms"] else 0.0
     step_tf = (B_PER_GPU * train_flops_per_sample() * (args.layers / L)) / (ms_resident / args.steps / 1e3) / 1e12
@@ -289,7 +295,7 @@ def main() -> None:
         "clocks": clocks,
         "roofline": {"bound": "tensor", "kernel": "gemm_nt_kernel<256,GELU,stationary> (MLP fc1: LN2(x) @ W1^T + b1, GELU)",
                      "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf if peak_tf else None,
-                     "traffic": None, "launches_timed": rec["launches"], "avg_launch_us": (rec["total_ms"] / max(rec["launches"], 1)) * 1e3,
+                     "traffic": traffic, "traffic_unit": "bytes/launch (ncu dram read+write)", "launches_timed": rec["launches"], "avg_launch_us": (rec["total_ms"] / max(rec["launches"], 1)) * 1e3,
                      "peak_source": peak_src},
     }
     if not args.no_cpu_baseline and world == 1:
