@@ -1,0 +1,124 @@
+"""Frame-incremental MaskGIT decode: per-layer temporal K/V cache + CUDA-graph replay of the one-frame pass.
+
+The reference's `maskgit_generate` (st_mask_git.py:337-467) re-runs `compute_logits` on the whole
+T-frame window for each of the K MaskGIT steps of each generated frame. Frames before `out_t` cannot
+change during those steps and, the temporal attention being causal (st_transformer.py:111) and the
+spatial attention per-frame, they influence frame `out_t` only through their temporal keys/values.
+A `DecodeSession` therefore
+  * runs the context frames through the network ONCE ("prefill"), keeping every layer's temporal K/V;
+  * runs only the frame being generated for each MaskGIT step ("step": 1/T of the reference's work);
+  * runs a finished frame once more to add its K/V to the cache before the next frame ("commit").
+Same logits as the full-window recompute up to bf16 summation order (tests/test_decode_gpu.py).
+
+A one-frame pass is ~450 launches of a few microseconds each, i.e. CPU-launch-bound, so each
+(frame index, mode) pass is captured once into a CUDA graph and replayed; all buffers a graph touches
+(token ids, K/V cache, per-frame action conditioning, logits) are owned by the session and static.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional, Tuple
+
+import torch
+
+from . import ops
+from .engine import Engine
+
+
+class DecodeSession:
+    def __init__(self, model, B: int, T: int, S: int, dom: Optional[str], d_action: int, device: torch.device,
+                 use_graphs: bool = True):
+        self.model = model
+        self.eng: Engine = model._engine
+        self.B, self.T, self.S, self.dom, self.d_action = B, T, S, dom, d_action
+        self.device = device
+        self.use_graphs = use_graphs
+        cfg = model.config
+        self.d1 = self.eng.dims(B, 1, S, dom is not None)
+        n, L = self.d1.n, cfg.num_layers
+        self.kv = torch.zeros(L, T, B * n, 512, device=device, dtype=torch.bfloat16)
+        self.ids = torch.zeros(B, 1, S, device=device, dtype=torch.long)
+        self.act_tb = self.hmods_tb = self.mods_tb = None
+        if dom is not None:
+            self.act_tb = torch.zeros(T * B, 256, device=device, dtype=torch.float32)
+            if self.d1.modulate:
+                self.hmods_tb = torch.zeros(L, T * B, 256, device=device, dtype=torch.bfloat16)
+                self.mods_tb = torch.zeros(L, T * B, 512, device=device, dtype=torch.float32)
+        self.graphs: Dict[Tuple[int, str], torch.cuda.CUDAGraph] = {}
+        self.outputs: Dict[Tuple[int, str], Optional[torch.Tensor]] = {}
+        self.warm = set()
+        self.pool = None
+        self.filled = 0
+        self._p: Optional[Dict[str, torch.Tensor]] = None
+        self._sig = None
+
+    # ------------------------------------------------------------------------------------------
+    def signature(self, p: Dict[str, torch.Tensor]):
+        """Addresses the captured graphs have baked in (fp32 biases / norms are read in place)."""
+        return tuple(p[k].data_ptr() for k in ("pos_embed_TSC", "out_x_proj.bias", "decoder.layers.0.mlp.fc1.bias")
+                     if k in p)
+
+    def begin(self, p: Dict[str, torch.Tensor], prompt_THW: torch.Tensor, n_ctx: int, actions: Optional[torch.Tensor],
+              skip_normalization: bool) -> None:
+        """Prefill: context frames [0, n_ctx) -> K/V cache; action conditioning of every frame of the window."""
+        eng, B, T, S, dom = self.eng, self.B, self.T, self.S, self.dom
+        sig = self.signature(p)
+        if sig != self._sig:  # parameters were re-allocated: captured graphs point at dead memory
+            self.graphs.clear()
+            self.outputs.clear()
+            self._sig = sig
+        self._p = p
+        dp = eng.dims(B, n_ctx, S, dom is not None)
+        ids = prompt_THW[:, :n_ctx].reshape(B, n_ctx, S).contiguous()
+        a_ctx = actions[:, :n_ctx].contiguous() if actions is not None else None
+        eng.forward(p, ids, a_ctx, dom, dp, False, skip_normalization, t0=0, kv=self.kv, mode="prefill")
+        self.filled = n_ctx
+        if dom is not None:
+            a_tb = actions.transpose(0, 1).reshape(T * B, -1).to(torch.float32).contiguous()  # (t, b) row order
+            act, c_bf = eng.action_stem(p, a_tb, dom, skip_normalization)
+            self.act_tb.copy_(act)
+            if self.d1.modulate:
+                eng.modulation_all_layers(p, c_bf, dom, self.d1.num_layers, False, hmods=self.hmods_tb, mods=self.mods_tb)
+
+    def _cond(self, t: int):
+        if self.dom is None:
+            return None
+        B = self.B
+        act = self.act_tb[t * B:(t + 1) * B]
+        mods = self.mods_tb[:, t * B:(t + 1) * B] if self.mods_tb is not None else None
+        return (act, mods)
+
+    def _run(self, t: int, mode: str):
+        logits, _ = self.eng.forward(self._p, self.ids, None, self.dom, self.d1, False, t0=t, kv=self.kv, mode=mode,
+                                     frame_cond=self._cond(t))
+        return logits
+
+    def _pass(self, frame_ids: torch.Tensor, t: int, mode: str) -> Optional[torch.Tensor]:
+        assert t == self.filled, f"decode session holds {self.filled} frames of context, asked for frame {t}"
+        self.ids.copy_(frame_ids.reshape(self.B, 1, self.S))
+        key = (t, mode)
+        if not self.use_graphs:
+            return self._run(t, mode)
+        if mode not in self.warm:  # first use of a mode: run eagerly (lazy one-time kernel attributes, caches)
+            self.warm.add(mode)
+            return self._run(t, mode)
+        g = self.graphs.get(key)
+        if g is None:
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            if self.pool is None:
+                self.pool = torch.cuda.graph_pool_handle()
+            with torch.cuda.graph(g, pool=self.pool):
+                out = self._run(t, mode)
+            self.graphs[key] = g
+            self.outputs[key] = out  # keeps the graph's output block alive (other graphs share the pool)
+        g.replay()
+        return self.outputs[key]
+
+    def step(self, frame_ids: torch.Tensor, t: int) -> torch.Tensor:
+        """Logits fp32 [B*S, nv*vs] of window frame t given the cached context (valid until the next pass)."""
+        return self._pass(frame_ids, t, "step")
+
+    def commit(self, frame_ids: torch.Tensor, t: int) -> None:
+        """Add finished frame t to the context."""
+        self._pass(frame_ids, t, "commit")
+        self.filled = t + 1

@@ -175,31 +175,81 @@ class Engine:
                 self._stem_w0[key] = (w0._version, ops.action_prep(w0.detach().contiguous(), stem_pad(w0.shape[1])))
 
     # ------------------------------------------------------------------------------------------
+    def action_stem(self, p: Dict[str, Tensor], a2d: Tensor, dom: str, skip_normalization: bool, sv: Optional[dict] = None):
+        """ActionStat + BasicMLP (st_mask_git.py:645-649) on rows [rows, d_a] -> (act fp32 [rows,256], bf16 copy)."""
+        Wp = self.weights.plain
+        da = a2d.shape[1]
+        mean = std = None
+        if not skip_normalization:
+            mean, std = p[f"action_preprocessor.{dom}.mean"], p[f"action_preprocessor.{dom}.std"]
+        q = f"action_mlp.{dom}.model."
+        a_prep = ops.action_prep(a2d, stem_pad(da), mean, std)
+        h1 = ops.gemm_nt(a_prep, self._stem_w0[q + "0.weight"][1], EPI_RESID, bias=p[q + "0.bias"])
+        h1n, st_stem = ops.ln_relu_fwd(h1, p[q + "1.weight"], p[q + "1.bias"])
+        act = ops.gemm_nt(h1n, Wp[q + "3.weight"], EPI_RESID, bias=p[q + "3.bias"])
+        c_bf = ops.ln_fwd(act, 0)
+        if sv is not None:
+            sv.update(a_prep=a_prep, h1=h1, h1n=h1n, st_stem=st_stem, c_bf=c_bf, da=da)
+        return act, c_bf
+
+    def modulation_all_layers(self, p: Dict[str, Tensor], c_bf: Tensor, dom: str, num_layers: int, want_z: bool,
+                              hmods: Optional[Tensor] = None, mods: Optional[Tensor] = None):
+        """adaLN_modulation (Linear -> SiLU -> Linear, st_mask_git.py:61-63,70) of every layer for rows c_bf.
+        Runs on the caller's current stream. Returns (hmods bf16 [L,rows,256], zmods or None, mods fp32 [L,rows,512])."""
+        Wp = self.weights.plain
+        rows, dev = c_bf.shape[0], c_bf.device
+        if hmods is None:
+            hmods = torch.empty(num_layers, rows, C, device=dev, dtype=torch.bfloat16)
+        zmods = torch.empty(num_layers, rows, C, device=dev, dtype=torch.bfloat16) if want_z else None
+        if mods is None:
+            mods = torch.empty(num_layers, rows, 2 * C, device=dev, dtype=torch.float32)
+        events = []
+        for i in range(num_layers):
+            ap = f"decoder.layers.{i}.action_projectors.{dom}."
+            ops.gemm_nt(c_bf, Wp[ap + "adaLN_modulation.0.weight"], EPI_SILU, bias=p[ap + "adaLN_modulation.0.bias"],
+                        out=hmods[i], out2=zmods[i] if want_z else None)
+            ops.gemm_nt(hmods[i], Wp[ap + "adaLN_modulation.2.weight"], EPI_RESID,
+                        bias=p[ap + "adaLN_modulation.2.bias"], out=mods[i])
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream())
+            events.append(ev)
+        return hmods, zmods, mods, events
+
+    def prepare_weights(self, p: Dict[str, Tensor], d: Dims, dom: Optional[str], training: bool) -> None:
+        self._prepare(p, d, dom, training)
+
     def forward(self, p: Dict[str, Tensor], ids: Tensor, actions: Optional[Tensor], dom: Optional[str], d: Dims,
-                training: bool, skip_normalization: bool = False):
-        """ids: i64 [B, T, S] (contiguous). Returns (logits fp32 [B*T*S, nv*vs], saved or None)."""
+                training: bool, skip_normalization: bool = False, *, t0: int = 0, kv=None, mode: str = "full",
+                frame_cond=None):
+        """ids: i64 [B, T, S] (contiguous). Returns (logits fp32 [B*T*S, nv*vs], saved or None).
+
+        Frame-incremental decode (inference only; `kv` = per-layer K/V cache tensors [Tmax, B*n, 512]):
+          mode "prefill": the T frames given are frames [t0, t0+T) of the window; their temporal K/V are
+                          appended to the cache; no head (returns None logits).
+          mode "step"   : T == 1, the frame is window frame t0; temporal attention reads cache frames [0, t0).
+          mode "commit" : as "step", but appends this frame's K/V to the cache and skips everything after
+                          the last layer's temporal K/V (no logits).
+        `frame_cond` (step/commit): precomputed (act fp32 [B,256] or None, mods fp32 [L,B,512] or None) of the frame,
+        replacing the action stem + adaLN chain. `actions`, if given, must hold exactly the T frames computed."""
+        assert mode in ("full", "prefill", "step", "commit")
+        assert mode == "full" or (not training and kv is not None)
         W = self.weights
-        self._prepare(p, d, dom if actions is not None else None, training)
+        has_act = actions is not None or frame_cond is not None
+        if frame_cond is None:
+            self._prepare(p, d, dom if actions is not None else None, training)
         Wp, sv = W.plain, {}
         B, T, S, n, M, N = d.B, d.T, d.S, d.n, d.M, d.N
         act = c_bf = None
-        if actions is not None:
-            # action stem: ActionStat + BasicMLP (st_mask_git.py:645-649)
+        if frame_cond is not None:
+            assert mode in ("step", "commit") and T == 1
+            act = frame_cond[0]
+        elif actions is not None:
             a2d = actions.reshape(M, -1).to(torch.float32).contiguous()
-            da = a2d.shape[1]
-            mean = std = None
-            if not skip_normalization:
-                mean, std = p[f"action_preprocessor.{dom}.mean"], p[f"action_preprocessor.{dom}.std"]
-            q = f"action_mlp.{dom}.model."
-            a_prep = ops.action_prep(a2d, stem_pad(da), mean, std)
-            h1 = ops.gemm_nt(a_prep, self._stem_w0[q + "0.weight"][1], EPI_RESID, bias=p[q + "0.bias"])
-            h1n, st_stem = ops.ln_relu_fwd(h1, p[q + "1.weight"], p[q + "1.bias"])
-            act = ops.gemm_nt(h1n, Wp[q + "3.weight"], EPI_RESID, bias=p[q + "3.bias"])
-            c_bf = ops.ln_fwd(act, 0)
-            if training:
-                sv.update(a_prep=a_prep, h1=h1, h1n=h1n, st_stem=st_stem, c_bf=c_bf, da=da)
+            act, c_bf = self.action_stem(p, a2d, dom, skip_normalization, sv if training else None)
         pos = p["pos_embed_TSC"]
         pos_n = pos.shape[2]
+        if t0:
+            pos = pos[:, t0:]
         E1 = p.get("token_embed.factored_embeds.1.weight") if d.nv == 2 else None
         x = ops.embed_fwd(ids, p["token_embed.factored_embeds.0.weight"], E1, p["token_embed.mask_token_embed"],
                           act if d.A else None, pos, pos_n, B, T, S, d.A, d.vs, d.mask_id)
@@ -208,26 +258,16 @@ class Engine:
         # one-tile GEMMs fill the tails of the main stream's kernels instead of serialising with them.
         hmods = zmods = mods = None
         mod_events = []
-        if d.modulate:
-            dev = x.device
-            hmods = torch.empty(d.num_layers, M, C, device=dev, dtype=torch.bfloat16)
-            zmods = torch.empty(d.num_layers, M, C, device=dev, dtype=torch.bfloat16) if training else None
-            mods = torch.empty(d.num_layers, M, 2 * C, device=dev, dtype=torch.float32)
+        if d.modulate and frame_cond is not None:
+            mods = frame_cond[1]
+        elif d.modulate:
             main = torch.cuda.current_stream()
-            side = self._side_stream(dev)
+            side = self._side_stream(x.device)
             fork = torch.cuda.Event()
             fork.record(main)
             with torch.cuda.stream(side):
                 side.wait_event(fork)
-                for i in range(d.num_layers):
-                    ap = f"decoder.layers.{i}.action_projectors.{dom}."
-                    ops.gemm_nt(c_bf, Wp[ap + "adaLN_modulation.0.weight"], EPI_SILU, bias=p[ap + "adaLN_modulation.0.bias"],
-                                out=hmods[i], out2=zmods[i] if training else None)
-                    ops.gemm_nt(hmods[i], Wp[ap + "adaLN_modulation.2.weight"], EPI_RESID,
-                                bias=p[ap + "adaLN_modulation.2.bias"], out=mods[i])
-                    ev = torch.cuda.Event()
-                    ev.record(side)
-                    mod_events.append(ev)
+                hmods, zmods, mods, mod_events = self.modulation_all_layers(p, c_bf, dom, d.num_layers, training)
         layers = []
         for i in range(d.num_layers):
             lp = f"decoder.layers.{i}."
@@ -241,8 +281,10 @@ class Engine:
             # ---- per-layer action conditioning (st_transformer.py:102-104; st_mask_git.py:66-76)
             if d.modulate:
                 ap = lp + f"action_projectors.{dom}."
-                torch.cuda.current_stream().wait_event(mod_events[i])
-                hmod, mod = hmods[i], mods[i]
+                if mod_events:
+                    torch.cuda.current_stream().wait_event(mod_events[i])
+                mod = mods[i]
+                hmod = hmods[i] if training else None
                 zmod = zmods[i] if training else None
                 am, stm = ops.ln_fwd(x1, 2, mod=mod, rows_per_group=n, eps=1e-6, want_stats=True)
                 x2 = ops.gemm_nt(am, Wp[ap + "linear_out.weight"], EPI_RESID, bias=p[ap + "linear_out.bias"], resid=x1,
@@ -254,7 +296,15 @@ class Engine:
             # ---- causal temporal attention, no pre-norm (st_transformer.py:111)
             at = ops.ln_fwd(x2, 0)
             qkv_t = ops.gemm_nt(at, Wp[lp + "temporal_attn.qkv.weight"], EPI_BF16, bias=p.get(lp + "temporal_attn.qkv.bias"))
-            att_t, lse_t = ops.attn_temporal_fwd(qkv_t, B, T, n, d.heads, d.scale, want_lse=training)
+            if mode in ("step", "commit"):
+                lse_t = None
+                att_t = ops.attn_temporal_cached(qkv_t, kv[i], t0, d.heads, d.scale)
+            else:
+                att_t, lse_t = ops.attn_temporal_fwd(qkv_t, B, T, n, d.heads, d.scale, want_lse=training)
+            if mode in ("prefill", "commit"):
+                ops.kv_cache_append(qkv_t, B, T, n, kv[i], t0)
+                if i == d.num_layers - 1:
+                    return None, None  # nothing downstream of the last layer's K/V is needed
             x3 = ops.gemm_nt(att_t, Wp[lp + "temporal_attn.proj.weight"], EPI_RESID, bias=p.get(lp + "temporal_attn.proj.bias"),
                              resid=x2, out=None if training else x2)
             # ---- MLP, pre-norm, erf-GELU (st_transformer.py:24-27,112)

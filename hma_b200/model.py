@@ -150,6 +150,11 @@ class _ForwardLoss(torch.autograd.Function):
 
 
 class STMaskGIT(nn.Module, PyTorchModelHubMixin):
+    # "incremental": frame-incremental decode with a temporal K/V cache (hma_b200/decode.py);
+    # "full": the reference algorithm (whole-window compute_logits per MaskGIT step, st_mask_git.py:384,394)
+    decode_algorithm = "incremental"
+    decode_cuda_graphs = True
+
     def __init__(self, config: GenieConfig):
         super().__init__()
         self.h = self.w = math.isqrt(config.S)
@@ -165,6 +170,7 @@ class STMaskGIT(nn.Module, PyTorchModelHubMixin):
         self.config = config
         self.action_mask_tokens = nn.Parameter(torch.zeros(1, config.T, 1, config.d_model))
         self._engine = Engine(config)
+        self._sessions = {}
         if (config.init_actions or config.use_actions) and config.action_domains is not None:
             self.init_action_projectors(config.action_domains, config.d_actions, config.action_stats, config.action_network)
 
@@ -289,6 +295,26 @@ class STMaskGIT(nn.Module, PyTorchModelHubMixin):
     def init_mask(self, prompt_THW, t=1):
         return torch.zeros(prompt_THW.size(0), t * self.seq_len, dtype=torch.bool, device=prompt_THW.device)
 
+    # ---------------------------------------------------------------- frame-incremental decode state
+    def _decode_session(self, prompt_THW, n_ctx: int, action_ids, domain, kwargs):
+        """A DecodeSession for this window shape with frames [0, n_ctx) of `prompt_THW` prefilled."""
+        from .decode import DecodeSession
+        B, T, H, W = prompt_THW.shape
+        dom = self._domain0(domain, action_ids)
+        if action_ids is not None:
+            assert action_ids.shape[1] == T, "action_ids must provide one action vector per frame"
+        key = (B, T, H * W, dom, action_ids.shape[-1] if action_ids is not None else 0, prompt_THW.device,
+               self.decode_cuda_graphs)
+        sess = self._sessions.get(key)
+        if sess is None:
+            self._sessions.clear()  # one live session: its K/V cache is the large allocation
+            sess = DecodeSession(self, B, T, H * W, dom, key[4], prompt_THW.device, use_graphs=self.decode_cuda_graphs)
+            self._sessions[key] = sess
+        p = self._buffers_dict()
+        p.update({k: v.detach() for k, v in self.named_parameters()})
+        sess.begin(p, prompt_THW, n_ctx, action_ids, kwargs.get("skip_normalization", False))
+        return sess
+
     # ---------------------------------------------------------------- st_mask_git.py:337-467
     @torch.no_grad()
     def maskgit_generate(self, prompt_THW: torch.LongTensor, out_t: int, maskgit_steps: int = 1, temperature: float = 0.0,
@@ -309,9 +335,16 @@ class STMaskGIT(nn.Module, PyTorchModelHubMixin):
         unmasked = torch.zeros(B, S, dtype=torch.uint8, device=prompt_THW.device)
         orig_logits = None
         samples = None
+        session = kwargs.pop("_session", None)
+        if session is None and self.decode_algorithm == "incremental":
+            session = self._decode_session(prompt_THW, out_t, action_ids, domain, kwargs)
         for step in range(maskgit_steps):
-            logits, _ = self._logits_nograd(prompt_THW, action_ids, domain, kwargs)
-            lf = logits.view(B, T, S, nv * vs)[:, out_t]  # strided view of frame out_t
+            if session is not None:
+                logits = session.step(frame, out_t)  # only frame out_t runs; context comes from the K/V cache
+                lf = logits.view(B, S, nv * vs)
+            else:
+                logits, _ = self._logits_nograd(prompt_THW, action_ids, domain, kwargs)
+                lf = logits.view(B, T, S, nv * vs)[:, out_t]  # strided view of frame out_t
             if orig_logits is None:
                 orig_logits = lf.clone()
             noise = None
@@ -351,11 +384,18 @@ class STMaskGIT(nn.Module, PyTorchModelHubMixin):
         full = torch.cat([inputs, torch.full((B, n_new, h, w), self.mask_token_id, dtype=torch.long,
                                              device=input_ids.device)], dim=1).contiguous()
         all_logits = []
+        session = None
+        if self.decode_algorithm == "incremental" and n_new > 0:
+            self._require_cuda(input_ids)
+            session = self._decode_session(full, inputs.size(1), action_ids, domain, kwargs)
+        last = inputs.size(1) + n_new - 1
         for t in range(inputs.size(1), inputs.size(1) + n_new):
             sample_HW, fl, _ = self.maskgit_generate(full, t, maskgit_steps=maskgit_steps, temperature=temperature,
-                                                     action_ids=action_ids, domain=domain, **kwargs)
+                                                     action_ids=action_ids, domain=domain, _session=session, **kwargs)
             full[:, t] = sample_HW
             all_logits.append(fl)
+            if session is not None and t != last:
+                session.commit(full[:, t], t)  # the finished frame joins the context of the next one
         tokens = full.reshape(B, -1)
         if return_logits:
             return tokens, torch.stack(all_logits, dim=3)

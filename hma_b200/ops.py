@@ -218,6 +218,27 @@ def attn_temporal_bwd(qkv, out, dout, lse, B: int, T: int, n: int, heads: int, s
     return dqkv
 
 
+def kv_cache_append(qkv: torch.Tensor, B: int, frames: int, n: int, kv: torch.Tensor, t0: int) -> None:
+    """K/V columns of `frames` frames of qkv ((b, t, s) order, [B*frames*n, 768]) -> cache frames [t0, t0+frames).
+    kv: bf16 [Tmax, B*n, 512]."""
+    C = 256
+    assert kv.dtype == BF16 and kv.shape[1] == B * n and kv.shape[2] == 2 * C and kv.is_contiguous()
+    assert t0 + frames <= kv.shape[0]
+    _call("kv_cache_append", B * frames * n * 2 * C * 4.0, "hma_kv_cache_append", qkv.data_ptr(), qkv.stride(0), C, 2 * C,
+          B, frames, n, kv.data_ptr(), kv.stride(0), t0, _s())
+
+
+def attn_temporal_cached(qkv: torch.Tensor, kv: Optional[torch.Tensor], n_prev: int, heads: int, scale: float) -> torch.Tensor:
+    """Temporal attention of ONE frame ([B*n, 768] q|k|v) over cache frames [0, n_prev) + itself."""
+    C = heads * 32
+    rows = qkv.shape[0]
+    out = torch.empty(rows, C, device=qkv.device, dtype=BF16)
+    _call("attn_temporal_cached", rows * C * 2.0 * (2 * n_prev + 4), "hma_attn_temporal_cached", qkv.data_ptr(), qkv.stride(0),
+          0, C, 2 * C, _p(kv) if n_prev else None, kv.stride(0) if kv is not None else 0, rows, n_prev, heads, float(scale),
+          out.data_ptr(), C, _s())
+    return out
+
+
 def embed_fwd(ids, E0, E1, mask_embed, act, pos, pos_n: int, B: int, T: int, S: int, A: int, vs: int, mask_id: int):
     x = torch.empty(B * T * (S + A), 256, device=ids.device, dtype=F32)
     _call("embed_fwd", B * T * (S + A) * 256 * 8.0, "hma_embed_fwd", ids.data_ptr(), E0.data_ptr(), _p(E1), mask_embed.data_ptr(), _p(act), pos.data_ptr(),

@@ -82,6 +82,18 @@ int hma_attn_temporal_bwd(const void* qkv, long long ld_qkv, const void* out, lo
                           long long ld_dout, const float* lse, int B, int T, int n, int heads, int q_col, int k_col,
                           int v_col, float scale, void* dqkv, long long ld_dqkv, void* stream);
 
+/* Frame-incremental MaskGIT decode (replaces the full-window recompute of st_mask_git.py:384,394 for
+ * the frames that cannot change; same results because st_transformer.py:111 is causal).
+ * kv cache: bf16, frame f at kv + f*frame_stride, token (b, s) at row b*n + s of [B*n, 512] = K | V.
+ * hma_kv_cache_append copies the K/V columns of `frames` frames of a (b, t, s)-ordered qkv matrix into
+ * cache frames [t0, t0+frames). hma_attn_temporal_cached: qkv holds ONE frame ([rows = B*n, ld_qkv]);
+ * each token attends to the cached K/V of its slot in frames [0, n_prev) and to its own K/V. 8 heads x 32. */
+int hma_kv_cache_append(const void* qkv, long long ld_qkv, int k_col, int v_col, int B, int frames, int n, void* kv,
+                        long long frame_stride, int t0, void* stream);
+int hma_attn_temporal_cached(const void* qkv, long long ld_qkv, int q_col, int k_col, int v_col, const void* kv,
+                             long long frame_stride, int rows, int n_prev, int heads, float scale, void* out,
+                             long long ldo, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Row-wise stages (d_model = 256): fp32 residual stream -> bf16 operand
  * ------------------------------------------------------------------------------------------- */

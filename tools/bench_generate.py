@@ -16,6 +16,8 @@ def main():
     ap.add_argument("--layers", type=int, default=32)
     ap.add_argument("--domains", type=int, default=4)
     ap.add_argument("--temperature", type=float, default=1.0)
+    ap.add_argument("--algorithm", default="incremental", choices=["incremental", "full"])
+    ap.add_argument("--no-graphs", action="store_true")
     args = ap.parse_args()
     from hma_b200 import GenieConfig, STMaskGIT
     dev = torch.device("cuda", 0)
@@ -34,6 +36,8 @@ def main():
             if p.dim() >= 2:
                 p.normal_(0.0, 0.02)
     model.eval()
+    model.decode_algorithm = args.algorithm
+    model.decode_cuda_graphs = not args.no_graphs
     g = torch.Generator().manual_seed(1234)
     prompt = torch.randint(0, 262144, (args.batch, Tp * S), generator=g).to(dev)
     actions = torch.randn(args.batch, T, d_actions[1], generator=g).to(dev)
@@ -41,7 +45,7 @@ def main():
     def run():
         return model.generate(prompt, None, (T - Tp) * S, maskgit_steps=args.steps_k, temperature=args.temperature,
                               action_ids=actions, domain=dom, h=[16], w=[16])
-    run(); torch.cuda.synchronize()
+    run(); run(); torch.cuda.synchronize()  # eager warm-up pass, then graph capture
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.reps):
@@ -52,7 +56,8 @@ def main():
     print(json.dumps({"metric": "maskgit_generated_frames_per_s", "value": frames / (ms / 1e3), "unit": "frames/s",
                       "ms_per_generate_call": ms, "config": {"workload": "HMA-MagVit 32L generate: 8 prompt -> 8 new frames, "
                       "16x16 tokens", "batch": args.batch, "maskgit_steps": args.steps_k, "temperature": args.temperature,
-                      "layers": args.layers, "algorithm": getattr(model, "decode_algorithm", "full-window recompute (reference algorithm)")},
+                      "layers": args.layers, "algorithm": ("frame-incremental, temporal K/V cache" + ("" if args.no_graphs else " + CUDA graphs"))
+                      if args.algorithm == "incremental" else "full-window recompute (reference algorithm)"},
                       "all_unmasked": bool((toks != 262144).all().item())}))
 
 if __name__ == "__main__":
