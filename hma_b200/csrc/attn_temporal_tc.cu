@@ -1,38 +1,47 @@
 // Causal attention over the T frames of each spatial slot on the tensor cores
-// (reference: attention.py:37-61 with causal=True, called from st_transformer.py:111).
+// (reference: attention.py:37-61 with causal=True, called from st_transformer.py:111), forward and
+// backward, reading the (B, T, n, 3C) activation in place: the "(B T) S C -> (B S) T C" transposes of
+// the reference (st_transformer.py:89,113) never happen.
 //
-// The sequences are tiny (T <= 128, head_dim 32), so SC = floor(128 / T) of them are packed into one
-// 128-row tile: a 3-D TMA box {32 channels, SC slots, T frames} lifts q / k / v of one head for SC
-// consecutive slots of one sample straight out of the (B, T, n, 3C) activation — row r of the tile is
-// (frame r / SC, slot r % SC), so the "(B T) S C -> (B S) T C" transposes of the reference
-// (st_transformer.py:89,113) never happen. S = Q K^T is one 128x128x32 tcgen05.mma; the softmax
-// warps apply the block-diagonal causal mask (same slot, earlier-or-equal frame) from a per-row
-// 128-bit mask, write P (bf16, 128-byte swizzle) and the P V product runs on the tensor core again.
-// Seven eighths of S is masked away, which is irrelevant: the stage is bound by the bytes of qkv.
-//
-// The backward has the same shape as the spatial one with a single (key tile, query tile) pair.
+// The sequences are tiny (T <= 128, head_dim 32) and the stage is bound by the bytes of qkv, so the
+// design is about keeping HBM busy, not the tensor core:
+//   * work unit = (sample, SC consecutive slots, head). Tp = T rounded up to a power of two, SC = 128 / Tp.
+//     ONE 3-D TMA box {32 channels, Tp frames, SC slots} per operand lifts q / k / v of the unit out of the
+//     activation as a 128-row tile in SLOT-MAJOR order (row = slot * Tp + frame): the score matrix
+//     S = Q K^T (one 128x128x32 tcgen05.mma) is then block diagonal with Tp x Tp causal blocks, and a
+//     softmax thread only touches the <= 32 columns of its own block (rows of padding frames / slots
+//     beyond n are computed on zero-filled or foreign-but-finite data and never stored).
+//   * persistent CTAs (one per SM) stream the units through a 4-stage (fwd) / 3-stage (bwd) TMA ring;
+//     two softmax warpgroups alternate units, each with its own TMEM accumulators and P (/dS) tiles,
+//     so the loads, the S contraction, the softmax, the P V contraction and the stores of neighbouring
+//     units overlap.
+//   * P tiles are zeroed once: a thread always writes the same columns of its row, everything else
+//     stays zero for the life of the CTA.
+// Backward recomputes the softmax of the (<= 128-key) row from S, so it needs neither the forward
+// output nor its log-sum-exp: delta = sum_j P_j dP_j is taken from the same registers.
 #include "common.cuh"
 #include "../../include/hma_b200.h"
 
 namespace hma {
 
 struct TemporalTcParams {
-  int B, T, n, heads, SC;
+  int B, T, Tp, n, heads, SC;
+  int chunks, units;
   int q_col, k_col, v_col;
   float scale, scale_log2;
   __nv_bfloat16* out;           // fwd: [tokens, ldo]
-  const __nv_bfloat16* out_c;   // bwd: forward output
   long long ldo;
-  float* lse;                   // [tokens, heads], log2 domain (fwd: optional output, bwd: input)
-  const __nv_bfloat16* dout;    // bwd
-  long long ld_dout;
+  float* lse;                   // fwd: optional [tokens, heads], log2 domain
   __nv_bfloat16* dqkv;          // bwd
   long long ld_dqkv;
 };
 
 constexpr int kTRowB = 64;
 constexpr int kTTile = 128 * kTRowB;   // 8 KB per operand tile
-constexpr int kTPanel = 128 * 128;     // [128 x 64] bf16 panel
+constexpr int kTPanel = 128 * 128;     // [128 x 64] bf16 panel (16 KB); a P / dS tile is two panels
+constexpr int kFwdStages = 4;
+constexpr int kBwdStages = 3;
+constexpr int kGroupThreads = 128;
 
 __device__ __forceinline__ uint64_t tdesc_sw64(uint32_t saddr) {
   uint64_t d = 0;
@@ -44,330 +53,448 @@ __device__ __forceinline__ uint64_t tdesc_sw64(uint32_t saddr) {
   return d;
 }
 
-// 128-bit column mask of tile row r: bit c set iff column c is (same slot, frame <= frame of r)
-__device__ __forceinline__ void row_mask(int r, int SC, int R, uint32_t (&m)[4]) {
-  m[0] = m[1] = m[2] = m[3] = 0u;
-  if (r >= R) return;
-  const int sl = r % SC, t = r / SC;
-  for (int tp = 0; tp <= t; ++tp) {
-    const int c = tp * SC + sl;
-    m[c >> 5] |= 1u << (c & 31);
+struct UnitCoord {
+  int b, s0, head;
+};
+__device__ __forceinline__ UnitCoord unit_coord(const TemporalTcParams& p, int u) {
+  UnitCoord c;
+  c.head = u % p.heads;
+  const int r = u / p.heads;
+  c.s0 = (r % p.chunks) * p.SC;
+  c.b = r / p.chunks;
+  return c;
+}
+
+// What a softmax thread needs to know about its tile row.
+struct RowInfo {
+  int row, quarter;
+  int sl, t;          // slot inside the unit, frame
+  int off;            // first column of this row's block inside its 32-column chunk
+  int nch;            // 32-column chunks per block (1 unless Tp > 32)
+  uint32_t col0;      // first TMEM / P column of the row's chunk 0 (warp-uniform)
+  bool frame_ok;      // t < T
+};
+__device__ __forceinline__ RowInfo row_info(const TemporalTcParams& p, int warp_in_group, int lane) {
+  RowInfo r;
+  r.quarter = warp_in_group;
+  r.row = warp_in_group * 32 + lane;
+  r.sl = r.row / p.Tp;
+  r.t = r.row % p.Tp;
+  if (p.Tp <= 32) {
+    r.off = (lane / p.Tp) * p.Tp;
+    r.nch = 1;
+    r.col0 = (uint32_t)warp_in_group * 32u;
+  } else {
+    r.off = 0;
+    r.nch = p.Tp / 32;
+    r.col0 = (uint32_t)(r.sl * p.Tp);
+  }
+  r.frame_ok = r.t < p.T;
+  return r;
+}
+// bit b of chunk j is set iff column (col0 + 32 j + b) is a key this row attends to (same slot, frame <= t)
+__device__ __forceinline__ uint32_t chunk_mask(const RowInfo& r, int j) {
+  if (!r.frame_ok) return 0u;  // padding rows attend to nothing: P = dS = 0, so they add nothing to dK / dV
+  const int cnt = r.t - 32 * j + 1;
+  if (cnt <= 0) return 0u;
+  const uint32_t m = cnt >= 32 ? 0xffffffffu : ((1u << cnt) - 1u);
+  return m << r.off;
+}
+
+__device__ __forceinline__ void store_p_chunk(uint32_t tile, int row, uint32_t col, const uint32_t (&pk)[16]) {
+  const uint32_t panel = tile + (col >> 6) * kTPanel;
+  const uint32_t c0 = col & 63u;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const uint32_t addr = panel + sw128_offset((uint32_t)row, c0 + q * 8);
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[4 * q]), "r"(pk[4 * q + 1]),
+                 "r"(pk[4 * q + 2]), "r"(pk[4 * q + 3]) : "memory");
   }
 }
 
-__device__ __forceinline__ void zero_tail_rows(uint32_t tile, int R, int tid, int nthreads) {
-  // rows [R, 128) of a [128 x 64 B] tile are never written by the TMA box: clear them (16 B per store)
-  const int vecs = (128 - R) * 4;
-  for (int i = tid; i < vecs; i += nthreads)
-    asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(tile + (uint32_t)R * kTRowB + (uint32_t)i * 16), "r"(0u) : "memory");
+__device__ __forceinline__ void store_row32_bf16(__nv_bfloat16* dst, const uint32_t (&r)[32], float mul) {
+  uint4* d4 = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+    d4[q] = make_uint4(pack_bf16(__uint_as_float(r[8 * q]) * mul, __uint_as_float(r[8 * q + 1]) * mul),
+                       pack_bf16(__uint_as_float(r[8 * q + 2]) * mul, __uint_as_float(r[8 * q + 3]) * mul),
+                       pack_bf16(__uint_as_float(r[8 * q + 4]) * mul, __uint_as_float(r[8 * q + 5]) * mul),
+                       pack_bf16(__uint_as_float(r[8 * q + 6]) * mul, __uint_as_float(r[8 * q + 7]) * mul));
+}
+
+__device__ __forceinline__ void zero_smem(uint32_t addr, int bytes, int tid, int nthreads) {
+  for (int i = tid * 16; i < bytes; i += nthreads * 16)
+    asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(addr + (uint32_t)i), "r"(0u) : "memory");
 }
 
 // ------------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(160, 4)
+__global__ void __launch_bounds__(320, 1)
 attn_temporal_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const TemporalTcParams p) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t bar_load, bar_s, bar_p, bar_o;
+  __shared__ __align__(8) uint64_t bar_full[kFwdStages], bar_empty[kFwdStages], bar_s[2], bar_p[2], bar_o[2], bar_ofree[2];
   __shared__ uint32_t tmem_base_slot;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t sQ = smem_base, sK = sQ + kTTile, sV = sK + kTTile, sP = sV + kTTile + 1024 * 0;  // 24 KB: aligned
+  const uint32_t sStage = smem_base;                              // kFwdStages x {Q, K, V}
+  const uint32_t sP = sStage + kFwdStages * 3 * kTTile;           // 2 x [128 x 128] bf16
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int chunks = (p.n + p.SC - 1) / p.SC;
-  const int head = blockIdx.x % p.heads;
-  const int chunk = (blockIdx.x / p.heads) % chunks;
-  const int b = blockIdx.x / (p.heads * chunks);
-  const int s0 = chunk * p.SC;
-  const int R = p.SC * p.T;
+  const int n_mine = (p.units - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
   if (threadIdx.x == 0) {
-    mbar_init(smem_u32(&bar_load), 1);
-    mbar_init(smem_u32(&bar_s), 1);
-    mbar_init(smem_u32(&bar_p), 128);
-    mbar_init(smem_u32(&bar_o), 1);
+    for (int s = 0; s < kFwdStages; ++s) {
+      mbar_init(smem_u32(&bar_full[s]), 1);
+      mbar_init(smem_u32(&bar_empty[s]), 1);
+    }
+    for (int g = 0; g < 2; ++g) {
+      mbar_init(smem_u32(&bar_s[g]), 1);
+      mbar_init(smem_u32(&bar_p[g]), kGroupThreads);
+      mbar_init(smem_u32(&bar_o[g]), 1);
+      mbar_init(smem_u32(&bar_ofree[g]), kGroupThreads);
+    }
     fence_barrier_init();
   }
-  if (warp == 4) {
-    tmem_alloc(smem_u32(&tmem_base_slot), 128);
+  if (warp == 9) {
+    tmem_alloc(smem_u32(&tmem_base_slot), 512);
     tmem_relinquish();
   }
-  if (R < 128) {
-    zero_tail_rows(sQ, R, threadIdx.x, blockDim.x);
-    zero_tail_rows(sK, R, threadIdx.x, blockDim.x);
-    zero_tail_rows(sV, R, threadIdx.x, blockDim.x);
-    fence_proxy_async();
-  }
+  zero_smem(sP, 4 * kTPanel, threadIdx.x, blockDim.x);
+  fence_proxy_async();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
 
-  if (warp == 4) {
+  if (warp == 8) {
+    // ---------------------------------------------------------------- TMA producer
     if (elect_one()) {
-      const uint32_t bl = smem_u32(&bar_load);
-      mbar_expect_tx(bl, (uint32_t)(3 * R * kTRowB));
-      tma_load_3d(sQ, &tmQKV, bl, p.q_col + head * 32, s0, b * p.T);
-      tma_load_3d(sK, &tmQKV, bl, p.k_col + head * 32, s0, b * p.T);
-      tma_load_3d(sV, &tmQKV, bl, p.v_col + head * 32, s0, b * p.T);
-      mbar_wait(bl, 0);
-      tc_fence_after();
+      tma_prefetch_desc(&tmQKV);
+      for (int i = 0; i < n_mine; ++i) {
+        const int st = i % kFwdStages;
+        mbar_wait(smem_u32(&bar_empty[st]), (uint32_t)(((i / kFwdStages) & 1) ^ 1));
+        const UnitCoord c = unit_coord(p, (int)blockIdx.x + i * (int)gridDim.x);
+        const uint32_t full = smem_u32(&bar_full[st]);
+        const uint32_t dst = sStage + (uint32_t)st * 3 * kTTile;
+        mbar_expect_tx(full, 3u * kTTile);
+        tma_load_3d(dst, &tmQKV, full, p.q_col + c.head * 32, c.b * p.T, c.s0);
+        tma_load_3d(dst + kTTile, &tmQKV, full, p.k_col + c.head * 32, c.b * p.T, c.s0);
+        tma_load_3d(dst + 2 * kTTile, &tmQKV, full, p.v_col + c.head * 32, c.b * p.T, c.s0);
+      }
+    }
+  } else if (warp == 9) {
+    // ---------------------------------------------------------------- UMMA issuer
+    if (elect_one()) {
       const uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);
       const uint32_t idesc_pv = umma_idesc_bf16(128, 32, 0, 1);
+      auto issue_pv = [&](int j) {
+        const int g = j & 1, k = j >> 1;
+        mbar_wait(smem_u32(&bar_p[g]), (uint32_t)(k & 1));
+        if (k >= 1) mbar_wait(smem_u32(&bar_ofree[g]), (uint32_t)((k - 1) & 1));
+        tc_fence_after();
+        const uint32_t tile = sP + (uint32_t)g * 2 * kTPanel;
+        const uint32_t sV = sStage + (uint32_t)(j % kFwdStages) * 3 * kTTile + 2 * kTTile;
+        const uint32_t tO = tmem_base + 256 + (uint32_t)g * 32;
 #pragma unroll
-      for (int k = 0; k < 2; ++k) umma_ss(tmem_base, tdesc_sw64(sQ + k * 32), tdesc_sw64(sK + k * 32), idesc_s, (uint32_t)k);
-      umma_commit(smem_u32(&bar_s));
-      mbar_wait(smem_u32(&bar_p), 0);
-      tc_fence_after();
-      // O aliases the first 32 columns of S: every softmax thread has finished reading S (bar_p)
+        for (int kk = 0; kk < 8; ++kk)
+          umma_ss(tO, umma_desc_kmajor(tile + (uint32_t)(kk >> 2) * kTPanel + (uint32_t)(kk & 3) * 32),
+                  tdesc_sw64(sV + (uint32_t)kk * 16 * kTRowB), idesc_pv, (uint32_t)(kk != 0));
+        umma_commit(smem_u32(&bar_o[g]));
+        umma_commit(smem_u32(&bar_empty[j % kFwdStages]));
+      };
+      for (int i = 0; i < n_mine; ++i) {
+        const int st = i % kFwdStages, g = i & 1;
+        mbar_wait(smem_u32(&bar_full[st]), (uint32_t)((i / kFwdStages) & 1));
+        tc_fence_after();
+        // S buffer g is free: the P V of unit i-2 was issued only after its softmax had consumed S
+        const uint32_t sQ = sStage + (uint32_t)st * 3 * kTTile, sK = sQ + kTTile;
+        const uint32_t tS = tmem_base + (uint32_t)g * 128;
 #pragma unroll
-      for (int kk = 0; kk < 8; ++kk)
-        umma_ss(tmem_base, umma_desc_kmajor(sP + (uint32_t)(kk >> 2) * kTPanel + (uint32_t)(kk & 3) * 32),
-                tdesc_sw64(sV + (uint32_t)kk * 16 * kTRowB), idesc_pv, (uint32_t)(kk != 0));
-      umma_commit(smem_u32(&bar_o));
+        for (int k = 0; k < 2; ++k) umma_ss(tS, tdesc_sw64(sQ + k * 32), tdesc_sw64(sK + k * 32), idesc_s, (uint32_t)k);
+        umma_commit(smem_u32(&bar_s[g]));
+        if (i >= 1) issue_pv(i - 1);
+      }
+      if (n_mine >= 1) issue_pv(n_mine - 1);
     }
   } else {
-    const int row = warp * 32 + lane;
-    const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
-    uint32_t mask[4];
-    row_mask(row, p.SC, R, mask);
-    mbar_wait(smem_u32(&bar_s), 0);
-    tc_fence_after();
-    float m = -INFINITY;
+    // ---------------------------------------------------------------- softmax + epilogue, group g = warp / 4
+    const int g = warp >> 2;
+    const RowInfo ri = row_info(p, warp & 3, lane);
+    const uint32_t lane_addr = (uint32_t)(ri.quarter * 32) << 16;
+    const uint32_t tS = tmem_base + (uint32_t)g * 128 + lane_addr;
+    const uint32_t tO = tmem_base + 256 + (uint32_t)g * 32 + lane_addr;
+    const uint32_t tile = sP + (uint32_t)g * 2 * kTPanel;
+    for (int i = g; i < n_mine; i += 2) {
+      const int k = i >> 1;
+      const UnitCoord c = unit_coord(p, (int)blockIdx.x + i * (int)gridDim.x);
+      mbar_wait(smem_u32(&bar_s[g]), (uint32_t)(k & 1));
+      tc_fence_after();
+      float m = -INFINITY;
+      for (int j = 0; j < ri.nch; ++j) {
+        uint32_t r[32];
+        tmem_ld_x32(tS + ri.col0 + 32 * j, r);
+        tmem_ld_wait();
+        const uint32_t mk = chunk_mask(ri, j);
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      uint32_t r[32];
-      tmem_ld_x32(tmem_base + lane_addr + c * 32, r);
-      tmem_ld_wait();
-#pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if ((mask[c] >> j) & 1u) m = fmaxf(m, __uint_as_float(r[j]));
-    }
-    const float mb = m * p.scale_log2;
-    float l = 0.f;
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      uint32_t r[32];
-      tmem_ld_x32(tmem_base + lane_addr + c * 32, r);
-      tmem_ld_wait();
-      uint32_t pk[16];
-#pragma unroll
-      for (int j = 0; j < 32; j += 2) {
-        const float p0 = ((mask[c] >> j) & 1u) ? fast_ex2(fmaf(__uint_as_float(r[j]), p.scale_log2, -mb)) : 0.f;
-        const float p1 = ((mask[c] >> (j + 1)) & 1u) ? fast_ex2(fmaf(__uint_as_float(r[j + 1]), p.scale_log2, -mb)) : 0.f;
-        const uint32_t w = pack_bf16(p0, p1);
-        l += bf16_lo(w) + bf16_hi(w);
-        pk[j >> 1] = w;
+        for (int b = 0; b < 32; ++b)
+          if ((mk >> b) & 1u) m = fmaxf(m, __uint_as_float(r[b]));
       }
-      const uint32_t panel = sP + (uint32_t)(c >> 1) * kTPanel;
+      const float mb = m * p.scale_log2;
+      float l = 0.f;
+      for (int j = 0; j < ri.nch; ++j) {
+        uint32_t r[32];
+        tmem_ld_x32(tS + ri.col0 + 32 * j, r);
+        tmem_ld_wait();
+        const uint32_t mk = chunk_mask(ri, j);
+        uint32_t pk[16];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const uint32_t addr = panel + sw128_offset((uint32_t)row, (uint32_t)((c & 1) * 32 + q * 8));
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[4 * q]), "r"(pk[4 * q + 1]),
-                     "r"(pk[4 * q + 2]), "r"(pk[4 * q + 3]) : "memory");
+        for (int b = 0; b < 32; b += 2) {
+          const float p0 = ((mk >> b) & 1u) ? fast_ex2(fmaf(__uint_as_float(r[b]), p.scale_log2, -mb)) : 0.f;
+          const float p1 = ((mk >> (b + 1)) & 1u) ? fast_ex2(fmaf(__uint_as_float(r[b + 1]), p.scale_log2, -mb)) : 0.f;
+          const uint32_t w = pack_bf16(p0, p1);
+          l += bf16_lo(w) + bf16_hi(w);
+          pk[b >> 1] = w;
+        }
+        store_p_chunk(tile, ri.row, ri.col0 + 32 * j, pk);
       }
-    }
-    fence_proxy_async();
-    tc_fence_before();
-    mbar_arrive(smem_u32(&bar_p));
-    mbar_wait(smem_u32(&bar_o), 0);
-    tc_fence_after();
-    uint32_t o[32];
-    tmem_ld_x32(tmem_base + lane_addr, o);
-    tmem_ld_wait();
-    const int sl = row % p.SC, t = row / p.SC;
-    if (row < R && s0 + sl < p.n) {
-      const float inv = 1.0f / l;
-      const size_t tok = ((size_t)b * p.T + t) * p.n + s0 + sl;
-      uint4* dst = reinterpret_cast<uint4*>(p.out + tok * p.ldo + head * 32);
-#pragma unroll
-      for (int q = 0; q < 4; ++q)
-        dst[q] = make_uint4(pack_bf16(__uint_as_float(o[8 * q]) * inv, __uint_as_float(o[8 * q + 1]) * inv),
-                            pack_bf16(__uint_as_float(o[8 * q + 2]) * inv, __uint_as_float(o[8 * q + 3]) * inv),
-                            pack_bf16(__uint_as_float(o[8 * q + 4]) * inv, __uint_as_float(o[8 * q + 5]) * inv),
-                            pack_bf16(__uint_as_float(o[8 * q + 6]) * inv, __uint_as_float(o[8 * q + 7]) * inv));
-      if (p.lse != nullptr) p.lse[tok * p.heads + head] = mb + log2f(l);
+      fence_proxy_async();
+      tc_fence_before();
+      mbar_arrive(smem_u32(&bar_p[g]));
+      mbar_wait(smem_u32(&bar_o[g]), (uint32_t)(k & 1));
+      tc_fence_after();
+      uint32_t o[32];
+      tmem_ld_x32(tO, o);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(smem_u32(&bar_ofree[g]));
+      if (ri.frame_ok && ri.sl < p.SC && c.s0 + ri.sl < p.n) {
+        const size_t tok = ((size_t)c.b * p.T + ri.t) * p.n + c.s0 + ri.sl;
+        store_row32_bf16(p.out + tok * p.ldo + c.head * 32, o, 1.0f / l);
+        if (p.lse != nullptr) p.lse[tok * p.heads + c.head] = mb + log2f(l);
+      }
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == 9) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 128);
+    tmem_dealloc(tmem_base, 512);
   }
 }
 
 // ------------------------------------------------------------------------------------------------
 // backward
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void store_row32_bf16(__nv_bfloat16* dst, const uint32_t (&r)[32]) {
-  uint4* d4 = reinterpret_cast<uint4*>(dst);
-#pragma unroll
-  for (int q = 0; q < 4; ++q)
-    d4[q] = make_uint4(pack_bf16(__uint_as_float(r[8 * q]), __uint_as_float(r[8 * q + 1])),
-                       pack_bf16(__uint_as_float(r[8 * q + 2]), __uint_as_float(r[8 * q + 3])),
-                       pack_bf16(__uint_as_float(r[8 * q + 4]), __uint_as_float(r[8 * q + 5])),
-                       pack_bf16(__uint_as_float(r[8 * q + 6]), __uint_as_float(r[8 * q + 7])));
-}
-
-__global__ void __launch_bounds__(288, 2)
+__global__ void __launch_bounds__(320, 1)
 attn_temporal_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
                             const TemporalTcParams p) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t bar_load, bar_sdp, bar_pds, bar_out;
+  __shared__ __align__(8) uint64_t bar_full[kBwdStages], bar_empty[kBwdStages], bar_sdp[2], bar_pds[2], bar_out[2], bar_free[2];
   __shared__ uint32_t tmem_base_slot;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t sQ = smem_base, sK = sQ + kTTile, sV = sK + kTTile, sDO = sV + kTTile;
-  const uint32_t sP = sDO + kTTile;          // 32 KB offset: aligned
-  const uint32_t sDS = sP + 2 * kTPanel;
+  const uint32_t sStage = smem_base;                              // kBwdStages x {Q, K, V, dO}
+  const uint32_t sPdS = sStage + kBwdStages * 4 * kTTile;         // 2 x {P, dS}, each [128 x 128] bf16
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int chunks = (p.n + p.SC - 1) / p.SC;
-  const int head = blockIdx.x % p.heads;
-  const int chunk = (blockIdx.x / p.heads) % chunks;
-  const int b = blockIdx.x / (p.heads * chunks);
-  const int s0 = chunk * p.SC;
-  const int R = p.SC * p.T;
+  const int n_mine = (p.units - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
   if (threadIdx.x == 0) {
-    mbar_init(smem_u32(&bar_load), 1);
-    mbar_init(smem_u32(&bar_sdp), 1);
-    mbar_init(smem_u32(&bar_pds), 256);
-    mbar_init(smem_u32(&bar_out), 1);
+    for (int s = 0; s < kBwdStages; ++s) {
+      mbar_init(smem_u32(&bar_full[s]), 1);
+      mbar_init(smem_u32(&bar_empty[s]), 1);
+    }
+    for (int g = 0; g < 2; ++g) {
+      mbar_init(smem_u32(&bar_sdp[g]), 1);
+      mbar_init(smem_u32(&bar_pds[g]), kGroupThreads);
+      mbar_init(smem_u32(&bar_out[g]), 1);
+      mbar_init(smem_u32(&bar_free[g]), kGroupThreads);
+    }
     fence_barrier_init();
   }
-  if (warp == 8) {
-    tmem_alloc(smem_u32(&tmem_base_slot), 256);
+  if (warp == 9) {
+    tmem_alloc(smem_u32(&tmem_base_slot), 512);
     tmem_relinquish();
   }
-  if (R < 128) {
-    zero_tail_rows(sQ, R, threadIdx.x, blockDim.x);
-    zero_tail_rows(sK, R, threadIdx.x, blockDim.x);
-    zero_tail_rows(sV, R, threadIdx.x, blockDim.x);
-    zero_tail_rows(sDO, R, threadIdx.x, blockDim.x);
-    fence_proxy_async();
-  }
+  zero_smem(sPdS, 8 * kTPanel, threadIdx.x, blockDim.x);
+  fence_proxy_async();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
-  const uint32_t tS = tmem_base, tDP = tmem_base + 128;
-  // after the compute warps have consumed S and dP their columns are reused for the three outputs
-  const uint32_t tDV = tmem_base, tDK = tmem_base + 32, tDQ = tmem_base + 64;
 
   if (warp == 8) {
     if (elect_one()) {
-      const uint32_t bl = smem_u32(&bar_load);
-      mbar_expect_tx(bl, (uint32_t)(4 * R * kTRowB));
-      tma_load_3d(sQ, &tmQKV, bl, p.q_col + head * 32, s0, b * p.T);
-      tma_load_3d(sK, &tmQKV, bl, p.k_col + head * 32, s0, b * p.T);
-      tma_load_3d(sV, &tmQKV, bl, p.v_col + head * 32, s0, b * p.T);
-      tma_load_3d(sDO, &tmDO, bl, head * 32, s0, b * p.T);
-      mbar_wait(bl, 0);
-      tc_fence_after();
-      const uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);
-      const uint32_t idesc_t = umma_idesc_bf16(128, 32, 1, 1);
-      const uint32_t idesc_q = umma_idesc_bf16(128, 32, 0, 1);
-#pragma unroll
-      for (int k = 0; k < 2; ++k) umma_ss(tS, tdesc_sw64(sQ + k * 32), tdesc_sw64(sK + k * 32), idesc_s, (uint32_t)k);
-#pragma unroll
-      for (int k = 0; k < 2; ++k) umma_ss(tDP, tdesc_sw64(sDO + k * 32), tdesc_sw64(sV + k * 32), idesc_s, (uint32_t)k);
-      umma_commit(smem_u32(&bar_sdp));
-      mbar_wait(smem_u32(&bar_pds), 0);
-      tc_fence_after();
-#pragma unroll
-      for (int kk = 0; kk < 8; ++kk) {
-        umma_ss(tDV, umma_desc_mnmajor(sP + kk * 2048, kTPanel), tdesc_sw64(sDO + kk * 1024), idesc_t, (uint32_t)(kk != 0));
-        umma_ss(tDK, umma_desc_mnmajor(sDS + kk * 2048, kTPanel), tdesc_sw64(sQ + kk * 1024), idesc_t, (uint32_t)(kk != 0));
-        umma_ss(tDQ, umma_desc_kmajor(sDS + (uint32_t)(kk >> 2) * kTPanel + (uint32_t)(kk & 3) * 32),
-                tdesc_sw64(sK + (uint32_t)kk * 16 * kTRowB), idesc_q, (uint32_t)(kk != 0));
+      tma_prefetch_desc(&tmQKV);
+      tma_prefetch_desc(&tmDO);
+      for (int i = 0; i < n_mine; ++i) {
+        const int st = i % kBwdStages;
+        mbar_wait(smem_u32(&bar_empty[st]), (uint32_t)(((i / kBwdStages) & 1) ^ 1));
+        const UnitCoord c = unit_coord(p, (int)blockIdx.x + i * (int)gridDim.x);
+        const uint32_t full = smem_u32(&bar_full[st]);
+        const uint32_t dst = sStage + (uint32_t)st * 4 * kTTile;
+        mbar_expect_tx(full, 4u * kTTile);
+        tma_load_3d(dst, &tmQKV, full, p.q_col + c.head * 32, c.b * p.T, c.s0);
+        tma_load_3d(dst + kTTile, &tmQKV, full, p.k_col + c.head * 32, c.b * p.T, c.s0);
+        tma_load_3d(dst + 2 * kTTile, &tmQKV, full, p.v_col + c.head * 32, c.b * p.T, c.s0);
+        tma_load_3d(dst + 3 * kTTile, &tmDO, full, c.head * 32, c.b * p.T, c.s0);
       }
-      umma_commit(smem_u32(&bar_out));
+    }
+  } else if (warp == 9) {
+    if (elect_one()) {
+      const uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);
+      const uint32_t idesc_t = umma_idesc_bf16(128, 32, 1, 1);   // dV, dK: both operands MN-major
+      const uint32_t idesc_q = umma_idesc_bf16(128, 32, 0, 1);   // dQ: A K-major, B MN-major
+      auto issue_out = [&](int j) {
+        const int g = j & 1, k = j >> 1;
+        mbar_wait(smem_u32(&bar_pds[g]), (uint32_t)(k & 1));
+        tc_fence_after();
+        const uint32_t st = sStage + (uint32_t)(j % kBwdStages) * 4 * kTTile;
+        const uint32_t sQ = st, sK = st + kTTile, sDO = st + 3 * kTTile;
+        const uint32_t sPt = sPdS + (uint32_t)g * 4 * kTPanel, sDS = sPt + 2 * kTPanel;
+        const uint32_t tb = tmem_base + (uint32_t)g * 256;  // outputs reuse the consumed S / dP columns
+        const uint32_t tDV = tb, tDK = tb + 32, tDQ = tb + 64;
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {
+          umma_ss(tDV, umma_desc_mnmajor(sPt + kk * 2048, kTPanel), tdesc_sw64(sDO + kk * 1024), idesc_t, (uint32_t)(kk != 0));
+          umma_ss(tDK, umma_desc_mnmajor(sDS + kk * 2048, kTPanel), tdesc_sw64(sQ + kk * 1024), idesc_t, (uint32_t)(kk != 0));
+          umma_ss(tDQ, umma_desc_kmajor(sDS + (uint32_t)(kk >> 2) * kTPanel + (uint32_t)(kk & 3) * 32),
+                  tdesc_sw64(sK + (uint32_t)kk * 16 * kTRowB), idesc_q, (uint32_t)(kk != 0));
+        }
+        umma_commit(smem_u32(&bar_out[g]));
+        umma_commit(smem_u32(&bar_empty[j % kBwdStages]));
+      };
+      for (int i = 0; i < n_mine; ++i) {
+        const int st = i % kBwdStages, g = i & 1, k = i >> 1;
+        mbar_wait(smem_u32(&bar_full[st]), (uint32_t)((i / kBwdStages) & 1));
+        if (k >= 1) mbar_wait(smem_u32(&bar_free[g]), (uint32_t)((k - 1) & 1));  // outputs of unit i-2 read out
+        tc_fence_after();
+        const uint32_t sb = sStage + (uint32_t)st * 4 * kTTile;
+        const uint32_t sQ = sb, sK = sb + kTTile, sV = sb + 2 * kTTile, sDO = sb + 3 * kTTile;
+        const uint32_t tS = tmem_base + (uint32_t)g * 256, tDP = tS + 128;
+#pragma unroll
+        for (int kq = 0; kq < 2; ++kq) umma_ss(tS, tdesc_sw64(sQ + kq * 32), tdesc_sw64(sK + kq * 32), idesc_s, (uint32_t)kq);
+#pragma unroll
+        for (int kq = 0; kq < 2; ++kq) umma_ss(tDP, tdesc_sw64(sDO + kq * 32), tdesc_sw64(sV + kq * 32), idesc_s, (uint32_t)kq);
+        umma_commit(smem_u32(&bar_sdp[g]));
+        if (i >= 1) issue_out(i - 1);
+      }
+      if (n_mine >= 1) issue_out(n_mine - 1);
     }
   } else {
-    const int quarter = warp & 3, half = warp >> 2;
-    const int row = quarter * 32 + lane;
-    const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
-    const int sl = row % p.SC, t = row / p.SC;
-    const bool valid = row < R && s0 + sl < p.n;
-    const size_t tok = ((size_t)b * p.T + t) * p.n + s0 + sl;
-    uint32_t mask[4];
-    row_mask(valid ? row : 128, p.SC, R, mask);
-    float L = 0.f, delta = 0.f;
-    if (valid) {
-      L = p.lse[tok * p.heads + head];
-      const uint4* o4 = reinterpret_cast<const uint4*>(p.out_c + tok * p.ldo + head * 32);
-      const uint4* g4 = reinterpret_cast<const uint4*>(p.dout + tok * p.ld_dout + head * 32);
+    const int g = warp >> 2;
+    const RowInfo ri = row_info(p, warp & 3, lane);
+    const uint32_t lane_addr = (uint32_t)(ri.quarter * 32) << 16;
+    const uint32_t tS = tmem_base + (uint32_t)g * 256 + lane_addr, tDP = tS + 128;
+    const uint32_t sPt = sPdS + (uint32_t)g * 4 * kTPanel, sDS = sPt + 2 * kTPanel;
+    for (int i = g; i < n_mine; i += 2) {
+      const int k = i >> 1;
+      const UnitCoord c = unit_coord(p, (int)blockIdx.x + i * (int)gridDim.x);
+      mbar_wait(smem_u32(&bar_sdp[g]), (uint32_t)(k & 1));
+      tc_fence_after();
+      // pass 1: row maximum
+      float m = -INFINITY;
+      for (int j = 0; j < ri.nch; ++j) {
+        uint32_t s[32];
+        tmem_ld_x32(tS + ri.col0 + 32 * j, s);
+        tmem_ld_wait();
+        const uint32_t mk = chunk_mask(ri, j);
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const uint4 a = o4[q], g = g4[q];
-        const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, gw[4] = {g.x, g.y, g.z, g.w};
-#pragma unroll
-        for (int j = 0; j < 4; ++j) delta += bf16_lo(aw[j]) * bf16_lo(gw[j]) + bf16_hi(aw[j]) * bf16_hi(gw[j]);
+        for (int b = 0; b < 32; ++b)
+          if ((mk >> b) & 1u) m = fmaxf(m, __uint_as_float(s[b]));
       }
-    }
-    mbar_wait(smem_u32(&bar_sdp), 0);
-    tc_fence_after();
+      const float mb = m * p.scale_log2;
+      // pass 2: softmax denominator and delta = sum_j P_j dP_j
+      float l = 0.f, pd = 0.f;
+      for (int j = 0; j < ri.nch; ++j) {
+        uint32_t s[32], dp[32];
+        tmem_ld_x32(tS + ri.col0 + 32 * j, s);
+        tmem_ld_x32(tDP + ri.col0 + 32 * j, dp);
+        tmem_ld_wait();
+        const uint32_t mk = chunk_mask(ri, j);
 #pragma unroll
-    for (int cc = 0; cc < 2; ++cc) {
-      const int c = half * 2 + cc;  // 32-column chunk of the 128-key tile
-      uint32_t s[32], dp[32];
-      tmem_ld_x32(tS + lane_addr + c * 32, s);
-      tmem_ld_x32(tDP + lane_addr + c * 32, dp);
-      tmem_ld_wait();
-      uint32_t pk[16], dk[16];
-#pragma unroll
-      for (int j = 0; j < 32; j += 2) {
-        float p0 = 0.f, p1 = 0.f, d0 = 0.f, d1 = 0.f;
-        if ((mask[c] >> j) & 1u) {
-          p0 = fast_ex2(fmaf(__uint_as_float(s[j]), p.scale_log2, -L));
-          d0 = p0 * (__uint_as_float(dp[j]) - delta) * p.scale;
+        for (int b = 0; b < 32; ++b) {
+          const float e = ((mk >> b) & 1u) ? fast_ex2(fmaf(__uint_as_float(s[b]), p.scale_log2, -mb)) : 0.f;
+          l += e;
+          pd = fmaf(e, __uint_as_float(dp[b]), pd);
         }
-        if ((mask[c] >> (j + 1)) & 1u) {
-          p1 = fast_ex2(fmaf(__uint_as_float(s[j + 1]), p.scale_log2, -L));
-          d1 = p1 * (__uint_as_float(dp[j + 1]) - delta) * p.scale;
-        }
-        pk[j >> 1] = pack_bf16(p0, p1);
-        dk[j >> 1] = pack_bf16(d0, d1);
       }
-      const uint32_t pan = (uint32_t)half * kTPanel;
+      const float inv = l > 0.f ? 1.0f / l : 0.f;  // l == 0 only on padding rows
+      const float delta = pd * inv;
+      // pass 3: P and dS tiles
+      for (int j = 0; j < ri.nch; ++j) {
+        uint32_t s[32], dp[32];
+        tmem_ld_x32(tS + ri.col0 + 32 * j, s);
+        tmem_ld_x32(tDP + ri.col0 + 32 * j, dp);
+        tmem_ld_wait();
+        const uint32_t mk = chunk_mask(ri, j);
+        uint32_t pk[16], dk[16];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const uint32_t off = pan + sw128_offset((uint32_t)row, (uint32_t)(cc * 32 + q * 8));
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sP + off), "r"(pk[4 * q]), "r"(pk[4 * q + 1]),
-                     "r"(pk[4 * q + 2]), "r"(pk[4 * q + 3]) : "memory");
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sDS + off), "r"(dk[4 * q]), "r"(dk[4 * q + 1]),
-                     "r"(dk[4 * q + 2]), "r"(dk[4 * q + 3]) : "memory");
+        for (int b = 0; b < 32; b += 2) {
+          float p0 = 0.f, p1 = 0.f, d0 = 0.f, d1 = 0.f;
+          if ((mk >> b) & 1u) {
+            p0 = fast_ex2(fmaf(__uint_as_float(s[b]), p.scale_log2, -mb)) * inv;
+            d0 = p0 * (__uint_as_float(dp[b]) - delta) * p.scale;
+          }
+          if ((mk >> (b + 1)) & 1u) {
+            p1 = fast_ex2(fmaf(__uint_as_float(s[b + 1]), p.scale_log2, -mb)) * inv;
+            d1 = p1 * (__uint_as_float(dp[b + 1]) - delta) * p.scale;
+          }
+          pk[b >> 1] = pack_bf16(p0, p1);
+          dk[b >> 1] = pack_bf16(d0, d1);
+        }
+        store_p_chunk(sPt, ri.row, ri.col0 + 32 * j, pk);
+        store_p_chunk(sDS, ri.row, ri.col0 + 32 * j, dk);
       }
-    }
-    fence_proxy_async();
-    tc_fence_before();
-    mbar_arrive(smem_u32(&bar_pds));
-    mbar_wait(smem_u32(&bar_out), 0);
-    tc_fence_after();
-    // warps 0-3: dQ and dK of their rows; warps 4-7: dV
-    if (half == 0) {
+      fence_proxy_async();
+      tc_fence_before();
+      mbar_arrive(smem_u32(&bar_pds[g]));
+      mbar_wait(smem_u32(&bar_out[g]), (uint32_t)(k & 1));
+      tc_fence_after();
+      const uint32_t tb = tmem_base + (uint32_t)g * 256 + lane_addr;
+      const bool valid = ri.frame_ok && ri.sl < p.SC && c.s0 + ri.sl < p.n;
+      const size_t tok = ((size_t)c.b * p.T + ri.t) * p.n + c.s0 + ri.sl;
+      __nv_bfloat16* drow = p.dqkv + (valid ? tok * p.ld_dqkv : 0) + c.head * 32;
       uint32_t r[32];
-      tmem_ld_x32(tDQ + lane_addr, r);
+      tmem_ld_x32(tb + 64, r);
       tmem_ld_wait();
-      if (valid) store_row32_bf16(p.dqkv + tok * p.ld_dqkv + p.q_col + head * 32, r);
-      tmem_ld_x32(tDK + lane_addr, r);
+      if (valid) store_row32_bf16(drow + p.q_col, r, 1.0f);
+      tmem_ld_x32(tb + 32, r);
       tmem_ld_wait();
-      if (valid) store_row32_bf16(p.dqkv + tok * p.ld_dqkv + p.k_col + head * 32, r);
-    } else {
-      uint32_t r[32];
-      tmem_ld_x32(tDV + lane_addr, r);
+      if (valid) store_row32_bf16(drow + p.k_col, r, 1.0f);
+      tmem_ld_x32(tb, r);
       tmem_ld_wait();
-      if (valid) store_row32_bf16(p.dqkv + tok * p.ld_dqkv + p.v_col + head * 32, r);
+      tc_fence_before();
+      mbar_arrive(smem_u32(&bar_free[g]));
+      if (valid) store_row32_bf16(drow + p.v_col, r, 1.0f);
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) {
+  if (warp == 9) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 256);
+    tmem_dealloc(tmem_base, 512);
   }
 }
 
-static int temporal_sc(int T) { return 128 / T; }
+static int fill_params(TemporalTcParams& p, int B, int T, int n, int heads, int q_col, int k_col, int v_col, float scale) {
+  HMA_REQUIRE(T >= 1 && T <= 128, "attn_temporal: T=%d must be in [1,128]", T);
+  HMA_REQUIRE(heads >= 1, "attn_temporal: bad heads");
+  p.B = B; p.T = T; p.n = n; p.heads = heads;
+  int tp = 1;
+  while (tp < T) tp <<= 1;
+  p.Tp = tp;
+  p.SC = 128 / tp;
+  p.chunks = (n + p.SC - 1) / p.SC;
+  p.units = B * p.chunks * heads;
+  p.q_col = q_col; p.k_col = k_col; p.v_col = v_col;
+  p.scale = scale; p.scale_log2 = scale * 1.4426950408889634f;
+  return 0;
+}
+
+// {32 channels, Tp frames, SC slots} box over the (B*T, n, ld) activation: dimension 1 = frames (stride n*ld),
+// dimension 2 = slots (stride ld), so the tile lands slot-major in shared memory.
+static int make_unit_map(CUtensorMap* tm, const void* base, long long ld, int B, int T, int n, const TemporalTcParams& p) {
+  return hma_host::make_tmap_bf16_3d_sw64(tm, base, (uint64_t)ld, (uint64_t)B * T, (uint64_t)n, (uint64_t)n * ld * 2,
+                                          (uint64_t)ld * 2, (uint32_t)p.Tp, (uint32_t)p.SC);
+}
 
 }  // namespace hma
 
@@ -376,61 +503,52 @@ extern "C" int hma_attn_temporal_fwd(const void* qkv, long long ld_qkv, int B, i
                                      void* stream_) {
   using namespace hma;
   if (B == 0 || n == 0) return 0;
-  HMA_REQUIRE(T >= 1 && T <= 128, "attn_temporal: T=%d must be in [1,128]", T);
   HMA_REQUIRE(ld_qkv % 8 == 0 && ldo % 8 == 0 && q_col % 8 == 0 && k_col % 8 == 0 && v_col % 8 == 0,
               "attn_temporal: 16-byte alignment required");
   TemporalTcParams p{};
-  p.B = B; p.T = T; p.n = n; p.heads = heads; p.SC = temporal_sc(T);
-  p.q_col = q_col; p.k_col = k_col; p.v_col = v_col;
-  p.scale = scale; p.scale_log2 = scale * 1.4426950408889634f;
+  if (int rc = fill_params(p, B, T, n, heads, q_col, k_col, v_col, scale)) return rc;
   p.out = static_cast<__nv_bfloat16*>(out); p.ldo = ldo; p.lse = lse;
   CUtensorMap tm;
-  int rc = hma_host::make_tmap_bf16_3d_sw64(&tm, qkv, (uint64_t)ld_qkv, (uint64_t)n, (uint64_t)B * T, (uint64_t)ld_qkv * 2,
-                                            (uint64_t)n * ld_qkv * 2, (uint32_t)p.SC, (uint32_t)T);
-  if (rc) return rc;
-  constexpr size_t smem = 1024 + 3 * kTTile + 2 * kTPanel;
+  if (int rc = make_unit_map(&tm, qkv, ld_qkv, B, T, n, p)) return rc;
+  constexpr size_t smem = 1024 + kFwdStages * 3 * kTTile + 4 * kTPanel;
   static bool attr_done = false;
   if (!attr_done) {
     HMA_CHECK_CUDA(cudaFuncSetAttribute(attn_temporal_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_done = true;
   }
-  const int chunks = (n + p.SC - 1) / p.SC;
-  attn_temporal_tc_fwd_kernel<<<B * chunks * heads, 160, smem, static_cast<cudaStream_t>(stream_)>>>(tm, p);
+  int grid = hma_host::sm_count();
+  if (grid > p.units) grid = p.units;
+  attn_temporal_tc_fwd_kernel<<<grid, 320, smem, static_cast<cudaStream_t>(stream_)>>>(tm, p);
   HMA_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 
+// `out` and `lse` of the forward are accepted for interface symmetry with the spatial kernel but not read:
+// the backward recomputes the (tiny) softmax rows.
 extern "C" int hma_attn_temporal_bwd(const void* qkv, long long ld_qkv, const void* out, long long ldo,
                                      const void* dout, long long ld_dout, const float* lse, int B, int T, int n,
                                      int heads, int q_col, int k_col, int v_col, float scale, void* dqkv,
                                      long long ld_dqkv, void* stream_) {
   using namespace hma;
+  (void)out; (void)ldo; (void)lse;
   if (B == 0 || n == 0) return 0;
-  HMA_REQUIRE(T >= 1 && T <= 128, "attn_temporal_bwd: T=%d must be in [1,128]", T);
-  HMA_REQUIRE(ld_qkv % 8 == 0 && ld_dout % 8 == 0 && ld_dqkv % 8 == 0 && ldo % 8 == 0, "attn_temporal_bwd: 16-byte alignment required");
-  HMA_REQUIRE(lse != nullptr, "attn_temporal_bwd: needs the forward log-sum-exp");
+  HMA_REQUIRE(ld_qkv % 8 == 0 && ld_dout % 8 == 0 && ld_dqkv % 8 == 0, "attn_temporal_bwd: 16-byte alignment required");
+  HMA_REQUIRE(q_col % 8 == 0 && k_col % 8 == 0 && v_col % 8 == 0, "attn_temporal_bwd: 16-byte alignment required");
   TemporalTcParams p{};
-  p.B = B; p.T = T; p.n = n; p.heads = heads; p.SC = temporal_sc(T);
-  p.q_col = q_col; p.k_col = k_col; p.v_col = v_col;
-  p.scale = scale; p.scale_log2 = scale * 1.4426950408889634f;
-  p.out_c = static_cast<const __nv_bfloat16*>(out); p.ldo = ldo; p.lse = const_cast<float*>(lse);
-  p.dout = static_cast<const __nv_bfloat16*>(dout); p.ld_dout = ld_dout;
+  if (int rc = fill_params(p, B, T, n, heads, q_col, k_col, v_col, scale)) return rc;
   p.dqkv = static_cast<__nv_bfloat16*>(dqkv); p.ld_dqkv = ld_dqkv;
   CUtensorMap tmQ, tmD;
-  int rc = hma_host::make_tmap_bf16_3d_sw64(&tmQ, qkv, (uint64_t)ld_qkv, (uint64_t)n, (uint64_t)B * T, (uint64_t)ld_qkv * 2,
-                                            (uint64_t)n * ld_qkv * 2, (uint32_t)p.SC, (uint32_t)T);
-  if (rc) return rc;
-  rc = hma_host::make_tmap_bf16_3d_sw64(&tmD, dout, (uint64_t)ld_dout, (uint64_t)n, (uint64_t)B * T, (uint64_t)ld_dout * 2,
-                                        (uint64_t)n * ld_dout * 2, (uint32_t)p.SC, (uint32_t)T);
-  if (rc) return rc;
-  constexpr size_t smem = 1024 + 4 * kTTile + 4 * kTPanel;
+  if (int rc = make_unit_map(&tmQ, qkv, ld_qkv, B, T, n, p)) return rc;
+  if (int rc = make_unit_map(&tmD, dout, ld_dout, B, T, n, p)) return rc;
+  constexpr size_t smem = 1024 + kBwdStages * 4 * kTTile + 8 * kTPanel;
   static bool attr_done = false;
   if (!attr_done) {
     HMA_CHECK_CUDA(cudaFuncSetAttribute(attn_temporal_tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_done = true;
   }
-  const int chunks = (n + p.SC - 1) / p.SC;
-  attn_temporal_tc_bwd_kernel<<<B * chunks * heads, 288, smem, static_cast<cudaStream_t>(stream_)>>>(tmQ, tmD, p);
+  int grid = hma_host::sm_count();
+  if (grid > p.units) grid = p.units;
+  attn_temporal_tc_bwd_kernel<<<grid, 320, smem, static_cast<cudaStream_t>(stream_)>>>(tmQ, tmD, p);
   HMA_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -300,7 +300,7 @@ class Engine:
                 lse_t = None
                 att_t = ops.attn_temporal_cached(qkv_t, kv[i], t0, d.heads, d.scale)
             else:
-                att_t, lse_t = ops.attn_temporal_fwd(qkv_t, B, T, n, d.heads, d.scale, want_lse=training)
+                att_t, lse_t = ops.attn_temporal_fwd(qkv_t, B, T, n, d.heads, d.scale, want_lse=False)  # bwd recomputes the rows
             if mode in ("prefill", "commit"):
                 ops.kv_cache_append(qkv_t, B, T, n, kv[i], t0)
                 if i == d.num_layers - 1:

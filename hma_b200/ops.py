@@ -213,7 +213,7 @@ def attn_temporal_bwd(qkv, out, dout, lse, B: int, T: int, n: int, heads: int, s
     C = heads * 32
     dqkv = torch.empty_like(qkv)
     _call("attn_temporal_bwd", B * T * n * C * 18.0, "hma_attn_temporal_bwd", qkv.data_ptr(), qkv.stride(0),
-          out.data_ptr(), out.stride(0), dout.data_ptr(), dout.stride(0), lse.data_ptr(), B, T, n, heads, 0, C, 2 * C,
+          out.data_ptr(), out.stride(0), dout.data_ptr(), dout.stride(0), _p(lse), B, T, n, heads, 0, C, 2 * C,
           float(scale), dqkv.data_ptr(), dqkv.stride(0), _s())
     return dqkv
 

@@ -75,7 +75,8 @@ int hma_attn_spatial_bwd(const void* qkv, long long ld_qkv, const void* out, lon
 
 /* Causal attention over the T frames of each of the n slots of each sample (attention.py:37-61 with
  * causal=True, st_transformer.py:111), reading the (B,T,n,.) layout in place. T <= 128.
- * lse: fp32 [tokens, heads] (log2 domain), optional in forward, required in backward. */
+ * lse: fp32 [tokens, heads] (log2 domain), optional output of the forward. The backward recomputes the
+ * (<= 128-key) softmax rows from q, k: its `out` and `lse` arguments are accepted but not read. */
 int hma_attn_temporal_fwd(const void* qkv, long long ld_qkv, int B, int T, int n, int heads, int q_col, int k_col,
                           int v_col, float scale, void* out, long long ldo, float* lse, void* stream);
 int hma_attn_temporal_bwd(const void* qkv, long long ld_qkv, const void* out, long long ldo, const void* dout,
