@@ -11,10 +11,12 @@
 //     S = Q K^T (one 128x128x32 tcgen05.mma) is then block diagonal with Tp x Tp causal blocks, and a
 //     softmax thread only touches the <= 32 columns of its own block (rows of padding frames / slots
 //     beyond n are computed on zero-filled or foreign-but-finite data and never stored).
-//   * persistent CTAs (one per SM) stream the units through a 4-stage (fwd) / 3-stage (bwd) TMA ring;
-//     two softmax warpgroups alternate units, each with its own TMEM accumulators and P (/dS) tiles,
-//     so the loads, the S contraction, the softmax, the P V contraction and the stores of neighbouring
-//     units overlap.
+//   * persistent CTAs (one per SM) stream the units through a 6-stage (fwd) / 3-stage (bwd) TMA ring;
+//     two softmax warpgroups alternate units, each with its own TMEM accumulators and P (/dS) tiles, and the
+//     single UMMA-issuing thread polls its barriers, so the loads, the S contraction, the softmax, the P V
+//     contraction and the stores of neighbouring units overlap. (Measured: the stage is bound by how many
+//     units are in flight per SM -- a stage is occupied from TMA issue to the end of its P V -- not by
+//     the softmax arithmetic.)
 //   * P tiles are zeroed once: a thread always writes the same columns of its row, everything else
 //     stays zero for the life of the CTA.
 // Backward recomputes the softmax of the (<= 128-key) row from S, so it needs neither the forward
@@ -39,7 +41,8 @@ struct TemporalTcParams {
 constexpr int kTRowB = 64;
 constexpr int kTTile = 128 * kTRowB;   // 8 KB per operand tile
 constexpr int kTPanel = 128 * 128;     // [128 x 64] bf16 panel (16 KB); a P / dS tile is two panels
-constexpr int kFwdStages = 4;
+constexpr int kFwdStages = 6;   // units in flight per SM: a stage stays occupied from TMA issue until its P V completes
+constexpr int kFwdGroups = 2;   // softmax warpgroups, one TMEM S buffer + one P tile each
 constexpr int kBwdStages = 3;
 constexpr int kGroupThreads = 128;
 
@@ -127,26 +130,52 @@ __device__ __forceinline__ void zero_smem(uint32_t addr, int bytes, int tid, int
     asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(addr + (uint32_t)i), "r"(0u) : "memory");
 }
 
+// Non-blocking mbarrier phase test (the UMMA issuer polls several barriers instead of blocking on one).
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}\n"
+      : "=r"(done)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return done != 0;
+}
+
+__device__ __forceinline__ float max32(const float (&s)[32]) {
+  float a = fmaxf(s[0], s[1]), b = fmaxf(s[2], s[3]), c = fmaxf(s[4], s[5]), d = fmaxf(s[6], s[7]);
+#pragma unroll
+  for (int j = 8; j < 32; j += 4) {
+    a = fmaxf(a, s[j]); b = fmaxf(b, s[j + 1]); c = fmaxf(c, s[j + 2]); d = fmaxf(d, s[j + 3]);
+  }
+  return fmaxf(fmaxf(a, b), fmaxf(c, d));
+}
+
 // ------------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(320, 1)
+constexpr int kFwdThreads = kFwdGroups * kGroupThreads + 64;
+
+__global__ void __launch_bounds__(kFwdThreads, 1)
 attn_temporal_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const TemporalTcParams p) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t bar_full[kFwdStages], bar_empty[kFwdStages], bar_s[2], bar_p[2], bar_o[2], bar_ofree[2];
+  __shared__ __align__(8) uint64_t bar_full[kFwdStages], bar_empty[kFwdStages], bar_s[kFwdGroups], bar_p[kFwdGroups],
+      bar_o[kFwdGroups], bar_ofree[kFwdGroups];
   __shared__ uint32_t tmem_base_slot;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sStage = smem_base;                              // kFwdStages x {Q, K, V}
-  const uint32_t sP = sStage + kFwdStages * 3 * kTTile;           // 2 x [128 x 128] bf16
+  const uint32_t sP = sStage + kFwdStages * 3 * kTTile;           // kFwdGroups x [128 x 128] bf16
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_mine = (p.units - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  constexpr int kProducerWarp = kFwdGroups * 4, kMmaWarp = kProducerWarp + 1;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kFwdStages; ++s) {
       mbar_init(smem_u32(&bar_full[s]), 1);
       mbar_init(smem_u32(&bar_empty[s]), 1);
     }
-    for (int g = 0; g < 2; ++g) {
+    for (int g = 0; g < kFwdGroups; ++g) {
       mbar_init(smem_u32(&bar_s[g]), 1);
       mbar_init(smem_u32(&bar_p[g]), kGroupThreads);
       mbar_init(smem_u32(&bar_o[g]), 1);
@@ -154,18 +183,18 @@ attn_temporal_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const Tem
     }
     fence_barrier_init();
   }
-  if (warp == 9) {
+  if (warp == kMmaWarp) {
     tmem_alloc(smem_u32(&tmem_base_slot), 512);
     tmem_relinquish();
   }
-  zero_smem(sP, 4 * kTPanel, threadIdx.x, blockDim.x);
+  zero_smem(sP, kFwdGroups * 2 * kTPanel, threadIdx.x, blockDim.x);
   fence_proxy_async();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
 
-  if (warp == 8) {
+  if (warp == kProducerWarp) {
     // ---------------------------------------------------------------- TMA producer
     if (elect_one()) {
       tma_prefetch_desc(&tmQKV);
@@ -181,39 +210,50 @@ attn_temporal_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const Tem
         tma_load_3d(dst + 2 * kTTile, &tmQKV, full, p.v_col + c.head * 32, c.b * p.T, c.s0);
       }
     }
-  } else if (warp == 9) {
-    // ---------------------------------------------------------------- UMMA issuer
+  } else if (warp == kMmaWarp) {
+    // ---------------------------------------------------------------- UMMA issuer (polls: no head-of-line blocking)
     if (elect_one()) {
       const uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);
       const uint32_t idesc_pv = umma_idesc_bf16(128, 32, 0, 1);
-      auto issue_pv = [&](int j) {
-        const int g = j & 1, k = j >> 1;
-        mbar_wait(smem_u32(&bar_p[g]), (uint32_t)(k & 1));
-        if (k >= 1) mbar_wait(smem_u32(&bar_ofree[g]), (uint32_t)((k - 1) & 1));
-        tc_fence_after();
-        const uint32_t tile = sP + (uint32_t)g * 2 * kTPanel;
-        const uint32_t sV = sStage + (uint32_t)(j % kFwdStages) * 3 * kTTile + 2 * kTTile;
-        const uint32_t tO = tmem_base + 256 + (uint32_t)g * 32;
+      int is = 0, ip = 0;  // next S / next P V to issue
+      uint32_t idle = 0;
+      while (ip < n_mine) {
+        bool progressed = false;
+        if (is < n_mine) {
+          const int st = is % kFwdStages, g = is % kFwdGroups, k = is / kFwdGroups;
+          // S buffer g (which O aliases) is free once the epilogue of unit is - kFwdGroups has read O
+          if (mbar_test(smem_u32(&bar_full[st]), (uint32_t)((is / kFwdStages) & 1)) &&
+              (k == 0 || mbar_test(smem_u32(&bar_ofree[g]), (uint32_t)((k - 1) & 1)))) {
+            tc_fence_after();
+            const uint32_t sQ = sStage + (uint32_t)st * 3 * kTTile, sK = sQ + kTTile;
+            const uint32_t tS = tmem_base + (uint32_t)g * 128;
 #pragma unroll
-        for (int kk = 0; kk < 8; ++kk)
-          umma_ss(tO, umma_desc_kmajor(tile + (uint32_t)(kk >> 2) * kTPanel + (uint32_t)(kk & 3) * 32),
-                  tdesc_sw64(sV + (uint32_t)kk * 16 * kTRowB), idesc_pv, (uint32_t)(kk != 0));
-        umma_commit(smem_u32(&bar_o[g]));
-        umma_commit(smem_u32(&bar_empty[j % kFwdStages]));
-      };
-      for (int i = 0; i < n_mine; ++i) {
-        const int st = i % kFwdStages, g = i & 1;
-        mbar_wait(smem_u32(&bar_full[st]), (uint32_t)((i / kFwdStages) & 1));
-        tc_fence_after();
-        // S buffer g is free: the P V of unit i-2 was issued only after its softmax had consumed S
-        const uint32_t sQ = sStage + (uint32_t)st * 3 * kTTile, sK = sQ + kTTile;
-        const uint32_t tS = tmem_base + (uint32_t)g * 128;
+            for (int kq = 0; kq < 2; ++kq) umma_ss(tS, tdesc_sw64(sQ + kq * 32), tdesc_sw64(sK + kq * 32), idesc_s, (uint32_t)kq);
+            umma_commit(smem_u32(&bar_s[g]));
+            ++is;
+            progressed = true;
+          }
+        }
+        if (ip < is) {
+          const int g = ip % kFwdGroups, k = ip / kFwdGroups;
+          if (mbar_test(smem_u32(&bar_p[g]), (uint32_t)(k & 1))) {
+            tc_fence_after();
+            const uint32_t tile = sP + (uint32_t)g * 2 * kTPanel;
+            const uint32_t sV = sStage + (uint32_t)(ip % kFwdStages) * 3 * kTTile + 2 * kTTile;
+            const uint32_t tO = tmem_base + (uint32_t)g * 128;  // over the consumed S columns
 #pragma unroll
-        for (int k = 0; k < 2; ++k) umma_ss(tS, tdesc_sw64(sQ + k * 32), tdesc_sw64(sK + k * 32), idesc_s, (uint32_t)k);
-        umma_commit(smem_u32(&bar_s[g]));
-        if (i >= 1) issue_pv(i - 1);
+            for (int kk = 0; kk < 8; ++kk)
+              umma_ss(tO, umma_desc_kmajor(tile + (uint32_t)(kk >> 2) * kTPanel + (uint32_t)(kk & 3) * 32),
+                      tdesc_sw64(sV + (uint32_t)kk * 16 * kTRowB), idesc_pv, (uint32_t)(kk != 0));
+            umma_commit(smem_u32(&bar_o[g]));
+            umma_commit(smem_u32(&bar_empty[ip % kFwdStages]));
+            ++ip;
+            progressed = true;
+          }
+        }
+        if (progressed) idle = 0;
+        else if (++idle > (1u << 24)) __trap();
       }
-      if (n_mine >= 1) issue_pv(n_mine - 1);
     }
   } else {
     // ---------------------------------------------------------------- softmax + epilogue, group g = warp / 4
@@ -221,40 +261,65 @@ attn_temporal_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const Tem
     const RowInfo ri = row_info(p, warp & 3, lane);
     const uint32_t lane_addr = (uint32_t)(ri.quarter * 32) << 16;
     const uint32_t tS = tmem_base + (uint32_t)g * 128 + lane_addr;
-    const uint32_t tO = tmem_base + 256 + (uint32_t)g * 32 + lane_addr;
+    const uint32_t tO = tS;
     const uint32_t tile = sP + (uint32_t)g * 2 * kTPanel;
-    for (int i = g; i < n_mine; i += 2) {
-      const int k = i >> 1;
+    const uint32_t mk0 = chunk_mask(ri, 0);
+    for (int i = g; i < n_mine; i += kFwdGroups) {
+      const int k = i / kFwdGroups;
       const UnitCoord c = unit_coord(p, (int)blockIdx.x + i * (int)gridDim.x);
       mbar_wait(smem_u32(&bar_s[g]), (uint32_t)(k & 1));
       tc_fence_after();
-      float m = -INFINITY;
-      for (int j = 0; j < ri.nch; ++j) {
+      float l, mb;
+      if (ri.nch == 1) {
+        // whole block of the row in registers: mask folded into the scores, 4-way split reductions
         uint32_t r[32];
-        tmem_ld_x32(tS + ri.col0 + 32 * j, r);
+        tmem_ld_x32(tS + ri.col0, r);
         tmem_ld_wait();
-        const uint32_t mk = chunk_mask(ri, j);
+        float sc[32];
 #pragma unroll
-        for (int b = 0; b < 32; ++b)
-          if ((mk >> b) & 1u) m = fmaxf(m, __uint_as_float(r[b]));
-      }
-      const float mb = m * p.scale_log2;
-      float l = 0.f;
-      for (int j = 0; j < ri.nch; ++j) {
-        uint32_t r[32];
-        tmem_ld_x32(tS + ri.col0 + 32 * j, r);
-        tmem_ld_wait();
-        const uint32_t mk = chunk_mask(ri, j);
+        for (int b = 0; b < 32; ++b) sc[b] = ((mk0 >> b) & 1u) ? __uint_as_float(r[b]) : -INFINITY;
+        const float m = max32(sc);
+        mb = ri.frame_ok ? m * p.scale_log2 : 0.f;
         uint32_t pk[16];
+        float l4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int b = 0; b < 32; b += 2) {
-          const float p0 = ((mk >> b) & 1u) ? fast_ex2(fmaf(__uint_as_float(r[b]), p.scale_log2, -mb)) : 0.f;
-          const float p1 = ((mk >> (b + 1)) & 1u) ? fast_ex2(fmaf(__uint_as_float(r[b + 1]), p.scale_log2, -mb)) : 0.f;
-          const uint32_t w = pack_bf16(p0, p1);
-          l += bf16_lo(w) + bf16_hi(w);
+          const uint32_t w = pack_bf16(fast_ex2(fmaf(sc[b], p.scale_log2, -mb)), fast_ex2(fmaf(sc[b + 1], p.scale_log2, -mb)));
+          l4[(b >> 1) & 1] += bf16_lo(w);
+          l4[2 + ((b >> 1) & 1)] += bf16_hi(w);
           pk[b >> 1] = w;
         }
-        store_p_chunk(tile, ri.row, ri.col0 + 32 * j, pk);
+        l = (l4[0] + l4[1]) + (l4[2] + l4[3]);
+        store_p_chunk(tile, ri.row, ri.col0, pk);
+      } else {
+        float m = -INFINITY;
+        for (int j = 0; j < ri.nch; ++j) {
+          uint32_t r[32];
+          tmem_ld_x32(tS + ri.col0 + 32 * j, r);
+          tmem_ld_wait();
+          const uint32_t mk = chunk_mask(ri, j);
+#pragma unroll
+          for (int b = 0; b < 32; ++b)
+            if ((mk >> b) & 1u) m = fmaxf(m, __uint_as_float(r[b]));
+        }
+        mb = m * p.scale_log2;
+        l = 0.f;
+        for (int j = 0; j < ri.nch; ++j) {
+          uint32_t r[32];
+          tmem_ld_x32(tS + ri.col0 + 32 * j, r);
+          tmem_ld_wait();
+          const uint32_t mk = chunk_mask(ri, j);
+          uint32_t pk[16];
+#pragma unroll
+          for (int b = 0; b < 32; b += 2) {
+            const float p0 = ((mk >> b) & 1u) ? fast_ex2(fmaf(__uint_as_float(r[b]), p.scale_log2, -mb)) : 0.f;
+            const float p1 = ((mk >> (b + 1)) & 1u) ? fast_ex2(fmaf(__uint_as_float(r[b + 1]), p.scale_log2, -mb)) : 0.f;
+            const uint32_t w = pack_bf16(p0, p1);
+            l += bf16_lo(w) + bf16_hi(w);
+            pk[b >> 1] = w;
+          }
+          store_p_chunk(tile, ri.row, ri.col0 + 32 * j, pk);
+        }
       }
       fence_proxy_async();
       tc_fence_before();
@@ -266,7 +331,7 @@ attn_temporal_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const Tem
       tmem_ld_wait();
       tc_fence_before();
       mbar_arrive(smem_u32(&bar_ofree[g]));
-      if (ri.frame_ok && ri.sl < p.SC && c.s0 + ri.sl < p.n) {
+      if (ri.frame_ok && c.s0 + ri.sl < p.n) {
         const size_t tok = ((size_t)c.b * p.T + ri.t) * p.n + c.s0 + ri.sl;
         store_row32_bf16(p.out + tok * p.ldo + c.head * 32, o, 1.0f / l);
         if (p.lse != nullptr) p.lse[tok * p.heads + c.head] = mb + log2f(l);
@@ -275,7 +340,7 @@ attn_temporal_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const Tem
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 9) {
+  if (warp == kMmaWarp) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }
@@ -342,41 +407,53 @@ attn_temporal_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __g
       const uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);
       const uint32_t idesc_t = umma_idesc_bf16(128, 32, 1, 1);   // dV, dK: both operands MN-major
       const uint32_t idesc_q = umma_idesc_bf16(128, 32, 0, 1);   // dQ: A K-major, B MN-major
-      auto issue_out = [&](int j) {
-        const int g = j & 1, k = j >> 1;
-        mbar_wait(smem_u32(&bar_pds[g]), (uint32_t)(k & 1));
-        tc_fence_after();
-        const uint32_t st = sStage + (uint32_t)(j % kBwdStages) * 4 * kTTile;
-        const uint32_t sQ = st, sK = st + kTTile, sDO = st + 3 * kTTile;
-        const uint32_t sPt = sPdS + (uint32_t)g * 4 * kTPanel, sDS = sPt + 2 * kTPanel;
-        const uint32_t tb = tmem_base + (uint32_t)g * 256;  // outputs reuse the consumed S / dP columns
-        const uint32_t tDV = tb, tDK = tb + 32, tDQ = tb + 64;
+      int is = 0, ip = 0;  // next S/dP pair, next output triple to issue
+      uint32_t idle = 0;
+      while (ip < n_mine) {
+        bool progressed = false;
+        if (is < n_mine) {
+          const int st = is % kBwdStages, g = is & 1, k = is >> 1;
+          // the outputs of unit is-2 alias this S/dP buffer: wait until its epilogue has read them
+          if (mbar_test(smem_u32(&bar_full[st]), (uint32_t)((is / kBwdStages) & 1)) &&
+              (k == 0 || mbar_test(smem_u32(&bar_free[g]), (uint32_t)((k - 1) & 1)))) {
+            tc_fence_after();
+            const uint32_t sb = sStage + (uint32_t)st * 4 * kTTile;
+            const uint32_t sQ = sb, sK = sb + kTTile, sV = sb + 2 * kTTile, sDO = sb + 3 * kTTile;
+            const uint32_t tS = tmem_base + (uint32_t)g * 256, tDP = tS + 128;
 #pragma unroll
-        for (int kk = 0; kk < 8; ++kk) {
-          umma_ss(tDV, umma_desc_mnmajor(sPt + kk * 2048, kTPanel), tdesc_sw64(sDO + kk * 1024), idesc_t, (uint32_t)(kk != 0));
-          umma_ss(tDK, umma_desc_mnmajor(sDS + kk * 2048, kTPanel), tdesc_sw64(sQ + kk * 1024), idesc_t, (uint32_t)(kk != 0));
-          umma_ss(tDQ, umma_desc_kmajor(sDS + (uint32_t)(kk >> 2) * kTPanel + (uint32_t)(kk & 3) * 32),
-                  tdesc_sw64(sK + (uint32_t)kk * 16 * kTRowB), idesc_q, (uint32_t)(kk != 0));
+            for (int kq = 0; kq < 2; ++kq) umma_ss(tS, tdesc_sw64(sQ + kq * 32), tdesc_sw64(sK + kq * 32), idesc_s, (uint32_t)kq);
+#pragma unroll
+            for (int kq = 0; kq < 2; ++kq) umma_ss(tDP, tdesc_sw64(sDO + kq * 32), tdesc_sw64(sV + kq * 32), idesc_s, (uint32_t)kq);
+            umma_commit(smem_u32(&bar_sdp[g]));
+            ++is;
+            progressed = true;
+          }
         }
-        umma_commit(smem_u32(&bar_out[g]));
-        umma_commit(smem_u32(&bar_empty[j % kBwdStages]));
-      };
-      for (int i = 0; i < n_mine; ++i) {
-        const int st = i % kBwdStages, g = i & 1, k = i >> 1;
-        mbar_wait(smem_u32(&bar_full[st]), (uint32_t)((i / kBwdStages) & 1));
-        if (k >= 1) mbar_wait(smem_u32(&bar_free[g]), (uint32_t)((k - 1) & 1));  // outputs of unit i-2 read out
-        tc_fence_after();
-        const uint32_t sb = sStage + (uint32_t)st * 4 * kTTile;
-        const uint32_t sQ = sb, sK = sb + kTTile, sV = sb + 2 * kTTile, sDO = sb + 3 * kTTile;
-        const uint32_t tS = tmem_base + (uint32_t)g * 256, tDP = tS + 128;
+        if (ip < is) {
+          const int g = ip & 1, k = ip >> 1;
+          if (mbar_test(smem_u32(&bar_pds[g]), (uint32_t)(k & 1))) {
+            tc_fence_after();
+            const uint32_t st = sStage + (uint32_t)(ip % kBwdStages) * 4 * kTTile;
+            const uint32_t sQ = st, sK = st + kTTile, sDO = st + 3 * kTTile;
+            const uint32_t sPt = sPdS + (uint32_t)g * 4 * kTPanel, sDS = sPt + 2 * kTPanel;
+            const uint32_t tb = tmem_base + (uint32_t)g * 256;  // outputs reuse the consumed S / dP columns
+            const uint32_t tDV = tb, tDK = tb + 32, tDQ = tb + 64;
 #pragma unroll
-        for (int kq = 0; kq < 2; ++kq) umma_ss(tS, tdesc_sw64(sQ + kq * 32), tdesc_sw64(sK + kq * 32), idesc_s, (uint32_t)kq);
-#pragma unroll
-        for (int kq = 0; kq < 2; ++kq) umma_ss(tDP, tdesc_sw64(sDO + kq * 32), tdesc_sw64(sV + kq * 32), idesc_s, (uint32_t)kq);
-        umma_commit(smem_u32(&bar_sdp[g]));
-        if (i >= 1) issue_out(i - 1);
+            for (int kk = 0; kk < 8; ++kk) {
+              umma_ss(tDV, umma_desc_mnmajor(sPt + kk * 2048, kTPanel), tdesc_sw64(sDO + kk * 1024), idesc_t, (uint32_t)(kk != 0));
+              umma_ss(tDK, umma_desc_mnmajor(sDS + kk * 2048, kTPanel), tdesc_sw64(sQ + kk * 1024), idesc_t, (uint32_t)(kk != 0));
+              umma_ss(tDQ, umma_desc_kmajor(sDS + (uint32_t)(kk >> 2) * kTPanel + (uint32_t)(kk & 3) * 32),
+                      tdesc_sw64(sK + (uint32_t)kk * 16 * kTRowB), idesc_q, (uint32_t)(kk != 0));
+            }
+            umma_commit(smem_u32(&bar_out[g]));
+            umma_commit(smem_u32(&bar_empty[ip % kBwdStages]));
+            ++ip;
+            progressed = true;
+          }
+        }
+        if (progressed) idle = 0;
+        else if (++idle > (1u << 24)) __trap();
       }
-      if (n_mine >= 1) issue_out(n_mine - 1);
     }
   } else {
     const int g = warp >> 2;
@@ -384,64 +461,98 @@ attn_temporal_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __g
     const uint32_t lane_addr = (uint32_t)(ri.quarter * 32) << 16;
     const uint32_t tS = tmem_base + (uint32_t)g * 256 + lane_addr, tDP = tS + 128;
     const uint32_t sPt = sPdS + (uint32_t)g * 4 * kTPanel, sDS = sPt + 2 * kTPanel;
+    const uint32_t mk0 = chunk_mask(ri, 0);
     for (int i = g; i < n_mine; i += 2) {
       const int k = i >> 1;
       const UnitCoord c = unit_coord(p, (int)blockIdx.x + i * (int)gridDim.x);
       mbar_wait(smem_u32(&bar_sdp[g]), (uint32_t)(k & 1));
       tc_fence_after();
-      // pass 1: row maximum
-      float m = -INFINITY;
-      for (int j = 0; j < ri.nch; ++j) {
-        uint32_t s[32];
-        tmem_ld_x32(tS + ri.col0 + 32 * j, s);
+      if (ri.nch == 1) {
+        // the whole block of the row lives in registers: one TMEM read of S and dP
+        uint32_t sr[32], dpr[32];
+        tmem_ld_x32(tS + ri.col0, sr);
+        tmem_ld_x32(tDP + ri.col0, dpr);
         tmem_ld_wait();
-        const uint32_t mk = chunk_mask(ri, j);
+        float e[32];
 #pragma unroll
-        for (int b = 0; b < 32; ++b)
-          if ((mk >> b) & 1u) m = fmaxf(m, __uint_as_float(s[b]));
-      }
-      const float mb = m * p.scale_log2;
-      // pass 2: softmax denominator and delta = sum_j P_j dP_j
-      float l = 0.f, pd = 0.f;
-      for (int j = 0; j < ri.nch; ++j) {
-        uint32_t s[32], dp[32];
-        tmem_ld_x32(tS + ri.col0 + 32 * j, s);
-        tmem_ld_x32(tDP + ri.col0 + 32 * j, dp);
-        tmem_ld_wait();
-        const uint32_t mk = chunk_mask(ri, j);
+        for (int b = 0; b < 32; ++b) e[b] = ((mk0 >> b) & 1u) ? __uint_as_float(sr[b]) : -INFINITY;
+        const float m = max32(e);
+        const float mb = ri.frame_ok ? m * p.scale_log2 : 0.f;
+        float l4[4] = {0.f, 0.f, 0.f, 0.f}, d4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int b = 0; b < 32; ++b) {
-          const float e = ((mk >> b) & 1u) ? fast_ex2(fmaf(__uint_as_float(s[b]), p.scale_log2, -mb)) : 0.f;
-          l += e;
-          pd = fmaf(e, __uint_as_float(dp[b]), pd);
+          e[b] = fast_ex2(fmaf(e[b], p.scale_log2, -mb));
+          l4[b & 3] += e[b];
+          d4[b & 3] = fmaf(e[b], __uint_as_float(dpr[b]), d4[b & 3]);
         }
-      }
-      const float inv = l > 0.f ? 1.0f / l : 0.f;  // l == 0 only on padding rows
-      const float delta = pd * inv;
-      // pass 3: P and dS tiles
-      for (int j = 0; j < ri.nch; ++j) {
-        uint32_t s[32], dp[32];
-        tmem_ld_x32(tS + ri.col0 + 32 * j, s);
-        tmem_ld_x32(tDP + ri.col0 + 32 * j, dp);
-        tmem_ld_wait();
-        const uint32_t mk = chunk_mask(ri, j);
+        const float l = (l4[0] + l4[1]) + (l4[2] + l4[3]);
+        const float inv = l > 0.f ? 1.0f / l : 0.f;  // l == 0 only on padding rows
+        const float delta = ((d4[0] + d4[1]) + (d4[2] + d4[3])) * inv;
+        const float inv_s = inv * p.scale;
         uint32_t pk[16], dk[16];
 #pragma unroll
         for (int b = 0; b < 32; b += 2) {
-          float p0 = 0.f, p1 = 0.f, d0 = 0.f, d1 = 0.f;
-          if ((mk >> b) & 1u) {
-            p0 = fast_ex2(fmaf(__uint_as_float(s[b]), p.scale_log2, -mb)) * inv;
-            d0 = p0 * (__uint_as_float(dp[b]) - delta) * p.scale;
-          }
-          if ((mk >> (b + 1)) & 1u) {
-            p1 = fast_ex2(fmaf(__uint_as_float(s[b + 1]), p.scale_log2, -mb)) * inv;
-            d1 = p1 * (__uint_as_float(dp[b + 1]) - delta) * p.scale;
-          }
-          pk[b >> 1] = pack_bf16(p0, p1);
-          dk[b >> 1] = pack_bf16(d0, d1);
+          pk[b >> 1] = pack_bf16(e[b] * inv, e[b + 1] * inv);
+          dk[b >> 1] = pack_bf16(e[b] * inv_s * (__uint_as_float(dpr[b]) - delta),
+                                 e[b + 1] * inv_s * (__uint_as_float(dpr[b + 1]) - delta));
         }
-        store_p_chunk(sPt, ri.row, ri.col0 + 32 * j, pk);
-        store_p_chunk(sDS, ri.row, ri.col0 + 32 * j, dk);
+        store_p_chunk(sPt, ri.row, ri.col0, pk);
+        store_p_chunk(sDS, ri.row, ri.col0, dk);
+      } else {
+        // pass 1: row maximum
+        float m = -INFINITY;
+        for (int j = 0; j < ri.nch; ++j) {
+          uint32_t s[32];
+          tmem_ld_x32(tS + ri.col0 + 32 * j, s);
+          tmem_ld_wait();
+          const uint32_t mk = chunk_mask(ri, j);
+#pragma unroll
+          for (int b = 0; b < 32; ++b)
+            if ((mk >> b) & 1u) m = fmaxf(m, __uint_as_float(s[b]));
+        }
+        const float mb = m * p.scale_log2;
+        // pass 2: softmax denominator and delta = sum_j P_j dP_j
+        float l = 0.f, pd = 0.f;
+        for (int j = 0; j < ri.nch; ++j) {
+          uint32_t s[32], dp[32];
+          tmem_ld_x32(tS + ri.col0 + 32 * j, s);
+          tmem_ld_x32(tDP + ri.col0 + 32 * j, dp);
+          tmem_ld_wait();
+          const uint32_t mk = chunk_mask(ri, j);
+#pragma unroll
+          for (int b = 0; b < 32; ++b) {
+            const float e = ((mk >> b) & 1u) ? fast_ex2(fmaf(__uint_as_float(s[b]), p.scale_log2, -mb)) : 0.f;
+            l += e;
+            pd = fmaf(e, __uint_as_float(dp[b]), pd);
+          }
+        }
+        const float inv = l > 0.f ? 1.0f / l : 0.f;
+        const float delta = pd * inv;
+        // pass 3: P and dS tiles
+        for (int j = 0; j < ri.nch; ++j) {
+          uint32_t s[32], dp[32];
+          tmem_ld_x32(tS + ri.col0 + 32 * j, s);
+          tmem_ld_x32(tDP + ri.col0 + 32 * j, dp);
+          tmem_ld_wait();
+          const uint32_t mk = chunk_mask(ri, j);
+          uint32_t pk[16], dk[16];
+#pragma unroll
+          for (int b = 0; b < 32; b += 2) {
+            float p0 = 0.f, p1 = 0.f, d0 = 0.f, d1 = 0.f;
+            if ((mk >> b) & 1u) {
+              p0 = fast_ex2(fmaf(__uint_as_float(s[b]), p.scale_log2, -mb)) * inv;
+              d0 = p0 * (__uint_as_float(dp[b]) - delta) * p.scale;
+            }
+            if ((mk >> (b + 1)) & 1u) {
+              p1 = fast_ex2(fmaf(__uint_as_float(s[b + 1]), p.scale_log2, -mb)) * inv;
+              d1 = p1 * (__uint_as_float(dp[b + 1]) - delta) * p.scale;
+            }
+            pk[b >> 1] = pack_bf16(p0, p1);
+            dk[b >> 1] = pack_bf16(d0, d1);
+          }
+          store_p_chunk(sPt, ri.row, ri.col0 + 32 * j, pk);
+          store_p_chunk(sDS, ri.row, ri.col0 + 32 * j, dk);
+        }
       }
       fence_proxy_async();
       tc_fence_before();
@@ -449,21 +560,21 @@ attn_temporal_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __g
       mbar_wait(smem_u32(&bar_out[g]), (uint32_t)(k & 1));
       tc_fence_after();
       const uint32_t tb = tmem_base + (uint32_t)g * 256 + lane_addr;
-      const bool valid = ri.frame_ok && ri.sl < p.SC && c.s0 + ri.sl < p.n;
+      const bool valid = ri.frame_ok && c.s0 + ri.sl < p.n;
       const size_t tok = ((size_t)c.b * p.T + ri.t) * p.n + c.s0 + ri.sl;
       __nv_bfloat16* drow = p.dqkv + (valid ? tok * p.ld_dqkv : 0) + c.head * 32;
-      uint32_t r[32];
-      tmem_ld_x32(tb + 64, r);
-      tmem_ld_wait();
-      if (valid) store_row32_bf16(drow + p.q_col, r, 1.0f);
-      tmem_ld_x32(tb + 32, r);
-      tmem_ld_wait();
-      if (valid) store_row32_bf16(drow + p.k_col, r, 1.0f);
-      tmem_ld_x32(tb, r);
+      uint32_t rq[32], rk[32], rv[32];
+      tmem_ld_x32(tb + 64, rq);
+      tmem_ld_x32(tb + 32, rk);
+      tmem_ld_x32(tb, rv);
       tmem_ld_wait();
       tc_fence_before();
       mbar_arrive(smem_u32(&bar_free[g]));
-      if (valid) store_row32_bf16(drow + p.v_col, r, 1.0f);
+      if (valid) {
+        store_row32_bf16(drow + p.q_col, rq, 1.0f);
+        store_row32_bf16(drow + p.k_col, rk, 1.0f);
+        store_row32_bf16(drow + p.v_col, rv, 1.0f);
+      }
     }
   }
   tc_fence_before();
@@ -510,7 +621,7 @@ extern "C" int hma_attn_temporal_fwd(const void* qkv, long long ld_qkv, int B, i
   p.out = static_cast<__nv_bfloat16*>(out); p.ldo = ldo; p.lse = lse;
   CUtensorMap tm;
   if (int rc = make_unit_map(&tm, qkv, ld_qkv, B, T, n, p)) return rc;
-  constexpr size_t smem = 1024 + kFwdStages * 3 * kTTile + 4 * kTPanel;
+  constexpr size_t smem = 1024 + kFwdStages * 3 * kTTile + kFwdGroups * 2 * kTPanel;
   static bool attr_done = false;
   if (!attr_done) {
     HMA_CHECK_CUDA(cudaFuncSetAttribute(attn_temporal_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -518,7 +629,7 @@ extern "C" int hma_attn_temporal_fwd(const void* qkv, long long ld_qkv, int B, i
   }
   int grid = hma_host::sm_count();
   if (grid > p.units) grid = p.units;
-  attn_temporal_tc_fwd_kernel<<<grid, 320, smem, static_cast<cudaStream_t>(stream_)>>>(tm, p);
+  attn_temporal_tc_fwd_kernel<<<grid, kFwdThreads, smem, static_cast<cudaStream_t>(stream_)>>>(tm, p);
   HMA_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
