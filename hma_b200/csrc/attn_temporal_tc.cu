@@ -45,6 +45,7 @@ constexpr int kFwdStages = 6;   // units in flight per SM: a stage stays occupie
 constexpr int kFwdGroups = 2;   // softmax warpgroups, one TMEM S buffer + one P tile each
 constexpr int kBwdStages = 3;
 constexpr int kGroupThreads = 128;
+constexpr int kBwdThreads = 2 * kGroupThreads + 5 * 32;  // + producer, S/dP issuer, dV / dK / dQ issuers
 
 __device__ __forceinline__ uint64_t tdesc_sw64(uint32_t saddr) {
   uint64_t d = 0;
@@ -55,6 +56,19 @@ __device__ __forceinline__ uint64_t tdesc_sw64(uint32_t saddr) {
   d |= 4ull << 61;
   return d;
 }
+
+// Descriptors are built once per role and advanced by adding (byte offset >> 4) to the low word: the single
+// thread that issues the contractions is on the critical path of every unit.
+__device__ __forceinline__ uint64_t mk_desc(uint32_t lo, uint32_t hi) {
+  uint64_t d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(hi));
+  return d;
+}
+constexpr uint32_t kHiSw64 = (512u >> 4) | (1u << 14) | (4u << 29);    // SBO 512, version 1, SWIZZLE_64B
+constexpr uint32_t kHiSw128 = (1024u >> 4) | (1u << 14) | (2u << 29);  // SBO 1024, version 1, SWIZZLE_128B
+__device__ __forceinline__ uint32_t lo_sw64(uint32_t addr) { return (addr >> 4) | ((2048u >> 4) << 16); }
+__device__ __forceinline__ uint32_t lo_k128(uint32_t addr) { return (addr >> 4) | ((16u >> 4) << 16); }
+__device__ __forceinline__ uint32_t lo_mn128(uint32_t addr) { return (addr >> 4) | ((uint32_t)(kTPanel >> 4) << 16); }
 
 struct UnitCoord {
   int b, s0, head;
@@ -155,7 +169,7 @@ __device__ __forceinline__ float max32(const float (&s)[32]) {
 // ------------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------------
-constexpr int kFwdThreads = kFwdGroups * kGroupThreads + 64;
+constexpr int kFwdThreads = kFwdGroups * kGroupThreads + 96;  // + producer, S issuer, P V issuer
 
 __global__ void __launch_bounds__(kFwdThreads, 1)
 attn_temporal_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const TemporalTcParams p) {
@@ -211,48 +225,40 @@ attn_temporal_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const Tem
       }
     }
   } else if (warp == kMmaWarp) {
-    // ---------------------------------------------------------------- UMMA issuer (polls: no head-of-line blocking)
+    // ---------------------------------------------------------------- S = Q K^T issuer
     if (elect_one()) {
       const uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);
+      const uint32_t q0 = lo_sw64(sStage);
+      for (int is = 0; is < n_mine; ++is) {
+        const int st = is % kFwdStages, g = is % kFwdGroups, k = is / kFwdGroups;
+        mbar_wait(smem_u32(&bar_full[st]), (uint32_t)((is / kFwdStages) & 1));
+        // S buffer g (which O aliases) is free once the epilogue of unit is - kFwdGroups has read O
+        if (k >= 1) mbar_wait(smem_u32(&bar_ofree[g]), (uint32_t)((k - 1) & 1));
+        tc_fence_after();
+        const uint32_t qlo = q0 + (uint32_t)st * (3 * kTTile >> 4), klo = qlo + (kTTile >> 4);
+        const uint32_t tS = tmem_base + (uint32_t)g * 128;
+        umma_ss(tS, mk_desc(qlo, kHiSw64), mk_desc(klo, kHiSw64), idesc_s, 0u);
+        umma_ss(tS, mk_desc(qlo + 2, kHiSw64), mk_desc(klo + 2, kHiSw64), idesc_s, 1u);
+        umma_commit(smem_u32(&bar_s[g]));
+      }
+    }
+  } else if (warp == kMmaWarp + 1) {
+    // ---------------------------------------------------------------- O = P V issuer
+    if (elect_one()) {
       const uint32_t idesc_pv = umma_idesc_bf16(128, 32, 0, 1);
-      int is = 0, ip = 0;  // next S / next P V to issue
-      uint32_t idle = 0;
-      while (ip < n_mine) {
-        bool progressed = false;
-        if (is < n_mine) {
-          const int st = is % kFwdStages, g = is % kFwdGroups, k = is / kFwdGroups;
-          // S buffer g (which O aliases) is free once the epilogue of unit is - kFwdGroups has read O
-          if (mbar_test(smem_u32(&bar_full[st]), (uint32_t)((is / kFwdStages) & 1)) &&
-              (k == 0 || mbar_test(smem_u32(&bar_ofree[g]), (uint32_t)((k - 1) & 1)))) {
-            tc_fence_after();
-            const uint32_t sQ = sStage + (uint32_t)st * 3 * kTTile, sK = sQ + kTTile;
-            const uint32_t tS = tmem_base + (uint32_t)g * 128;
+      const uint32_t v0 = lo_sw64(sStage + 2 * kTTile), p0 = lo_k128(sP);
+      for (int ip = 0; ip < n_mine; ++ip) {
+        const int st = ip % kFwdStages, g = ip % kFwdGroups, k = ip / kFwdGroups;
+        mbar_wait(smem_u32(&bar_p[g]), (uint32_t)(k & 1));
+        tc_fence_after();
+        const uint32_t plo = p0 + (uint32_t)g * (2 * kTPanel >> 4), vlo = v0 + (uint32_t)st * (3 * kTTile >> 4);
+        const uint32_t tO = tmem_base + (uint32_t)g * 128;  // over the consumed S columns
 #pragma unroll
-            for (int kq = 0; kq < 2; ++kq) umma_ss(tS, tdesc_sw64(sQ + kq * 32), tdesc_sw64(sK + kq * 32), idesc_s, (uint32_t)kq);
-            umma_commit(smem_u32(&bar_s[g]));
-            ++is;
-            progressed = true;
-          }
-        }
-        if (ip < is) {
-          const int g = ip % kFwdGroups, k = ip / kFwdGroups;
-          if (mbar_test(smem_u32(&bar_p[g]), (uint32_t)(k & 1))) {
-            tc_fence_after();
-            const uint32_t tile = sP + (uint32_t)g * 2 * kTPanel;
-            const uint32_t sV = sStage + (uint32_t)(ip % kFwdStages) * 3 * kTTile + 2 * kTTile;
-            const uint32_t tO = tmem_base + (uint32_t)g * 128;  // over the consumed S columns
-#pragma unroll
-            for (int kk = 0; kk < 8; ++kk)
-              umma_ss(tO, umma_desc_kmajor(tile + (uint32_t)(kk >> 2) * kTPanel + (uint32_t)(kk & 3) * 32),
-                      tdesc_sw64(sV + (uint32_t)kk * 16 * kTRowB), idesc_pv, (uint32_t)(kk != 0));
-            umma_commit(smem_u32(&bar_o[g]));
-            umma_commit(smem_u32(&bar_empty[ip % kFwdStages]));
-            ++ip;
-            progressed = true;
-          }
-        }
-        if (progressed) idle = 0;
-        else if (++idle > (1u << 24)) __trap();
+        for (int kk = 0; kk < 8; ++kk)
+          umma_ss(tO, mk_desc(plo + (uint32_t)(((kk >> 2) * kTPanel + (kk & 3) * 32) >> 4), kHiSw128),
+                  mk_desc(vlo + (uint32_t)(kk * 1024 >> 4), kHiSw64), idesc_pv, (uint32_t)(kk != 0));
+        umma_commit(smem_u32(&bar_o[g]));
+        umma_commit(smem_u32(&bar_empty[st]));
       }
     }
   } else {
@@ -349,7 +355,7 @@ attn_temporal_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const Tem
 // ------------------------------------------------------------------------------------------------
 // backward
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(320, 1)
+__global__ void __launch_bounds__(kBwdThreads, 1)
 attn_temporal_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
                             const TemporalTcParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -364,12 +370,12 @@ attn_temporal_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __g
   if (threadIdx.x == 0) {
     for (int s = 0; s < kBwdStages; ++s) {
       mbar_init(smem_u32(&bar_full[s]), 1);
-      mbar_init(smem_u32(&bar_empty[s]), 1);
+      mbar_init(smem_u32(&bar_empty[s]), 3);   // three output issuers release a stage
     }
     for (int g = 0; g < 2; ++g) {
       mbar_init(smem_u32(&bar_sdp[g]), 1);
       mbar_init(smem_u32(&bar_pds[g]), kGroupThreads);
-      mbar_init(smem_u32(&bar_out[g]), 1);
+      mbar_init(smem_u32(&bar_out[g]), 3);
       mbar_init(smem_u32(&bar_free[g]), kGroupThreads);
     }
     fence_barrier_init();
@@ -403,56 +409,56 @@ attn_temporal_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __g
       }
     }
   } else if (warp == 9) {
+    // ---------------------------------------------------------------- S = Q K^T and dP = dO V^T issuer
     if (elect_one()) {
       const uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);
-      const uint32_t idesc_t = umma_idesc_bf16(128, 32, 1, 1);   // dV, dK: both operands MN-major
-      const uint32_t idesc_q = umma_idesc_bf16(128, 32, 0, 1);   // dQ: A K-major, B MN-major
-      int is = 0, ip = 0;  // next S/dP pair, next output triple to issue
-      uint32_t idle = 0;
-      while (ip < n_mine) {
-        bool progressed = false;
-        if (is < n_mine) {
-          const int st = is % kBwdStages, g = is & 1, k = is >> 1;
-          // the outputs of unit is-2 alias this S/dP buffer: wait until its epilogue has read them
-          if (mbar_test(smem_u32(&bar_full[st]), (uint32_t)((is / kBwdStages) & 1)) &&
-              (k == 0 || mbar_test(smem_u32(&bar_free[g]), (uint32_t)((k - 1) & 1)))) {
-            tc_fence_after();
-            const uint32_t sb = sStage + (uint32_t)st * 4 * kTTile;
-            const uint32_t sQ = sb, sK = sb + kTTile, sV = sb + 2 * kTTile, sDO = sb + 3 * kTTile;
-            const uint32_t tS = tmem_base + (uint32_t)g * 256, tDP = tS + 128;
+      const uint32_t q0 = lo_sw64(sStage);
+      for (int is = 0; is < n_mine; ++is) {
+        const int st = is % kBwdStages, g = is & 1, k = is >> 1;
+        mbar_wait(smem_u32(&bar_full[st]), (uint32_t)((is / kBwdStages) & 1));
+        // the outputs of unit is-2 alias this S/dP buffer: wait until its epilogue has read them
+        if (k >= 1) mbar_wait(smem_u32(&bar_free[g]), (uint32_t)((k - 1) & 1));
+        tc_fence_after();
+        const uint32_t qlo = q0 + (uint32_t)st * (4 * kTTile >> 4), klo = qlo + (kTTile >> 4), vlo = klo + (kTTile >> 4),
+                       dlo = vlo + (kTTile >> 4);
+        const uint32_t tS = tmem_base + (uint32_t)g * 256, tDP = tS + 128;
+        umma_ss(tS, mk_desc(qlo, kHiSw64), mk_desc(klo, kHiSw64), idesc_s, 0u);
+        umma_ss(tS, mk_desc(qlo + 2, kHiSw64), mk_desc(klo + 2, kHiSw64), idesc_s, 1u);
+        umma_ss(tDP, mk_desc(dlo, kHiSw64), mk_desc(vlo, kHiSw64), idesc_s, 0u);
+        umma_ss(tDP, mk_desc(dlo + 2, kHiSw64), mk_desc(vlo + 2, kHiSw64), idesc_s, 1u);
+        umma_commit(smem_u32(&bar_sdp[g]));
+      }
+    }
+  } else if (warp >= 10) {
+    // ---------------------------------------------------------------- output issuers: warp 10 dV, 11 dK, 12 dQ
+    if (elect_one()) {
+      const int which = warp - 10;
+      const uint32_t idesc = which == 2 ? umma_idesc_bf16(128, 32, 0, 1)   // dQ: A K-major, B MN-major
+                                        : umma_idesc_bf16(128, 32, 1, 1);  // dV, dK: both operands MN-major
+      // A: P (dV) or dS (dK, dQ) tile of the group; B: dO (dV), Q (dK) or K (dQ) tile of the stage
+      const uint32_t a_base = sPdS + (which == 0 ? 0u : 2u * kTPanel);
+      const uint32_t a0 = which == 2 ? lo_k128(a_base) : lo_mn128(a_base);
+      const uint32_t b0 = lo_sw64(sStage + (which == 0 ? 3u : (which == 1 ? 0u : 1u)) * kTTile);
+      const uint32_t tcol = which == 0 ? 0u : (which == 1 ? 32u : 64u);  // outputs reuse the consumed S / dP columns
+      for (int ip = 0; ip < n_mine; ++ip) {
+        const int st = ip % kBwdStages, g = ip & 1, k = ip >> 1;
+        mbar_wait(smem_u32(&bar_pds[g]), (uint32_t)(k & 1));
+        tc_fence_after();
+        const uint32_t alo = a0 + (uint32_t)g * (4 * kTPanel >> 4), blo = b0 + (uint32_t)st * (4 * kTTile >> 4);
+        const uint32_t tD = tmem_base + (uint32_t)g * 256 + tcol;
+        if (which == 2) {
 #pragma unroll
-            for (int kq = 0; kq < 2; ++kq) umma_ss(tS, tdesc_sw64(sQ + kq * 32), tdesc_sw64(sK + kq * 32), idesc_s, (uint32_t)kq);
+          for (int kk = 0; kk < 8; ++kk)
+            umma_ss(tD, mk_desc(alo + (uint32_t)(((kk >> 2) * kTPanel + (kk & 3) * 32) >> 4), kHiSw128),
+                    mk_desc(blo + (uint32_t)(kk * 1024 >> 4), kHiSw64), idesc, (uint32_t)(kk != 0));
+        } else {
 #pragma unroll
-            for (int kq = 0; kq < 2; ++kq) umma_ss(tDP, tdesc_sw64(sDO + kq * 32), tdesc_sw64(sV + kq * 32), idesc_s, (uint32_t)kq);
-            umma_commit(smem_u32(&bar_sdp[g]));
-            ++is;
-            progressed = true;
-          }
+          for (int kk = 0; kk < 8; ++kk)
+            umma_ss(tD, mk_desc(alo + (uint32_t)(kk * 2048 >> 4), kHiSw128), mk_desc(blo + (uint32_t)(kk * 1024 >> 4), kHiSw64),
+                    idesc, (uint32_t)(kk != 0));
         }
-        if (ip < is) {
-          const int g = ip & 1, k = ip >> 1;
-          if (mbar_test(smem_u32(&bar_pds[g]), (uint32_t)(k & 1))) {
-            tc_fence_after();
-            const uint32_t st = sStage + (uint32_t)(ip % kBwdStages) * 4 * kTTile;
-            const uint32_t sQ = st, sK = st + kTTile, sDO = st + 3 * kTTile;
-            const uint32_t sPt = sPdS + (uint32_t)g * 4 * kTPanel, sDS = sPt + 2 * kTPanel;
-            const uint32_t tb = tmem_base + (uint32_t)g * 256;  // outputs reuse the consumed S / dP columns
-            const uint32_t tDV = tb, tDK = tb + 32, tDQ = tb + 64;
-#pragma unroll
-            for (int kk = 0; kk < 8; ++kk) {
-              umma_ss(tDV, umma_desc_mnmajor(sPt + kk * 2048, kTPanel), tdesc_sw64(sDO + kk * 1024), idesc_t, (uint32_t)(kk != 0));
-              umma_ss(tDK, umma_desc_mnmajor(sDS + kk * 2048, kTPanel), tdesc_sw64(sQ + kk * 1024), idesc_t, (uint32_t)(kk != 0));
-              umma_ss(tDQ, umma_desc_kmajor(sDS + (uint32_t)(kk >> 2) * kTPanel + (uint32_t)(kk & 3) * 32),
-                      tdesc_sw64(sK + (uint32_t)kk * 16 * kTRowB), idesc_q, (uint32_t)(kk != 0));
-            }
-            umma_commit(smem_u32(&bar_out[g]));
-            umma_commit(smem_u32(&bar_empty[ip % kBwdStages]));
-            ++ip;
-            progressed = true;
-          }
-        }
-        if (progressed) idle = 0;
-        else if (++idle > (1u << 24)) __trap();
+        umma_commit(smem_u32(&bar_out[g]));
+        umma_commit(smem_u32(&bar_empty[st]));
       }
     }
   } else {
@@ -659,7 +665,7 @@ extern "C" int hma_attn_temporal_bwd(const void* qkv, long long ld_qkv, const vo
   }
   int grid = hma_host::sm_count();
   if (grid > p.units) grid = p.units;
-  attn_temporal_tc_bwd_kernel<<<grid, 320, smem, static_cast<cudaStream_t>(stream_)>>>(tmQ, tmD, p);
+  attn_temporal_tc_bwd_kernel<<<grid, kBwdThreads, smem, static_cast<cudaStream_t>(stream_)>>>(tmQ, tmD, p);
   HMA_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
