@@ -97,6 +97,7 @@ attn_spatial_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
     fence_barrier_init();
   }
   __syncthreads();
+  pdl_wait();
   if (warp == 8) {
     // start the operand loads first: they overlap the per-row statistics below
     if (elect_one()) {
@@ -323,7 +324,7 @@ extern "C" int hma_attn_spatial_bwd(const void* qkv, long long ld_qkv, const voi
     HMA_CHECK_CUDA(cudaFuncSetAttribute(attn_spatial_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_done = true;
   }
-  attn_spatial_bwd_kernel<<<frames * heads, 288, smem, static_cast<cudaStream_t>(stream_)>>>(tmQ, tmD, p);
-  HMA_CHECK_CUDA(cudaGetLastError());
+  HMA_CHECK_CUDA(hma_host::launch_pdl(attn_spatial_bwd_kernel, dim3(frames * heads), dim3(288), smem,
+                                      static_cast<cudaStream_t>(stream_), tmQ, tmD, p));
   return 0;
 }

@@ -131,6 +131,7 @@ attn_spatial_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnFwd
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
+  pdl_wait();  // several waves of CTAs: dependents are released by CTA exit, not early
   const uint32_t tS = tmem_base;
   const uint32_t tOa = tmem_base + 192;
   const uint32_t tOb = tmem_base + 224;
@@ -276,7 +277,7 @@ extern "C" int hma_attn_spatial_fwd(const void* qkv, long long ld_qkv, int frame
     HMA_CHECK_CUDA(cudaFuncSetAttribute(attn_spatial_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_done = true;
   }
-  attn_spatial_fwd_kernel<<<frames * heads, 160, smem, static_cast<cudaStream_t>(stream_)>>>(tm, p);
-  HMA_CHECK_CUDA(cudaGetLastError());
+  HMA_CHECK_CUDA(hma_host::launch_pdl(attn_spatial_fwd_kernel, dim3(frames * heads), dim3(160), smem,
+                                      static_cast<cudaStream_t>(stream_), tm, p));
   return 0;
 }

@@ -52,6 +52,8 @@ __device__ __forceinline__ float head_dot(const float (&q)[8], const uint4& ku) 
 __global__ void __launch_bounds__(256) attn_temporal_cached_kernel(const TemporalCachedParams p) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * 8 + warp;
+  pdl_wait();
+  pdl_launch_dependents();
   if (row >= p.rows) return;
   const __nv_bfloat16* qrow = p.qkv + row * p.ld_qkv;
   float q[8];
@@ -115,6 +117,8 @@ struct KvAppendParams {
 
 __global__ void __launch_bounds__(256) kv_append_kernel(const KvAppendParams p) {
   const long long total = (long long)p.B * p.frames * p.n * 64;  // 16-byte pieces: 32 of K + 32 of V per token
+  pdl_wait();
+  pdl_launch_dependents();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int piece = (int)(i & 63);
     const long long tok = i >> 6;  // (b, t, s) order
@@ -146,8 +150,8 @@ extern "C" int hma_attn_temporal_cached(const void* qkv, long long ld_qkv, int q
   p.rows = rows; p.n_prev = n_prev;
   p.scale_log2 = scale * 1.4426950408889634f;
   p.out = static_cast<__nv_bfloat16*>(out); p.ldo = ldo;
-  attn_temporal_cached_kernel<<<(rows + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream_)>>>(p);
-  HMA_CHECK_CUDA(cudaGetLastError());
+  HMA_CHECK_CUDA(hma_host::launch_pdl(attn_temporal_cached_kernel, dim3((rows + 7) / 8), dim3(256), 0,
+                                      static_cast<cudaStream_t>(stream_), p));
   return 0;
 }
 
@@ -166,7 +170,6 @@ extern "C" int hma_kv_cache_append(const void* qkv, long long ld_qkv, int k_col,
   long long blocks = (total + 255) / 256;
   const long long cap = (long long)hma_host::sm_count() * 16;
   if (blocks > cap) blocks = cap;
-  kv_append_kernel<<<(int)blocks, 256, 0, static_cast<cudaStream_t>(stream_)>>>(p);
-  HMA_CHECK_CUDA(cudaGetLastError());
+  HMA_CHECK_CUDA(hma_host::launch_pdl(kv_append_kernel, dim3((int)blocks), dim3(256), 0, static_cast<cudaStream_t>(stream_), p));
   return 0;
 }

@@ -207,6 +207,8 @@ attn_temporal_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const Tem
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
+  pdl_wait();
+  pdl_launch_dependents();
 
   if (warp == kProducerWarp) {
     // ---------------------------------------------------------------- TMA producer
@@ -390,6 +392,8 @@ attn_temporal_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __g
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
+  pdl_wait();
+  pdl_launch_dependents();
 
   if (warp == 8) {
     if (elect_one()) {
@@ -635,8 +639,8 @@ extern "C" int hma_attn_temporal_fwd(const void* qkv, long long ld_qkv, int B, i
   }
   int grid = hma_host::sm_count();
   if (grid > p.units) grid = p.units;
-  attn_temporal_tc_fwd_kernel<<<grid, kFwdThreads, smem, static_cast<cudaStream_t>(stream_)>>>(tm, p);
-  HMA_CHECK_CUDA(cudaGetLastError());
+  HMA_CHECK_CUDA(hma_host::launch_pdl(attn_temporal_tc_fwd_kernel, dim3(grid), dim3(kFwdThreads), smem,
+                                      static_cast<cudaStream_t>(stream_), tm, p));
   return 0;
 }
 
@@ -665,7 +669,7 @@ extern "C" int hma_attn_temporal_bwd(const void* qkv, long long ld_qkv, const vo
   }
   int grid = hma_host::sm_count();
   if (grid > p.units) grid = p.units;
-  attn_temporal_tc_bwd_kernel<<<grid, kBwdThreads, smem, static_cast<cudaStream_t>(stream_)>>>(tmQ, tmD, p);
-  HMA_CHECK_CUDA(cudaGetLastError());
+  HMA_CHECK_CUDA(hma_host::launch_pdl(attn_temporal_tc_bwd_kernel, dim3(grid), dim3(kBwdThreads), smem,
+                                      static_cast<cudaStream_t>(stream_), tmQ, tmD, p));
   return 0;
 }

@@ -83,6 +83,17 @@ __device__ __forceinline__ void fence_proxy_async() {
 }
 
 // ------------------------------------------------------------------------------------------
+// Programmatic dependent launch: kernels are launched with programmatic stream serialization
+// (hma_host::launch_pdl), so a kernel's CTAs may start while the previous kernel in the stream is
+// still draining. Everything before pdl_wait() (barrier init, TMEM allocation, descriptor
+// prefetch, shared-memory zeroing) overlaps the predecessor's tail; pdl_wait() returns once the
+// predecessor grid has completed and its memory is visible. NO global memory may be read or
+// written before it. pdl_launch_dependents() lets the next kernel's CTAs be scheduled early.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// ------------------------------------------------------------------------------------------
 // TMA (cp.async.bulk.tensor), 2-D tiles
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
@@ -283,6 +294,25 @@ int make_tmap_bf16_3d_sw64(CUtensorMap* map, const void* base, uint64_t d0, uint
                            uint64_t stride1_bytes, uint64_t stride2_bytes, uint32_t b1, uint32_t b2);
 
 int sm_count();
+bool pdl_enabled();  // HMA_B200_NO_PDL=1 turns programmatic dependent launch off (A/B measurements)
+
+// Launch `kern` with programmatic stream serialization; the kernel MUST call hma::pdl_wait() before it
+// touches global memory.
+template <class... KArgs, class... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                              Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
 
 #define HMA_CHECK_CUDA(expr)                                                              \
   do {                                                                                    \

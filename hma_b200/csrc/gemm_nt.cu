@@ -247,6 +247,8 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
+  pdl_wait();               // everything above overlapped the previous kernel's tail
+  pdl_launch_dependents();
 
   if (warp == 0) {
     // ---------------------------------------------------------------- TMA producer
@@ -367,8 +369,7 @@ static int launch_nt(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmN
   if (per_n < 1) per_n = 1;
   if (per_n > m_tiles) per_n = m_tiles;
   const int grid = per_n * n_tiles;
-  kern<<<grid, 384, smem, stream>>>(tmA, tmB, p);
-  HMA_CHECK_CUDA(cudaGetLastError());
+  HMA_CHECK_CUDA(hma_host::launch_pdl(kern, dim3(grid), dim3(384), smem, stream, tmA, tmB, p));
   return 0;
 }
 

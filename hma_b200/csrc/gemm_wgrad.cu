@@ -69,6 +69,8 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
+  pdl_wait();
+  pdl_launch_dependents();
 
   if (warp == 0) {
     if (elect_one()) {
@@ -158,8 +160,7 @@ static int launch_wgrad(const void* G, long long ldg, const void* X, long long l
   chunk = (chunk + 63) / 64 * 64;
   splits = (p.tokens + chunk - 1) / chunk;
   p.chunk = chunk;
-  kern<<<dim3(tiles, splits), 256, smem, stream>>>(tmG, tmX, p);
-  HMA_CHECK_CUDA(cudaGetLastError());
+  HMA_CHECK_CUDA(hma_host::launch_pdl(kern, dim3(tiles, splits), dim3(256), smem, stream, tmG, tmX, p));
   return 0;
 }
 

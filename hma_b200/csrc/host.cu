@@ -1,5 +1,6 @@
 // Host-side plumbing shared by every entry point: error string, TMA descriptor encoding
 // (through the driver entry point, so the library does not link libcuda), SM count.
+#include <cstdlib>
 #include "common.cuh"
 #include "../../include/hma_b200.h"
 
@@ -81,6 +82,15 @@ int make_tmap_bf16_3d_sw64(CUtensorMap* map, const void* base, uint64_t d0, uint
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   HMA_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(3d) failed with CUresult %d", (int)r);
   return 0;
+}
+
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("HMA_B200_NO_PDL");
+    v = (e != nullptr && e[0] == '1') ? 0 : 1;
+  }
+  return v == 1;
 }
 
 int sm_count() {

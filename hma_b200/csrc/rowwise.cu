@@ -61,6 +61,8 @@ struct LnParams {
 };
 
 __global__ void __launch_bounds__(256) ln_fwd_kernel(const LnParams p) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row = blockIdx.x * 8 + warp;
   if (row >= p.rows) return;
@@ -123,6 +125,8 @@ struct LnBwdParams {
 };
 
 __global__ void __launch_bounds__(256) ln_bwd_kernel(const LnBwdParams p) {
+  pdl_wait();
+  pdl_launch_dependents();
   __shared__ float red[8][2 * kC];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int r0 = blockIdx.x * p.rows_per_cta;
@@ -254,7 +258,7 @@ extern "C" int hma_ln_fwd(const float* x, long long ldx, int rows, int mode, con
               "ln_fwd: bad row remap %d -> %d", src_group, dst_group);
   LnParams p{x, ldx, rows, mode, gamma, beta, mod, rows_per_group, eps, static_cast<__nv_bfloat16*>(y), ldy, stats,
              src_group, dst_group};
-  ln_fwd_kernel<<<(rows + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream_)>>>(p);
+  HMA_CHECK_CUDA(hma_host::launch_pdl(ln_fwd_kernel, dim3((rows + 7) / 8), dim3(256), 0, static_cast<cudaStream_t>(stream_), p));
   HMA_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -275,7 +279,7 @@ extern "C" int hma_ln_bwd(const void* dy, long long lddy, const float* x, long l
                 rows_per_group > 0 ? rows_per_group : rows, rpc, dx, lddx, dgamma, dbeta, dmod,
                 static_cast<__nv_bfloat16*>(dy_next), colsum_next};
   HMA_REQUIRE(colsum_next == nullptr || dy_next != nullptr, "ln_bwd: colsum_next needs dy_next");
-  ln_bwd_kernel<<<(rows + rpc - 1) / rpc, 256, 0, static_cast<cudaStream_t>(stream_)>>>(p);
+  HMA_CHECK_CUDA(hma_host::launch_pdl(ln_bwd_kernel, dim3((rows + rpc - 1) / rpc), dim3(256), 0, static_cast<cudaStream_t>(stream_), p));
   HMA_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -295,6 +299,8 @@ extern "C" int hma_cast_transpose(const float* W, int R, int Cc, void* Wb, void*
 namespace hma {
 
 __global__ void __launch_bounds__(256) cast_flat_kernel(const float* x, __nv_bfloat16* y, long long count4) {
+  pdl_wait();
+  pdl_launch_dependents();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= count4) return;
   const float4 v = reinterpret_cast<const float4*>(x)[i];
@@ -390,8 +396,7 @@ extern "C" int hma_cast_bf16(const float* x, void* y, long long count, void* str
   if (count == 0) return 0;
   HMA_REQUIRE(count % 4 == 0, "cast_bf16: element count must be a multiple of 4");
   const long long c4 = count / 4;
-  cast_flat_kernel<<<(unsigned)((c4 + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream_)>>>(
-      x, static_cast<__nv_bfloat16*>(y), c4);
+  HMA_CHECK_CUDA(hma_host::launch_pdl(cast_flat_kernel, dim3((unsigned)((c4 + 255) / 256)), dim3(256), 0, static_cast<cudaStream_t>(stream_), x, static_cast<__nv_bfloat16*>(y), c4));
   HMA_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -472,6 +477,8 @@ namespace hma {
 // y = bf16(x) for fp32 rows of 256, plus (optionally) colsum[c] += sum_r x[r, c] of the ROUNDED values:
 // the bias gradient of the projection that consumes y, for free while the row streams by.
 __global__ void __launch_bounds__(256) cast_colsum_kernel(const float* x, __nv_bfloat16* y, int rows, float* colsum) {
+  pdl_wait();
+  pdl_launch_dependents();
   __shared__ float red[8][kC];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int r0 = blockIdx.x * 64;
@@ -504,6 +511,8 @@ __global__ void __launch_bounds__(256) cast_colsum_kernel(const float* x, __nv_b
 // out[c] += sum_r G[r, c], bf16 G with C % 8 == 0, C <= 2048: 16-byte loads, 128-row slabs per CTA.
 __global__ void __launch_bounds__(256) colsum_wide_kernel(const __nv_bfloat16* G, long long ld, int rows, int C,
                                                           float* out) {
+  pdl_wait();
+  pdl_launch_dependents();
   extern __shared__ float wred[];  // [groups][C]
   const int vec_per_row = C / 8;
   const int groups = 256 / vec_per_row;  // row groups processed concurrently (>= 1)
@@ -568,8 +577,7 @@ __global__ void __launch_bounds__(256) cast_transpose_batched_kernel(const CastD
 extern "C" int hma_cast_colsum(const float* x, void* y, int rows, float* colsum, void* stream_) {
   using namespace hma;
   if (rows == 0) return 0;
-  cast_colsum_kernel<<<(rows + 63) / 64, 256, 0, static_cast<cudaStream_t>(stream_)>>>(
-      x, static_cast<__nv_bfloat16*>(y), rows, colsum);
+  HMA_CHECK_CUDA(hma_host::launch_pdl(cast_colsum_kernel, dim3((rows + 63) / 64), dim3(256), 0, static_cast<cudaStream_t>(stream_), x, static_cast<__nv_bfloat16*>(y), rows, colsum));
   HMA_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -592,8 +600,7 @@ extern "C" int hma_colsum_bf16(const void* G, long long ld, int rows, int C, flo
   const int groups = 256 / vec_per_row;
   HMA_REQUIRE(groups >= 1, "colsum: C too wide");
   const size_t smem = (size_t)groups * C * sizeof(float);
-  colsum_wide_kernel<<<(rows + 127) / 128, 256, smem, static_cast<cudaStream_t>(stream_)>>>(
-      static_cast<const __nv_bfloat16*>(G), ld, rows, C, out);
+  HMA_CHECK_CUDA(hma_host::launch_pdl(colsum_wide_kernel, dim3((rows + 127) / 128), dim3(256), smem, static_cast<cudaStream_t>(stream_), static_cast<const __nv_bfloat16*>(G), ld, rows, C, out));
   HMA_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
