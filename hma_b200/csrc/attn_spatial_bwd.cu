@@ -36,7 +36,9 @@ constexpr int kBRowB = 64;
 constexpr int kBMaxN = 320;
 constexpr int kBTile = kBMaxN * kBRowB;   // 20 KB per operand
 constexpr int kBPanel = 128 * 128;        // [128 x 64] bf16 panel
-constexpr int kComputeThreads = 256;
+constexpr int kComputeWarps = 16;
+constexpr int kComputeThreads = kComputeWarps * 32;
+constexpr int kBwdThreads = kComputeThreads + 96;  // + three UMMA-issuing warps (the first also issues the TMA loads)
 
 __device__ __forceinline__ uint64_t bdesc_sw64(uint32_t saddr) {
   uint64_t d = 0;
@@ -58,7 +60,7 @@ __device__ __forceinline__ void store_head_row(__nv_bfloat16* dst, const uint32_
                        pack_bf16(__uint_as_float(r[8 * q + 6]), __uint_as_float(r[8 * q + 7])));
 }
 
-__global__ void __launch_bounds__(288, 1)
+__global__ void __launch_bounds__(kBwdThreads, 1)
 attn_spatial_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
                         const AttnBwdParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -89,7 +91,7 @@ attn_spatial_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
     mbar_init(smem_u32(&bar_tfree), kComputeThreads);
     for (int i = 0; i < 2; ++i) {
       mbar_init(smem_u32(&bar_pds[i]), kComputeThreads);
-      mbar_init(smem_u32(&bar_mma[i]), 1);
+      mbar_init(smem_u32(&bar_mma[i]), 2);  // dV/dK issuer + dQ issuer
     }
     mbar_init(smem_u32(&bar_kv), 1);
     mbar_init(smem_u32(&bar_epi), kComputeThreads);
@@ -98,7 +100,7 @@ attn_spatial_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
   }
   __syncthreads();
   pdl_wait();
-  if (warp == 8) {
+  if (warp == kComputeWarps) {
     // start the operand loads first: they overlap the per-row statistics below
     if (elect_one()) {
       const uint32_t bl = smem_u32(&bar_load);
@@ -136,76 +138,107 @@ attn_spatial_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
   const uint32_t tS = tmem_base, tDP = tmem_base + 128, tDQ = tmem_base + 256, tDK = tmem_base + 352,
                  tDV = tmem_base + 384;
 
-  if (warp == 8) {
+  if (warp >= kComputeWarps) {
+    // ---------------------------------------------------------------- three UMMA issuers (one elected lane each):
+    //   warp 16: S = Q K^T and dP = dO V^T of the NEXT tile pair as soon as TMEM is handed back
+    //   warp 17: dV += P^T dO and dK += dS^T Q          warp 18: dQ += dS K
+    // A single issuing thread was the bottleneck (28 tcgen05.mma + their descriptors per tile pair); descriptors
+    // are now a constant high word plus a low word advanced by (byte offset >> 4).
     if (elect_one()) {
+      const int role = warp - kComputeWarps;
+      const int NI = ntile * ntile;
       mbar_wait(smem_u32(&bar_load), 0);
       tc_fence_after();
-
-      auto issue_sdp = [&](int kt, int qt) {
-        const int nk = min(128, n - kt * 128);
-        const uint32_t idesc = umma_idesc_bf16(128, nk, 0, 0);
-        const uint32_t q_addr = sQ + (uint32_t)qt * 128 * kBRowB;
-        const uint32_t do_addr = sDO + (uint32_t)qt * 128 * kBRowB;
-        const uint32_t k_addr = sK + (uint32_t)kt * 128 * kBRowB;
-        const uint32_t v_addr = sV + (uint32_t)kt * 128 * kBRowB;
-#pragma unroll
-        for (int k = 0; k < 2; ++k) umma_ss(tS, bdesc_sw64(q_addr + k * 32), bdesc_sw64(k_addr + k * 32), idesc, (uint32_t)k);
-#pragma unroll
-        for (int k = 0; k < 2; ++k) umma_ss(tDP, bdesc_sw64(do_addr + k * 32), bdesc_sw64(v_addr + k * 32), idesc, (uint32_t)k);
+      constexpr uint32_t kHi64 = (512u >> 4) | (1u << 14) | (4u << 29);    // SBO 512, version 1, SWIZZLE_64B
+      constexpr uint32_t kHi128 = (1024u >> 4) | (1u << 14) | (2u << 29);  // SBO 1024, version 1, SWIZZLE_128B
+      auto lo64 = [](uint32_t addr) { return (addr >> 4) | ((2048u >> 4) << 16); };
+      auto mk = [](uint32_t lo, uint32_t hi) {
+        uint64_t d;
+        asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(hi));
+        return d;
       };
-
-      const uint32_t idesc_t = umma_idesc_bf16(128, 32, 1, 1);   // dV, dK: both operands MN-major
-      const uint32_t idesc_q = umma_idesc_bf16(128, 32, 0, 1);   // dQ: A K-major, B MN-major
-      const int NI = ntile * ntile;
-      issue_sdp(0, 0);
-      umma_commit(smem_u32(&bar_sdp));
-      for (int it = 0; it < NI; ++it) {
-        const int kt = it / ntile, qt = it % ntile;
-        const int nk = min(128, n - kt * 128);
-        const int kq = min(128, n - qt * 128);
-        const int bsel = it & 1;
-        // S / dP of the next pair as soon as this pair's have been copied out of TMEM
-        mbar_wait(smem_u32(&bar_tfree), (uint32_t)(it & 1));
-        tc_fence_after();
-        if (it + 1 < NI) {
-          issue_sdp((it + 1) / ntile, (it + 1) % ntile);
+      if (role == 0) {
+        const uint32_t q0 = lo64(sQ), k0 = lo64(sK), v0 = lo64(sV), d0 = lo64(sDO);
+        constexpr uint32_t kTileStep = (128u * kBRowB) >> 4;
+        int kt = 0, qt = 0;
+        for (int it = 0; it < NI; ++it) {
+          if (it > 0) {  // S / dP of pair `it` once pair it-1 has been copied out of TMEM
+            mbar_wait(smem_u32(&bar_tfree), (uint32_t)((it - 1) & 1));
+            tc_fence_after();
+          }
+          const int nk = min(128, n - kt * 128);
+          const uint32_t idesc = umma_idesc_bf16(128, nk, 0, 0);
+          const uint32_t ql = q0 + (uint32_t)qt * kTileStep, dl = d0 + (uint32_t)qt * kTileStep;
+          const uint32_t kl = k0 + (uint32_t)kt * kTileStep, vl = v0 + (uint32_t)kt * kTileStep;
+          umma_ss(tS, mk(ql, kHi64), mk(kl, kHi64), idesc, 0u);
+          umma_ss(tS, mk(ql + 2, kHi64), mk(kl + 2, kHi64), idesc, 1u);
+          umma_ss(tDP, mk(dl, kHi64), mk(vl, kHi64), idesc, 0u);
+          umma_ss(tDP, mk(dl + 2, kHi64), mk(vl + 2, kHi64), idesc, 1u);
           umma_commit(smem_u32(&bar_sdp));
+          if (++qt == ntile) { qt = 0; ++kt; }
         }
-        mbar_wait(smem_u32(&bar_pds[bsel]), (uint32_t)((it >> 1) & 1));
-        tc_fence_after();
-        if (qt == 0 && kt > 0) {
-          mbar_wait(smem_u32(&bar_epi), (uint32_t)((kt - 1) & 1));
+      } else if (role == 1) {
+        const uint32_t idesc_t = umma_idesc_bf16(128, 32, 1, 1);   // both operands MN-major
+        const uint32_t p0 = (sP0 >> 4) | ((uint32_t)(kBPanel >> 4) << 16);
+        const uint32_t q0 = lo64(sQ), d0 = lo64(sDO);
+        int kt = 0, qt = 0;
+        for (int it = 0; it < NI; ++it) {
+          const int bsel = it & 1;
+          const int kq16 = min(128, n - qt * 128) >> 4;
+          mbar_wait(smem_u32(&bar_pds[bsel]), (uint32_t)((it >> 1) & 1));
+          if (qt == 0 && kt > 0) mbar_wait(smem_u32(&bar_epi), (uint32_t)((kt - 1) & 1));  // dK / dV of the last key tile read out
           tc_fence_after();
+          const uint32_t pl = p0 + (uint32_t)bsel * (kPdsBuf >> 4), sl = pl + ((2 * kBPanel) >> 4);
+          const uint32_t ql = q0 + (uint32_t)qt * ((128u * kBRowB) >> 4), dl = d0 + (uint32_t)qt * ((128u * kBRowB) >> 4);
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk) {
+            if (kk < kq16) {
+              umma_ss(tDV, mk(pl + (uint32_t)(kk * 2048 >> 4), kHi128), mk(dl + (uint32_t)(kk * 1024 >> 4), kHi64), idesc_t,
+                      (uint32_t)((qt | kk) != 0));
+              umma_ss(tDK, mk(sl + (uint32_t)(kk * 2048 >> 4), kHi128), mk(ql + (uint32_t)(kk * 1024 >> 4), kHi64), idesc_t,
+                      (uint32_t)((qt | kk) != 0));
+            }
+          }
+          umma_commit(smem_u32(&bar_mma[bsel]));
+          if (qt == ntile - 1) umma_commit(smem_u32(&bar_kv));
+          if (++qt == ntile) { qt = 0; ++kt; }
         }
-        const uint32_t sP = sP0 + (uint32_t)bsel * kPdsBuf;
-        const uint32_t sDS = sP + 2 * kBPanel;
-        const uint32_t q_addr = sQ + (uint32_t)qt * 128 * kBRowB;
-        const uint32_t do_addr = sDO + (uint32_t)qt * 128 * kBRowB;
-        for (int kk = 0; kk < kq / 16; ++kk) {
-          umma_ss(tDV, umma_desc_mnmajor(sP + kk * 2048, kBPanel), bdesc_sw64(do_addr + kk * 1024), idesc_t,
-                  (uint32_t)((qt | kk) != 0));
-          umma_ss(tDK, umma_desc_mnmajor(sDS + kk * 2048, kBPanel), bdesc_sw64(q_addr + kk * 1024), idesc_t,
-                  (uint32_t)((qt | kk) != 0));
+      } else {
+        const uint32_t idesc_q = umma_idesc_bf16(128, 32, 0, 1);   // A K-major, B MN-major
+        const uint32_t s0 = ((sP0 + 2 * kBPanel) >> 4) | ((16u >> 4) << 16);
+        const uint32_t k0 = lo64(sK);
+        int kt = 0, qt = 0;
+        for (int it = 0; it < NI; ++it) {
+          const int bsel = it & 1;
+          const int nk16 = min(128, n - kt * 128) >> 4;
+          mbar_wait(smem_u32(&bar_pds[bsel]), (uint32_t)((it >> 1) & 1));
+          tc_fence_after();
+          const uint32_t sl = s0 + (uint32_t)bsel * (kPdsBuf >> 4);
+          const uint32_t kl = k0 + (uint32_t)kt * ((128u * kBRowB) >> 4);
+          const uint32_t tD = tDQ + (uint32_t)qt * 32;
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk) {
+            if (kk < nk16)
+              umma_ss(tD, mk(sl + (uint32_t)(((kk >> 2) * kBPanel + (kk & 3) * 32) >> 4), kHi128),
+                      mk(kl + (uint32_t)(kk * 16 * kBRowB >> 4), kHi64), idesc_q, (uint32_t)((kt | kk) != 0));
+          }
+          umma_commit(smem_u32(&bar_mma[bsel]));
+          if (it == NI - 1) umma_commit(smem_u32(&bar_final));
+          if (++qt == ntile) { qt = 0; ++kt; }
         }
-        for (int kk = 0; kk < nk / 16; ++kk)
-          umma_ss(tDQ + (uint32_t)qt * 32, umma_desc_kmajor(sDS + (uint32_t)(kk >> 2) * kBPanel + (uint32_t)(kk & 3) * 32),
-                  bdesc_sw64(sK + (uint32_t)(kt * 128 + kk * 16) * kBRowB), idesc_q, (uint32_t)((kt | kk) != 0));
-        umma_commit(smem_u32(&bar_mma[bsel]));
-        if (qt == ntile - 1) umma_commit(smem_u32(&bar_kv));
-        if (it == NI - 1) umma_commit(smem_u32(&bar_final));
       }
     }
   } else {
-    // ---------------------------------------------------------------- compute warps 0..7
-    const int quarter = warp & 3, half = warp >> 2;
+    // ---------------------------------------------------------------- compute warps 0..15
+    // warp w owns TMEM lane quarter w % 4 (query rows) and the 32-key column chunk w / 4 of the 128-key tile:
+    // four warps per scheduler keep the exp / dS arithmetic flowing while others wait on TMEM or barriers.
+    const int quarter = warp & 3, colq = warp >> 2;
     const int row = quarter * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
     int it = 0;
     for (int kt = 0; kt < ntile; ++kt) {
       const int nk = min(128, n - kt * 128);
       for (int qt = 0; qt < ntile; ++qt, ++it) {
-        // (9 warps -> three share one SM sub-partition -> <= 168 registers: do every spin-wait BEFORE the
-        //  128 S/dP registers become live so nothing spills inside a wait loop)
         const int bsel = it & 1;
         if (it >= 2) mbar_wait(smem_u32(&bar_mma[bsel]), (uint32_t)(((it - 2) >> 1) & 1));
         mbar_wait(smem_u32(&bar_sdp), (uint32_t)(it & 1));
@@ -213,43 +246,52 @@ attn_spatial_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
         const int qi = qt * 128 + row;
         const float L = qi < n ? s_lse[qi] : 0.f;
         const float delta = qi < n ? s_delta[qi] : 0.f;
-        // copy this warp's S / dP columns to registers and hand TMEM back to the tensor core
-        uint32_t s[2][32], dp[2][32];
-        const bool has0 = half * 64 < nk, has1 = half * 64 + 32 < nk;  // warp-uniform
-        if (has0) {
-          tmem_ld_x32(tS + lane_addr + half * 64, s[0]);
-          tmem_ld_x32(tDP + lane_addr + half * 64, dp[0]);
-        }
-        if (has1) {
-          tmem_ld_x32(tS + lane_addr + half * 64 + 32, s[1]);
-          tmem_ld_x32(tDP + lane_addr + half * 64 + 32, dp[1]);
-        }
-        tmem_ld_wait();
-        tc_fence_before();
-        mbar_arrive(smem_u32(&bar_tfree));
+        // S -> P (bf16, to shared memory), then dP -> dS with P re-expanded from its bf16 form: at most 48 tile
+        // values are live per thread (the 17-warp CTA leaves 96 registers per thread). TMEM goes back to the
+        // tensor core as soon as dP has been copied out.
+        const bool has = colq * 32 < nk;  // warp-uniform
         const uint32_t sP = sP0 + (uint32_t)bsel * kPdsBuf;
         const uint32_t sDS = sP + 2 * kBPanel;
+        const uint32_t pan = (uint32_t)(colq >> 1) * kBPanel;
+        uint32_t pk[16];
+        {
+          uint32_t s[32];
+          tmem_ld_x32(tS + lane_addr + colq * 32, s);  // unconditional: columns past nk are allocated, just unused
+          tmem_ld_wait();
+          if (has) {
 #pragma unroll
-        for (int cc = 0; cc < 2; ++cc) {
-          if (cc == 0 ? !has0 : !has1) continue;
-          uint32_t pk[16], dk[16];
+            for (int j = 0; j < 32; j += 2)
+              pk[j >> 1] = pack_bf16(fast_ex2(fmaf(__uint_as_float(s[j]), p.scale_log2, -L)),
+                                     fast_ex2(fmaf(__uint_as_float(s[j + 1]), p.scale_log2, -L)));
 #pragma unroll
-          for (int j = 0; j < 32; j += 2) {
-            const float p0 = fast_ex2(fmaf(__uint_as_float(s[cc][j]), p.scale_log2, -L));
-            const float p1 = fast_ex2(fmaf(__uint_as_float(s[cc][j + 1]), p.scale_log2, -L));
-            const float d0 = p0 * (__uint_as_float(dp[cc][j]) - delta) * p.scale;
-            const float d1 = p1 * (__uint_as_float(dp[cc][j + 1]) - delta) * p.scale;
-            pk[j >> 1] = pack_bf16(p0, p1);
-            dk[j >> 1] = pack_bf16(d0, d1);
+            for (int q = 0; q < 4; ++q) {
+              const uint32_t off = pan + sw128_offset((uint32_t)row, (uint32_t)((colq & 1) * 32 + q * 8));
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sP + off), "r"(pk[4 * q]), "r"(pk[4 * q + 1]),
+                           "r"(pk[4 * q + 2]), "r"(pk[4 * q + 3]) : "memory");
+            }
           }
-          const uint32_t pan = (uint32_t)half * kBPanel;
+        }
+        {
+          uint32_t dp[32];
+          tmem_ld_x32(tDP + lane_addr + colq * 32, dp);
+          tmem_ld_wait();
+          tc_fence_before();
+          mbar_arrive(smem_u32(&bar_tfree));
+          if (has) {
+            const float nds = -delta * p.scale;
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const uint32_t off = pan + sw128_offset((uint32_t)row, (uint32_t)(cc * 32 + q * 8));
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sP + off), "r"(pk[4 * q]), "r"(pk[4 * q + 1]),
-                         "r"(pk[4 * q + 2]), "r"(pk[4 * q + 3]) : "memory");
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sDS + off), "r"(dk[4 * q]), "r"(dk[4 * q + 1]),
-                         "r"(dk[4 * q + 2]), "r"(dk[4 * q + 3]) : "memory");
+            for (int q = 0; q < 4; ++q) {
+              uint32_t dk[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const int e = q * 8 + 2 * j;
+                const float d0 = bf16_lo(pk[e >> 1]) * fmaf(__uint_as_float(dp[e]), p.scale, nds);
+                const float d1 = bf16_hi(pk[e >> 1]) * fmaf(__uint_as_float(dp[e + 1]), p.scale, nds);
+                dk[j] = pack_bf16(d0, d1);
+              }
+              const uint32_t off = pan + sw128_offset((uint32_t)row, (uint32_t)((colq & 1) * 32 + q * 8));
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sDS + off), "r"(dk[0]), "r"(dk[1]), "r"(dk[2]), "r"(dk[3]) : "memory");
+            }
           }
         }
         fence_proxy_async();
@@ -259,32 +301,30 @@ attn_spatial_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
           mbar_wait(smem_u32(&bar_kv), (uint32_t)(kt & 1));
           tc_fence_after();
           uint32_t r[32];
-          tmem_ld_x32((half == 0 ? tDK : tDV) + lane_addr, r);
+          if (colq < 2) tmem_ld_x32((colq == 0 ? tDK : tDV) + lane_addr, r);
           tmem_ld_wait();
           tc_fence_before();
           mbar_arrive(smem_u32(&bar_epi));
           const int ki = kt * 128 + row;
-          if (ki < n)
-            store_head_row(p.dqkv + (size_t)(row0 + ki) * p.ld_dqkv + (half == 0 ? p.k_col : p.v_col) + head * 32, r);
+          if (colq < 2 && ki < n)
+            store_head_row(p.dqkv + (size_t)(row0 + ki) * p.ld_dqkv + (colq == 0 ? p.k_col : p.v_col) + head * 32, r);
         }
       }
     }
     mbar_wait(smem_u32(&bar_final), 0);
     tc_fence_after();
-    if (half == 0) {
-      for (int qt = 0; qt < ntile; ++qt) {
-        uint32_t r[32];
-        tmem_ld_x32(tDQ + (uint32_t)qt * 32 + lane_addr, r);
-        tmem_ld_wait();
-        const int qi = qt * 128 + row;
-        if (qi < n) store_head_row(p.dqkv + (size_t)(row0 + qi) * p.ld_dqkv + p.q_col + head * 32, r);
-      }
+    if (colq < ntile) {  // warps 4*qt .. 4*qt+3 store the dQ rows of query tile qt
+      uint32_t r[32];
+      tmem_ld_x32(tDQ + (uint32_t)colq * 32 + lane_addr, r);
+      tmem_ld_wait();
+      const int qi = colq * 128 + row;
+      if (qi < n) store_head_row(p.dqkv + (size_t)(row0 + qi) * p.ld_dqkv + p.q_col + head * 32, r);
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) {
+  if (warp == kComputeWarps) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }
@@ -324,7 +364,7 @@ extern "C" int hma_attn_spatial_bwd(const void* qkv, long long ld_qkv, const voi
     HMA_CHECK_CUDA(cudaFuncSetAttribute(attn_spatial_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_done = true;
   }
-  HMA_CHECK_CUDA(hma_host::launch_pdl(attn_spatial_bwd_kernel, dim3(frames * heads), dim3(288), smem,
+  HMA_CHECK_CUDA(hma_host::launch_pdl(attn_spatial_bwd_kernel, dim3(frames * heads), dim3(kBwdThreads), smem,
                                       static_cast<cudaStream_t>(stream_), tmQ, tmD, p));
   return 0;
 }
