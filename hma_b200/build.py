@@ -45,6 +45,9 @@ def _stale(target: Path, deps: list[Path]) -> bool:
 
 def build(force: bool = False, verbose: bool = False) -> Path:
     OBJ.mkdir(exist_ok=True)
+    flags = list(NVCC_FLAGS)
+    if os.environ.get("HMA_B200_TIMELINE") == "1":  # development: clock64() event tables (tools/timeline.py)
+        flags += ["-DHMA_TIMELINE"]
     sources = sorted(CSRC.glob("*.cu"))
     headers = sorted(CSRC.glob("*.cuh")) + [ROOT / "include" / "hma_b200.h"]
     nvcc = _nvcc()
@@ -52,7 +55,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     def compile_one(src: Path) -> Path:
         obj = OBJ / (src.stem + ".o")
         if force or _stale(obj, [src] + headers):
-            cmd = [nvcc, *NVCC_FLAGS, "-c", str(src), "-o", str(obj)]
+            cmd = [nvcc, *flags, "-c", str(src), "-o", str(obj)]
             if verbose:
                 cmd.insert(1, "-Xptxas=-v")
                 print(" ".join(cmd), flush=True)

@@ -100,6 +100,7 @@ attn_spatial_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
   }
   __syncthreads();
   pdl_wait();
+  if (threadIdx.x == 0) HMA_TL(0, 0);
   if (warp == kComputeWarps) {
     // start the operand loads first: they overlap the per-row statistics below
     if (elect_one()) {
@@ -149,6 +150,7 @@ attn_spatial_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
       const int NI = ntile * ntile;
       mbar_wait(smem_u32(&bar_load), 0);
       tc_fence_after();
+      if (role == 0) HMA_TL(11, 0);
       constexpr uint32_t kHi64 = (512u >> 4) | (1u << 14) | (4u << 29);    // SBO 512, version 1, SWIZZLE_64B
       constexpr uint32_t kHi128 = (1024u >> 4) | (1u << 14) | (2u << 29);  // SBO 1024, version 1, SWIZZLE_128B
       auto lo64 = [](uint32_t addr) { return (addr >> 4) | ((2048u >> 4) << 16); };
@@ -175,6 +177,7 @@ attn_spatial_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
           umma_ss(tDP, mk(dl, kHi64), mk(vl, kHi64), idesc, 0u);
           umma_ss(tDP, mk(dl + 2, kHi64), mk(vl + 2, kHi64), idesc, 1u);
           umma_commit(smem_u32(&bar_sdp));
+          HMA_TL(1, it);
           if (++qt == ntile) { qt = 0; ++kt; }
         }
       } else if (role == 1) {
@@ -188,6 +191,7 @@ attn_spatial_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
           mbar_wait(smem_u32(&bar_pds[bsel]), (uint32_t)((it >> 1) & 1));
           if (qt == 0 && kt > 0) mbar_wait(smem_u32(&bar_epi), (uint32_t)((kt - 1) & 1));  // dK / dV of the last key tile read out
           tc_fence_after();
+          HMA_TL(2, it);
           const uint32_t pl = p0 + (uint32_t)bsel * (kPdsBuf >> 4), sl = pl + ((2 * kBPanel) >> 4);
           const uint32_t ql = q0 + (uint32_t)qt * ((128u * kBRowB) >> 4), dl = d0 + (uint32_t)qt * ((128u * kBRowB) >> 4);
 #pragma unroll
@@ -201,6 +205,7 @@ attn_spatial_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
           }
           umma_commit(smem_u32(&bar_mma[bsel]));
           if (qt == ntile - 1) umma_commit(smem_u32(&bar_kv));
+          HMA_TL(3, it);
           if (++qt == ntile) { qt = 0; ++kt; }
         }
       } else {
@@ -224,6 +229,7 @@ attn_spatial_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
           }
           umma_commit(smem_u32(&bar_mma[bsel]));
           if (it == NI - 1) umma_commit(smem_u32(&bar_final));
+          HMA_TL(4, it);
           if (++qt == ntile) { qt = 0; ++kt; }
         }
       }
@@ -235,21 +241,38 @@ attn_spatial_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
     const int quarter = warp & 3, colq = warp >> 2;
     const int row = quarter * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+    auto store_dkdv = [&](int kt) {  // warps 0-3 store dK, warps 4-7 dV; every compute thread releases the accumulators
+      mbar_wait(smem_u32(&bar_kv), (uint32_t)(kt & 1));
+      tc_fence_after();
+      uint32_t r[32];
+      tmem_ld_x32((colq == 0 ? tDK : tDV) + lane_addr, r);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(smem_u32(&bar_epi));
+      const int ki = kt * 128 + row;
+      if (colq < 2 && ki < n)
+        store_head_row(p.dqkv + (size_t)(row0 + ki) * p.ld_dqkv + (colq == 0 ? p.k_col : p.v_col) + head * 32, r);
+    };
+    int pending_kt = -1;
     int it = 0;
     for (int kt = 0; kt < ntile; ++kt) {
       const int nk = min(128, n - kt * 128);
       for (int qt = 0; qt < ntile; ++qt, ++it) {
         const int bsel = it & 1;
         if (it >= 2) mbar_wait(smem_u32(&bar_mma[bsel]), (uint32_t)(((it - 2) >> 1) & 1));
+        if (threadIdx.x == 0) HMA_TL(5, it);
         mbar_wait(smem_u32(&bar_sdp), (uint32_t)(it & 1));
         tc_fence_after();
+        if (threadIdx.x == 0) HMA_TL(6, it);
         const int qi = qt * 128 + row;
         const float L = qi < n ? s_lse[qi] : 0.f;
         const float delta = qi < n ? s_delta[qi] : 0.f;
         // S -> P (bf16, to shared memory), then dP -> dS with P re-expanded from its bf16 form: at most 48 tile
         // values are live per thread (the 17-warp CTA leaves 96 registers per thread). TMEM goes back to the
         // tensor core as soon as dP has been copied out.
-        const bool has = colq * 32 < nk;  // warp-uniform
+        // warp-uniform: this warp's key columns exist, and so do its query rows (rows past the frame are never
+        // read by the dV / dK contractions and only produce dQ rows that are not stored)
+        const bool has = colq * 32 < nk && quarter * 32 < min(128, n - qt * 128);
         const uint32_t sP = sP0 + (uint32_t)bsel * kPdsBuf;
         const uint32_t sDS = sP + 2 * kBPanel;
         const uint32_t pan = (uint32_t)(colq >> 1) * kBPanel;
@@ -277,6 +300,7 @@ attn_spatial_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
           tmem_ld_wait();
           tc_fence_before();
           mbar_arrive(smem_u32(&bar_tfree));
+          if (threadIdx.x == 0) HMA_TL(7, it);
           if (has) {
             const float nds = -delta * p.scale;
 #pragma unroll
@@ -296,23 +320,20 @@ attn_spatial_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
         }
         fence_proxy_async();
         mbar_arrive(smem_u32(&bar_pds[bsel]));
-        if (qt == ntile - 1) {
-          // dK / dV of this key tile are complete: warps 0-3 store dK, warps 4-7 store dV
-          mbar_wait(smem_u32(&bar_kv), (uint32_t)(kt & 1));
-          tc_fence_after();
-          uint32_t r[32];
-          if (colq < 2) tmem_ld_x32((colq == 0 ? tDK : tDV) + lane_addr, r);
-          tmem_ld_wait();
-          tc_fence_before();
-          mbar_arrive(smem_u32(&bar_epi));
-          const int ki = kt * 128 + row;
-          if (colq < 2 && ki < n)
-            store_head_row(p.dqkv + (size_t)(row0 + ki) * p.ld_dqkv + (colq == 0 ? p.k_col : p.v_col) + head * 32, r);
+        if (threadIdx.x == 0) HMA_TL(8, it);
+        // dK / dV of a finished key tile are written out one iteration late, after the P / dS of the next tile
+        // pair have been handed to the tensor core, so the stores overlap its contractions
+        if (pending_kt >= 0) {
+          store_dkdv(pending_kt);
+          pending_kt = -1;
         }
+        if (qt == ntile - 1) pending_kt = kt;
       }
     }
+    if (pending_kt >= 0) store_dkdv(pending_kt);
     mbar_wait(smem_u32(&bar_final), 0);
     tc_fence_after();
+    if (threadIdx.x == 0) HMA_TL(9, 0);
     if (colq < ntile) {  // warps 4*qt .. 4*qt+3 store the dQ rows of query tile qt
       uint32_t r[32];
       tmem_ld_x32(tDQ + (uint32_t)colq * 32 + lane_addr, r);
@@ -324,6 +345,7 @@ attn_spatial_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
 
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) HMA_TL(10, 0);
   if (warp == kComputeWarps) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
@@ -368,3 +390,5 @@ extern "C" int hma_attn_spatial_bwd(const void* qkv, long long ld_qkv, const voi
                                       static_cast<cudaStream_t>(stream_), tmQ, tmD, p));
   return 0;
 }
+
+HMA_DEFINE_TIMELINE_READER(hma_timeline_attn_spatial_bwd)

@@ -94,6 +94,27 @@ __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;"
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 // ------------------------------------------------------------------------------------------
+// Development aid (build with HMA_B200_TIMELINE=1): CTA 0 stamps clock64() into a per-source-file
+// table, event `ev` (< 16), slot `i` (< 64); a file that uses it also emits a reader entry point with
+// HMA_DEFINE_TIMELINE_READER(hma_timeline_<file>) (see tools/timeline.py). Compiled out otherwise.
+// ------------------------------------------------------------------------------------------
+#ifdef HMA_TIMELINE
+static __device__ long long g_timeline[16 * 64];
+#define HMA_DEFINE_TIMELINE_READER(fn)                                                              \
+  extern "C" int fn(long long* host_dst) {                                                          \
+    if (cudaDeviceSynchronize() != cudaSuccess) return -1;                                          \
+    return cudaMemcpyFromSymbol(host_dst, hma::g_timeline, sizeof(long long) * 16 * 64) == cudaSuccess ? 0 : -1; \
+  }
+#define HMA_TL(ev, i)                                                                   \
+  do {                                                                                  \
+    if (blockIdx.x == 0 && blockIdx.y == 0 && (i) < 64) g_timeline[(ev) * 64 + (i)] = clock64(); \
+  } while (0)
+#else
+#define HMA_TL(ev, i) do { } while (0)
+#define HMA_DEFINE_TIMELINE_READER(fn)
+#endif
+
+// ------------------------------------------------------------------------------------------
 // TMA (cp.async.bulk.tensor), 2-D tiles
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {

@@ -1,0 +1,44 @@
+#!/usr/bin/env python
+"""Per-CTA event timeline of one kernel (development aid). Build with HMA_B200_TIMELINE=1, then e.g.
+    HMA_B200_TIMELINE=1 python -m hma_b200.build --force && python tools/timeline.py attn_spatial_bwd
+Prints clock64() stamps of CTA 0 relative to its first event, one row per loop iteration."""
+import ctypes, sys, os
+import numpy as np
+import torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from hma_b200 import ops, _lib
+
+KERNELS = {
+    "attn_spatial_bwd": dict(names={0: "start", 11: "loaded", 1: "SdP_issued", 6: "sdp_ready", 5: "c:top", 7: "c:tmem_freed", 8: "c:pds_arrived",
+                                    2: "dVdK:go", 3: "dVdK:done", 4: "dQ:done", 9: "final", 10: "end"}),
+}
+
+def run_attn_spatial_bwd():
+    frames, n, H = 128, 320, 8
+    qkv = torch.randn(frames * n, 768, device="cuda").bfloat16()
+    out, lse = ops.attn_spatial_fwd(qkv, frames, n, H, 0.17, True)
+    dout = torch.randn_like(out)
+    for _ in range(3):
+        ops.attn_spatial_bwd(qkv, out, dout, lse, frames, n, H, 0.17)
+
+def main():
+    name = sys.argv[1]
+    globals()["run_" + name]()
+    torch.cuda.synchronize()
+    buf = (ctypes.c_longlong * (16 * 64))()
+    fn = getattr(_lib.lib(), "hma_timeline_" + name)
+    fn.argtypes = [ctypes.c_void_p]
+    assert fn(buf) == 0
+    a = np.array(buf).reshape(16, 64)
+    names = KERNELS[name]["names"]
+    t0 = a[0, 0]
+    single = [e for e in names if e in (0, 9, 10, 11)]
+    print(" ".join(f"{names[e]}={a[e, 0] - t0}" for e in single))
+    per_it = [e for e in sorted(names) if e not in single]
+    for i in range(12):
+        if all(a[e, i] == 0 for e in per_it):
+            break
+        print(i, " ".join(f"{names[e]}={a[e, i] - t0:6d}" for e in per_it))
+
+if __name__ == "__main__":
+    main()
