@@ -190,16 +190,20 @@ attn_spatial_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnFwd
     uint32_t ps = 0, po = 0;
     for (int t = 0; t < ntiles; ++t) {
       float ma, la, mb = -INFINITY, lb = 0.f;
+      // rows past the frame (second half of the last query tile) are never stored: their warps skip the
+      // exp work (the MUFU pipe is the bottleneck of this kernel) and leave stale, finite P rows behind
+      const bool live = t * 128 + warp * 32 < n;  // warp-uniform
       mbar_wait(smem_u32(&bar_s), ps); ps ^= 1u;
       tc_fence_after();
-      softmax_block(tS + lane_addr, na, p.scale_log2, sP, row, ma, la);
+      ma = -INFINITY; la = 0.f;
+      if (live) softmax_block(tS + lane_addr, na, p.scale_log2, sP, row, ma, la);
       fence_proxy_async();
       tc_fence_before();
       mbar_arrive(smem_u32(&bar_p));
       if (nb > 0) {
         mbar_wait(smem_u32(&bar_s), ps); ps ^= 1u;
         tc_fence_after();
-        softmax_block(tS + lane_addr, nb, p.scale_log2, sP, row, mb, lb);
+        if (live) softmax_block(tS + lane_addr, nb, p.scale_log2, sP, row, mb, lb);
         fence_proxy_async();
         tc_fence_before();
         mbar_arrive(smem_u32(&bar_p));

@@ -6,6 +6,7 @@
 //
 // One CTA = one 128 x BNW tile of dW over one slice of the tokens (split-K); partial tiles are
 // added into fp32 dW with vector red.global. Same warp roles as gemm_nt.cu.
+#include <cstdlib>
 #include "common.cuh"
 #include "../../include/hma_b200.h"
 
@@ -18,13 +19,15 @@ struct WgradParams {
   long long ldw;
 };
 
-constexpr int kWStages = 4;
 constexpr int kBox = 64 * 64 * 2;  // one [64 tok x 64 ch] bf16 box = 8 KB
+// ~192 KB of operand stages per CTA whatever the tile width
+template <int BNW> struct WStages { static constexpr int value = (192 * 1024) / ((2 + BNW / 64) * kBox); };
 
 template <int BNW>
 __global__ void __launch_bounds__(256, 1)
 gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CUtensorMap tmX,
                   const WgradParams p) {
+  constexpr int kWStages = WStages<BNW>::value;
   constexpr int kGStage = 2 * kBox;
   constexpr int kXStage = (BNW / 64) * kBox;
   constexpr int kStage = kGStage + kXStage;
@@ -146,7 +149,7 @@ static int launch_wgrad(const void* G, long long ldg, const void* X, long long l
   if (rc) return rc;
   rc = hma_host::make_tmap_bf16_2d(&tmX, X, (uint64_t)p.Nw, (uint64_t)p.tokens, (uint64_t)ldx * 2, 64, 64);
   if (rc) return rc;
-  constexpr size_t smem = 1024 + (size_t)kWStages * (2 * kBox + (BNW / 64) * kBox);
+  constexpr size_t smem = 1024 + (size_t)WStages<BNW>::value * (2 * kBox + (BNW / 64) * kBox);
   auto kern = gemm_wgrad_kernel<BNW>;
   static bool attr_done = false;
   if (!attr_done) {
@@ -173,10 +176,29 @@ extern "C" int hma_gemm_wgrad(const void* G, long long ldg, const void* X, long 
   if (tokens == 0) return 0;
   HMA_REQUIRE(tokens > 0 && Mw > 0 && Nw > 0, "gemm_wgrad: bad shape tokens=%d Mw=%d Nw=%d", tokens, Mw, Nw);
   HMA_REQUIRE(Mw % 128 == 0, "gemm_wgrad: Mw=%d must be a multiple of 128", Mw);
-  HMA_REQUIRE(Nw % 128 == 0, "gemm_wgrad: Nw=%d must be a multiple of 128", Nw);
+  HMA_REQUIRE(Nw % 64 == 0, "gemm_wgrad: Nw=%d must be a multiple of 64", Nw);
   HMA_REQUIRE((ldw % 4) == 0 && (reinterpret_cast<uintptr_t>(dW) & 15) == 0, "gemm_wgrad: dW must be 16-byte aligned");
   WgradParams p;
   p.tokens = tokens; p.Mw = Mw; p.Nw = Nw; p.chunk = 0; p.dW = dW; p.ldw = ldw;
-  if (Nw % 256 == 0) return launch_wgrad<256>(G, ldg, X, ldx, p, stream);
-  return launch_wgrad<128>(G, ldg, X, ldx, p, stream);
+  // Tile width: every CTA adds its 128 x BNW partial tile into dW with L2 atomics (measured ~0.76 T float adds/s,
+  // the largest single cost of the 128 x 256 version), while a narrower tile re-reads the operands through L2
+  // more often. Pick the width that minimises max(HBM time, L2 time) + atomic time.
+  const int sms = hma_host::sm_count();
+  int best = 0;
+  double best_t = 0.0;
+  for (int bnw : {64, 128, 256}) {
+    if (Nw % bnw != 0) continue;
+    const int tiles = (Mw / 128) * (Nw / bnw);
+    int splits = sms / tiles;
+    if (splits < 1) splits = 1;
+    const double ctas = (double)tiles * splits;
+    const double t_atom = ctas * 128.0 * bnw / 0.76e12;
+    const double t_l2 = 2.0 * tokens * ((double)Mw * (Nw / bnw) + (double)Nw * (Mw / 128)) / 20e12;
+    const double t_hbm = 2.0 * tokens * ((double)Mw + Nw) / 6.5e12;
+    const double t = (t_l2 > t_hbm ? t_l2 : t_hbm) + t_atom;
+    if (best == 0 || t < best_t) { best = bnw; best_t = t; }
+  }
+  if (best == 256) return launch_wgrad<256>(G, ldg, X, ldx, p, stream);
+  if (best == 128) return launch_wgrad<128>(G, ldg, X, ldx, p, stream);
+  return launch_wgrad<64>(G, ldg, X, ldx, p, stream);
 }
