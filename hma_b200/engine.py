@@ -401,6 +401,7 @@ class Engine:
             fork.record(main)  # dact zero-fill and the gradient buffer memset precede the side-stream chain
             side.wait_event(fork)
         dy = None  # bf16 copy of dx whose column sums are already in the consumer's bias gradient
+        side_keep = []
         for i in reversed(range(d.num_layers)):
             L = sv["layers"][i]
             lp = f"decoder.layers.{i}."
@@ -444,7 +445,7 @@ class Engine:
                     ops.gemm_wgrad(dzm, sv["c_bf"], g2(ap + "adaLN_modulation.0.weight"))
                     ops.colsum_bf16(dzm, g2(ap + "adaLN_modulation.0.bias"))
                     ops.gemm_nt(dzm, Wt[ap + "adaLN_modulation.0.weight"], EPI_RESID, resid=dact, out=dact)
-                    dmod.record_stream(side)
+                    side_keep.append((dmod, dmod_bf, dzm))  # alive until the side stream has been joined
             else:
                 dy = ops.cast_colsum(dx, g.get(lp + "spatial_attn.proj.bias"))
             # ---- spatial attention
@@ -463,6 +464,7 @@ class Engine:
             join = torch.cuda.Event()
             join.record(side)
             main.wait_event(join)
+            side_keep.clear()
 
         # ---- embedding / positional / action-token gradients
         ops.embed_bwd(sv["ids"], dx, sv["pos_n"], B, T, S, d.A, d.vs, d.mask_id,

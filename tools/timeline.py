@@ -9,6 +9,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from hma_b200 import ops, _lib
 
 KERNELS = {
+    "gemm_wgrad": dict(single=(0, 3, 4, 5), names={0: "start", 3: "mma_done", 4: "red_issued", 5: "end", 1: "tma_issued", 2: "full"}),
     "attn_spatial_bwd": dict(names={0: "start", 11: "loaded", 1: "SdP_issued", 6: "sdp_ready", 5: "c:top", 7: "c:tmem_freed", 8: "c:pds_arrived",
                                     2: "dVdK:go", 3: "dVdK:done", 4: "dQ:done", 9: "final", 10: "end"}),
 }
@@ -21,6 +22,15 @@ def run_attn_spatial_bwd():
     for _ in range(3):
         ops.attn_spatial_bwd(qkv, out, dout, lse, frames, n, H, 0.17)
 
+def run_gemm_wgrad():
+    N = 40960
+    Mw, Nw = int(os.environ.get("MW", 256)), int(os.environ.get("NW", 256))
+    Gs = [torch.randn(N, Mw, device="cuda").bfloat16() for _ in range(6)]   # rotate buffers: operands come from HBM
+    Xs = [torch.randn(N, Nw, device="cuda").bfloat16() for _ in range(6)]
+    dW = torch.zeros(Mw, Nw, device="cuda")
+    for i in range(6):
+        ops.gemm_wgrad(Gs[i], Xs[i], dW)
+
 def main():
     name = sys.argv[1]
     globals()["run_" + name]()
@@ -32,10 +42,10 @@ def main():
     a = np.array(buf).reshape(16, 64)
     names = KERNELS[name]["names"]
     t0 = a[0, 0]
-    single = [e for e in names if e in (0, 9, 10, 11)]
+    single = [e for e in names if e in KERNELS[name].get('single', (0, 9, 10, 11))]
     print(" ".join(f"{names[e]}={a[e, 0] - t0}" for e in single))
     per_it = [e for e in sorted(names) if e not in single]
-    for i in range(12):
+    for i in range(40):
         if all(a[e, i] == 0 for e in per_it):
             break
         print(i, " ".join(f"{names[e]}={a[e, i] - t0:6d}" for e in per_it))
