@@ -119,6 +119,27 @@ def cosine_schedule(u: float) -> float:  # st_mask_git.py:116-125
     return math.cos(u * math.pi / 2)
 
 
+class _LazyParams:
+    """Read-only name -> tensor view of a module's parameters and buffers for the inference paths. The name table
+    is built once (a model with 40 action domains has ~8000 parameters; rebuilding a dict of detached tensors per
+    call cost ~20 ms); tensors are detached at lookup time, so in-place updates, .to() moves and the autograd
+    version counter (which tells the engine when to refresh its bf16 weight copies) are always current."""
+
+    def __init__(self, module: nn.Module):
+        self._t = dict(module.named_parameters())
+        self._t.update(dict(module.named_buffers()))
+
+    def __getitem__(self, k):
+        return self._t[k].detach()
+
+    def get(self, k, default=None):
+        t = self._t.get(k)
+        return default if t is None else t.detach()
+
+    def __contains__(self, k):
+        return k in self._t
+
+
 # ------------------------------------------------------------------------------------------------
 # autograd bridge: one Function for logits + loss, so DDP / optimizers see ordinary .grad tensors
 # ------------------------------------------------------------------------------------------------
@@ -171,6 +192,7 @@ class STMaskGIT(nn.Module, PyTorchModelHubMixin):
         self.action_mask_tokens = nn.Parameter(torch.zeros(1, config.T, 1, config.d_model))
         self._engine = Engine(config)
         self._sessions = {}
+        self._lazy = None
         if (config.init_actions or config.use_actions) and config.action_domains is not None:
             self.init_action_projectors(config.action_domains, config.d_actions, config.action_stats, config.action_network)
 
@@ -201,6 +223,12 @@ class STMaskGIT(nn.Module, PyTorchModelHubMixin):
                 else:
                     layer.action_projectors[dom] = nn.Identity()
         self.to(dev)
+        self._lazy = None
+
+    def _inference_params(self) -> _LazyParams:
+        if self._lazy is None:
+            self._lazy = _LazyParams(self)
+        return self._lazy
 
     # ---------------------------------------------------------------- plumbing
     def _buffers_dict(self):
@@ -235,8 +263,7 @@ class STMaskGIT(nn.Module, PyTorchModelHubMixin):
         if action_ids is not None:
             assert action_ids.shape[1] == T, "action_ids must provide one action vector per frame"
         d = self._engine.dims(B, T, H * W, action_ids is not None)
-        p = self._buffers_dict()
-        p.update({k: v.detach() for k, v in self.named_parameters()})
+        p = self._inference_params()
         ids = x_THW.reshape(B, T, H * W).contiguous()
         logits, _ = self._engine.forward(p, ids, action_ids, dom, d, training=False,
                                          skip_normalization=kwargs.get("skip_normalization", False))
@@ -310,8 +337,7 @@ class STMaskGIT(nn.Module, PyTorchModelHubMixin):
             self._sessions.clear()  # one live session: its K/V cache is the large allocation
             sess = DecodeSession(self, B, T, H * W, dom, key[4], prompt_THW.device, use_graphs=self.decode_cuda_graphs)
             self._sessions[key] = sess
-        p = self._buffers_dict()
-        p.update({k: v.detach() for k, v in self.named_parameters()})
+        p = self._inference_params()
         sess.begin(p, prompt_THW, n_ctx, action_ids, kwargs.get("skip_normalization", False))
         return sess
 

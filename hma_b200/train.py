@@ -109,6 +109,7 @@ class TrainStep:
         self.sumsq = torch.zeros(1, device=dev, dtype=torch.float32)
         self.ones = torch.ones(1, device=dev, dtype=torch.float32)
         self.step_count = 0
+        self.dom_steps: Dict[int, int] = {}  # arena offset of a domain block -> optimizer steps it has received
         self.pg = process_group
         self.world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
         self.rank = dist.get_rank(process_group) if self.world > 1 else 0
@@ -127,11 +128,11 @@ class TrainStep:
             self._p = p
         return self._p
 
-    def _adamw(self, lo: int, n: int, g: torch.Tensor, scale: float) -> None:
+    def _adamw(self, lo: int, n: int, g: torch.Tensor, scale: float, step: int) -> None:
         a = self.arena.flat
         _lib.call("hma_adamw_step", a.data_ptr() + 4 * lo, g.data_ptr(), self.m.data_ptr() + 4 * lo,
                   self.v.data_ptr() + 4 * lo, n, self.lr, self.betas[0], self.betas[1], self.eps, self.wd,
-                  self.step_count, scale, self.sumsq.data_ptr() if self.max_norm is not None else None,
+                  step, scale, self.sumsq.data_ptr() if self.max_norm is not None else None,
                   float(self.max_norm or 0.0), ops._s())
 
     # ------------------------------------------------------------------------------------------
@@ -226,9 +227,12 @@ class TrainStep:
             _lib.call("hma_sumsq", g_shared.data_ptr(), shared, self.sumsq.data_ptr(), ops._s())
             for _, n_r, g in updates:
                 _lib.call("hma_sumsq", g.data_ptr(), n_r, self.sumsq.data_ptr(), ops._s())
-        self._adamw(0, shared, g_shared, scale)
+        self._adamw(0, shared, g_shared, scale, self.step_count)
         for lo, n_r, g in updates:
-            self._adamw(lo, n_r, g, scale)
+            # torch.optim.AdamW counts steps per parameter and skips parameters without a gradient, so a domain's
+            # bias correction follows the number of updates THAT domain has received (train_multi.py:593-598)
+            self.dom_steps[lo] = self.dom_steps.get(lo, 0) + 1
+            self._adamw(lo, n_r, g, scale, self.dom_steps[lo])
         # parameters changed underneath torch's version counters: drop the cached bf16 inference copies
         eng.weights._versions.clear()
         eng._stem_w0.clear()
