@@ -39,10 +39,15 @@ struct GemmNtParams {
 constexpr int kBM = 128;
 constexpr int kBK = 64;
 constexpr int kAStage = kBM * kBK * 2;      // 16 KB
-constexpr int kEpiWarps = 8;
+// Epilogue warps: 8 (two per TMEM lane quarter), or 16 for the GELU epilogue, whose arithmetic (erf, two bf16
+// outputs per accumulator) is issue- and latency-bound with only two warps per scheduler.
+template <int EPI> struct EpiWarps { static constexpr int value = (EPI == HMA_EPI_GELU_BF16) ? 16 : 8; };
+// Per-warp staging buffer: 32 padded fp32 rows when the epilogue transposes fp32 (residual / d-activation), else bf16 rows.
+template <int EPI> struct StageBytes {
+  static constexpr int value = (EPI == HMA_EPI_RESID_F32 || EPI == HMA_EPI_DGELU_BF16 || EPI == HMA_EPI_DSILU_BF16) ? 32 * 144 : 32 * 80;
+};
 constexpr int kStageF32Row = 144;           // 32 fp32 + 16 B pad: conflict-free 16-byte row writes
 constexpr int kStageBf16Row = 80;           // 32 bf16 + 16 B pad
-constexpr int kStageBytes = 32 * kStageF32Row;  // per epilogue warp
 constexpr int kSmemLimit = 227 * 1024 - 1024;
 
 __device__ __forceinline__ void sts_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
@@ -193,11 +198,14 @@ __device__ __forceinline__ void epilogue_chunk(const GemmNtParams& p, const uint
 }
 
 template <int BN, int EPI, bool STAT>
-__global__ void __launch_bounds__(384, 1)
+__global__ void __launch_bounds__(128 + 32 * EpiWarps<EPI>::value, 1)
 gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const GemmNtParams p) {
   constexpr int kStages = (BN == 256) ? 3 : 4;
   constexpr int kBStage = BN * kBK * 2;
+  constexpr int kEpiWarps = EpiWarps<EPI>::value;
+  constexpr int kStageBytes = StageBytes<EPI>::value;
+  constexpr int kColGroups = kEpiWarps / 4;  // warps sharing a TMEM lane quarter split the 32-column chunks
   constexpr uint32_t kTmemCols = 2 * BN;
   constexpr uint32_t kIdesc = umma_idesc_bf16(kBM, BN, 0, 0);
 
@@ -306,13 +314,13 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else if (warp >= 4) {
     // ---------------------------------------------------------------- epilogue
     const int ew = warp & 3;         // TMEM lane quarter this warp may read
-    const int eh = (warp - 4) >> 2;  // which 32-column chunks (c % 2 == eh)
+    const int eh = (warp - 4) >> 2;  // which 32-column chunks (c % kColGroups == eh)
     const uint32_t stage_buf = smemStage + (uint32_t)(warp - 4) * kStageBytes;
     // Global operands of the epilogue (fp32 residual / saved pre-activation) do not depend on the
     // accumulator: they are fetched one chunk ahead, the first chunk of a tile BEFORE waiting for the
     // MMAs, so their HBM latency hides behind the tensor-core work.
     constexpr bool kPrefetch = (EPI == HMA_EPI_RESID_F32 || EPI == HMA_EPI_DGELU_BF16 || EPI == HMA_EPI_DSILU_BF16);
-    constexpr int kChunks = BN / 64;  // chunks per warp and tile
+    constexpr int kChunks = BN / 32 / kColGroups;  // chunks per warp and tile
     int it = 0;
     for (int m_blk = m_start; m_blk < m_tiles; m_blk += m_step, ++it) {
       const int as = it & 1;
@@ -324,9 +332,9 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       tc_fence_after();
 #pragma unroll
       for (int j = 0; j < kChunks; ++j) {
-        const int c = eh + 2 * j;
+        const int c = eh + kColGroups * j;
         if constexpr (kPrefetch) {
-          if (j + 1 < kChunks) prefetch_chunk<EPI>(p, row0, n_blk * BN + (c + 2) * 32, lane, pf[(j + 1) & 1]);
+          if (j + 1 < kChunks) prefetch_chunk<EPI>(p, row0, n_blk * BN + (c + kColGroups) * 32, lane, pf[(j + 1) & 1]);
         }
         uint32_t r[32];
         tmem_ld_x32(tmem_addr(tmem_base, (uint32_t)(ew * 32), (uint32_t)(as * BN + c * 32)), r);
@@ -346,16 +354,17 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
 }
 
-template <int BN>
+template <int BN, int EPI>
 static size_t smem_need(int KB, bool stat) {
   constexpr int kStages = (BN == 256) ? 3 : 4;
   constexpr int kBStage = BN * kBK * 2;
-  return 1024 + (size_t)kStages * kAStage + (size_t)(stat ? KB : kStages) * kBStage + (size_t)kEpiWarps * kStageBytes;
+  return 1024 + (size_t)kStages * kAStage + (size_t)(stat ? KB : kStages) * kBStage +
+         (size_t)EpiWarps<EPI>::value * StageBytes<EPI>::value;
 }
 
 template <int BN, int EPI, bool STAT>
 static int launch_nt(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmNtParams& p, cudaStream_t stream) {
-  const size_t smem = smem_need<BN>(p.K / kBK, STAT);
+  const size_t smem = smem_need<BN, EPI>(p.K / kBK, STAT);
   auto kern = gemm_nt_kernel<BN, EPI, STAT>;
   static bool attr_done = false;  // idempotent; racing threads set the same value
   if (!attr_done) {
@@ -369,7 +378,7 @@ static int launch_nt(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmN
   if (per_n < 1) per_n = 1;
   if (per_n > m_tiles) per_n = m_tiles;
   const int grid = per_n * n_tiles;
-  HMA_CHECK_CUDA(hma_host::launch_pdl(kern, dim3(grid), dim3(384), smem, stream, tmA, tmB, p));
+  HMA_CHECK_CUDA(hma_host::launch_pdl(kern, dim3(grid), dim3(128 + 32 * EpiWarps<EPI>::value), smem, stream, tmA, tmB, p));
   return 0;
 }
 
@@ -378,10 +387,10 @@ static int dispatch_nt(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
                        cudaStream_t stream) {
   const int KB = p.K / kBK;
   if (bn == 256) {
-    const bool stat = smem_need<256>(KB, true) <= (size_t)kSmemLimit;
+    const bool stat = smem_need<256, EPI>(KB, true) <= (size_t)kSmemLimit;
     return stat ? launch_nt<256, EPI, true>(tmA, tmB, p, stream) : launch_nt<256, EPI, false>(tmA, tmB, p, stream);
   }
-  const bool stat = smem_need<128>(KB, true) <= (size_t)kSmemLimit;
+  const bool stat = smem_need<128, EPI>(KB, true) <= (size_t)kSmemLimit;
   return stat ? launch_nt<128, EPI, true>(tmA, tmB, p, stream) : launch_nt<128, EPI, false>(tmA, tmB, p, stream);
 }
 

@@ -9,6 +9,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from hma_b200 import ops, _lib
 
 KERNELS = {
+    "gemm_nt": dict(single=(0, 10), names={0: "start", 10: "end", 1: "mma:top", 2: "mma:tmem_free", 3: "mma:committed", 4: "epi:top",
+                                           5: "epi:acc_ready", 6: "epi:done"}),
     "gemm_wgrad": dict(single=(0, 3, 4, 5), names={0: "start", 3: "mma_done", 4: "red_issued", 5: "end", 1: "tma_issued", 2: "full"}),
     "attn_spatial_bwd": dict(names={0: "start", 11: "loaded", 1: "SdP_issued", 6: "sdp_ready", 5: "c:top", 7: "c:tmem_freed", 8: "c:pds_arrived",
                                     2: "dVdK:go", 3: "dVdK:done", 4: "dQ:done", 9: "final", 10: "end"}),
@@ -30,6 +32,17 @@ def run_gemm_wgrad():
     dW = torch.zeros(Mw, Nw, device="cuda")
     for i in range(6):
         ops.gemm_wgrad(Gs[i], Xs[i], dW)
+
+def run_gemm_nt():
+    M, N, K, epi = 40960, int(os.environ.get("N", 1024)), int(os.environ.get("K", 256)), int(os.environ.get("EPI", 1))
+    As = [torch.randn(M, K, device="cuda").bfloat16() for _ in range(4)]
+    W = torch.randn(N, K, device="cuda").bfloat16()
+    bias = torch.randn(N, device="cuda")
+    outs = [torch.empty(M, N, device="cuda", dtype=torch.float32 if epi == 3 else torch.bfloat16) for _ in range(2)]
+    out2 = [torch.empty(M, N, device="cuda", dtype=torch.bfloat16) for _ in range(2)]
+    for i in range(4):
+        ops.gemm_nt(As[i], W, epi, out=outs[i % 2], bias=bias, out2=out2[i % 2] if epi == 1 else None,
+                    aux=out2[i % 2] if epi == 2 else None, resid=outs[(i + 1) % 2] if epi == 3 else None)
 
 def main():
     name = sys.argv[1]
