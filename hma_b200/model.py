@@ -308,6 +308,12 @@ class STMaskGIT(nn.Module, PyTorchModelHubMixin):
         if action_ids is not None:
             assert action_ids.shape[1] == T, "action_ids must provide one action vector per frame"
         d = self._engine.dims(B, T, H * W, action_ids is not None)
+        if action_ids is not None:
+            # st_mask_git.py:703-710: the reference draws an action-drop mask from the CPU generator on every forward.
+            # It only matters with jointly_predict_actions (not implemented), but the two draws are kept so that the
+            # CPU RNG stream of a training script stays in step with the reference.
+            drop_ratio = torch.rand(len(action_ids), 1, 1)
+            self.relevant_action_mask = (torch.rand(len(action_ids), T, 1) < drop_ratio).unsqueeze(-1)
         if torch.is_grad_enabled():
             named = [(k, v) for k, v in self.named_parameters()]
             names = [k for k, _ in named]

@@ -61,3 +61,30 @@ def test_c_abi_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/hma_b200.h but not exported"
     assert lib.hma_abi_version() == 1
+
+
+def test_forward_consumes_cpu_rng_like_the_reference(monkeypatch):
+    """st_mask_git.py:707-708: two CPU torch.rand draws per forward with actions. Checked on
+    the CPU-side bookkeeping only (the CUDA path is patched out)."""
+    import torch
+    from hma_b200 import GenieConfig, STMaskGIT
+    from hma_b200 import model as M
+
+    cfg = GenieConfig(num_layers=1, num_heads=8, d_model=256, T=3, S=256, num_factored_vocabs=2, qk_norm=False,
+                      action_network="concat+modulate")
+    m = STMaskGIT(cfg)
+    m.init_action_projectors(["a"], [4], [[[0.0] * 4, [1.0] * 4]], "concat+modulate")
+    m._require_cuda = lambda t: None
+    m._logits_nograd = lambda *a, **k: (torch.zeros(2 * 3 * 256, 1024), None)
+    monkeypatch.setattr(M.ops, "ce_fwd", lambda *a, **k: (torch.zeros(2), None, None))
+    ids = torch.zeros(2, 3 * 256, dtype=torch.long)
+    acts = torch.zeros(2, 3, 4)
+    torch.manual_seed(5)
+    with torch.no_grad():
+        m(ids, ids, action_ids=acts, domain=["a", "a"])
+    after = torch.rand(1)
+    torch.manual_seed(5)
+    torch.rand(2, 1, 1)
+    torch.rand(2, 3, 1)
+    assert torch.equal(after, torch.rand(1))
+    assert m.relevant_action_mask.shape == (2, 3, 1, 1)

@@ -166,3 +166,45 @@ def test_maskgit_generate_api(setup):
                           action_ids=r["actions"].cuda(), domain=[dom, dom], h=[16], w=[16])
     assert toks.shape == (B, 4 * 256) and (toks != cfg.mask_token_id).all()
     assert torch.equal(toks[:, : 2 * 256].cpu(), r["labels"][:, : 2 * 256])
+
+
+def test_config5_long_context_T32_heterogeneous_domains():
+    """BASELINE configs[4]: 32 frames x 16x16 tokens with heterogeneous action stems (d_a = 2, 14, 70 here), against the
+    CPU oracle on the same weights: loss, logits and gradients of shared and per-domain parameters."""
+    from hma_b200 import GenieConfig, STMaskGIT
+
+    T = 32
+    domains, d_actions, adims = ["d2", "d14", "d70"], [2, 14, 70], [2, 14, 7]
+    ocfg = O.OracleConfig(num_layers=2, num_heads=8, d_model=256, T=T, S=256, num_factored_vocabs=2, use_mup=False,
+                          qk_norm=False, qkv_bias=False, action_network="concat+modulate")
+    sd = O.make_state_dict(ocfg, domains, d_actions, seed=3, action_dims=adims)
+    cfg = GenieConfig(num_layers=2, num_heads=8, d_model=256, T=T, S=256, num_factored_vocabs=2, use_mup=False,
+                      qk_norm=False, qkv_bias=False, action_network="concat+modulate")
+    model = STMaskGIT(cfg)
+    model.init_action_projectors(domains, d_actions, [[[0.0] * a, [1.0] * a] for a in adims], "concat+modulate")
+    model.load_state_dict(sd, strict=True)
+    model = model.cuda()
+    g = torch.Generator().manual_seed(17)
+    for dom, da in zip(domains, d_actions):
+        labels = torch.randint(0, 262144, (1, T * 256), generator=g)
+        mask = torch.rand(1, T, 256, generator=g) < 0.5
+        mask[:, 0] = False
+        ids = torch.where(mask.view(1, -1), torch.full_like(labels, 262144), labels)
+        acts = torch.randn(1, T, da, generator=g)
+        params = {k: v.clone().requires_grad_(v.is_floating_point() and "action_preprocessor" not in k) for k, v in sd.items()}
+        loss, acc, logits = O.forward(ids, labels, acts, [dom], params, ocfg)
+        loss.backward()
+        model.zero_grad(set_to_none=True)
+        out = model(ids.cuda(), labels.cuda(), action_ids=acts.cuda(), domain=[dom])
+        out.loss.backward()
+        assert abs(out.loss.item() - loss.item()) <= 1e-2 * abs(loss.item()), (dom, out.loss.item(), loss.item())
+        d = out.logits.float().cpu() - logits.detach()
+        assert d.abs().max() <= 1e-2 * logits.abs().max(), (dom, d.abs().max())
+        named = dict(model.named_parameters())
+        for k in ("decoder.layers.0.temporal_attn.qkv.weight", "decoder.layers.1.mlp.fc2.weight", "pos_embed_TSC",
+                  f"action_mlp.{dom}.model.0.weight", f"decoder.layers.0.action_projectors.{dom}.adaLN_modulation.2.weight"):
+            gr, gc = params[k].grad, named[k].grad.cpu()
+            assert abs(gc.norm().item() - gr.norm().item()) <= 5e-2 * gr.norm().item(), (dom, k)
+        other = [x for x in domains if x != dom][0]
+        go = named[f"action_mlp.{other}.model.0.weight"].grad
+        assert go is None or go.abs().max().item() == 0.0
