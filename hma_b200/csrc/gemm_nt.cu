@@ -34,6 +34,7 @@ struct GemmNtParams {
   const __nv_bfloat16* aux;
   long long ldaux;
   float alpha;
+  float* colsum;  // d-activation epilogues: colsum[N] += column sums of the output (the bias gradient of the Linear below)
 };
 
 constexpr int kBM = 128;
@@ -153,7 +154,7 @@ __device__ __forceinline__ void prefetch_chunk(const GemmNtParams& p, int row0, 
 
 template <int EPI>
 __device__ __forceinline__ void epilogue_chunk(const GemmNtParams& p, const uint32_t (&r)[32], int row0, int n0,
-                                               int lane, uint32_t stage, const float4 (&pf)[8]) {
+                                               int lane, uint32_t stage, const float4 (&pf)[8], float4& csum) {
   // r: 32 consecutive fp32 accumulator columns [n0, n0+32) of output row (row0 + lane).
   float v[32];
 #pragma unroll
@@ -182,6 +183,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmNtParams& p, const uint
         const float g0 = a.x * act_bwd<EPI>(bf16_lo(z.x)), g1 = a.y * act_bwd<EPI>(bf16_hi(z.x));
         const float g2 = a.z * act_bwd<EPI>(bf16_lo(z.y)), g3 = a.w * act_bwd<EPI>(bf16_hi(z.y));
         *reinterpret_cast<uint2*>(out + (size_t)row * p.ldo + n0 + cc) = make_uint2(pack_bf16(g0, g1), pack_bf16(g2, g3));
+        csum.x += g0; csum.y += g1; csum.z += g2; csum.w += g3;  // this lane's 4 columns of the chunk, over its 8 rows
       }
     });
   } else if constexpr (EPI == HMA_EPI_RESID_F32) {
@@ -321,6 +323,11 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // MMAs, so their HBM latency hides behind the tensor-core work.
     constexpr bool kPrefetch = (EPI == HMA_EPI_RESID_F32 || EPI == HMA_EPI_DGELU_BF16 || EPI == HMA_EPI_DSILU_BF16);
     constexpr int kChunks = BN / 32 / kColGroups;  // chunks per warp and tile
+    // bias gradient of the layer below (d-activation epilogues): a CTA keeps one n-block, so each lane accumulates
+    // the column sums of its 4 columns of every chunk over all of the CTA's row tiles in registers
+    float4 csum[kChunks];
+#pragma unroll
+    for (int j = 0; j < kChunks; ++j) csum[j] = make_float4(0.f, 0.f, 0.f, 0.f);
     int it = 0;
     for (int m_blk = m_start; m_blk < m_tiles; m_blk += m_step, ++it) {
       const int as = it & 1;
@@ -339,10 +346,29 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         uint32_t r[32];
         tmem_ld_x32(tmem_addr(tmem_base, (uint32_t)(ew * 32), (uint32_t)(as * BN + c * 32)), r);
         tmem_ld_wait();
-        epilogue_chunk<EPI>(p, r, row0, n_blk * BN + c * 32, lane, stage_buf, pf[j & 1]);
+        epilogue_chunk<EPI>(p, r, row0, n_blk * BN + c * 32, lane, stage_buf, pf[j & 1], csum[j]);
       }
       tc_fence_before();
       mbar_arrive(smem_u32(&bar_tempty[as]));
+    }
+    if constexpr (EPI == HMA_EPI_DGELU_BF16 || EPI == HMA_EPI_DSILU_BF16) {
+      if (p.colsum != nullptr) {
+#pragma unroll
+        for (int j = 0; j < kChunks; ++j) {
+          float4 t = csum[j];  // lanes with equal lane % 8 hold the same columns for different rows
+#pragma unroll
+          for (int o = 8; o < 32; o <<= 1) {
+            t.x += __shfl_xor_sync(0xffffffffu, t.x, o);
+            t.y += __shfl_xor_sync(0xffffffffu, t.y, o);
+            t.z += __shfl_xor_sync(0xffffffffu, t.z, o);
+            t.w += __shfl_xor_sync(0xffffffffu, t.w, o);
+          }
+          if (lane < 8) {
+            float* dst = p.colsum + n_blk * BN + (eh + kColGroups * j) * 32 + lane * 4;
+            atomicAdd(dst, t.x); atomicAdd(dst + 1, t.y); atomicAdd(dst + 2, t.z); atomicAdd(dst + 3, t.w);
+          }
+        }
+      }
     }
   }
 
@@ -399,7 +425,7 @@ static int dispatch_nt(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
 extern "C" int hma_gemm_nt(const void* A, long long lda, const void* B, long long ldb, int M, int N, int K,
                            int epi, void* out, long long ldo, void* out2, long long ldo2, const float* bias,
                            const float* resid, long long ldr, const void* aux, long long ldaux, float alpha,
-                           void* stream_) {
+                           float* colsum, void* stream_) {
   using namespace hma;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (M == 0) return 0;
@@ -420,6 +446,9 @@ extern "C" int hma_gemm_nt(const void* A, long long lda, const void* B, long lon
   p.bias = bias; p.resid = resid; p.ldr = ldr;
   p.aux = static_cast<const __nv_bfloat16*>(aux); p.ldaux = ldaux;
   p.alpha = alpha;
+  p.colsum = colsum;
+  HMA_REQUIRE(colsum == nullptr || epi == HMA_EPI_DGELU_BF16 || epi == HMA_EPI_DSILU_BF16,
+              "gemm_nt: colsum is only produced by the d-activation epilogues");
   switch (epi) {
     case HMA_EPI_BF16: return dispatch_nt<HMA_EPI_BF16>(tmA, tmB, p, bn, stream);
     case HMA_EPI_GELU_BF16: return dispatch_nt<HMA_EPI_GELU_BF16>(tmA, tmB, p, bn, stream);

@@ -409,10 +409,8 @@ class Engine:
             if dy is None:
                 dy = ops.cast_colsum(dx, g.get(lp + "mlp.fc2.bias"))
             ops.gemm_wgrad(dy, L["h"], g2(lp + "mlp.fc2.weight"))
-            dz = ops.gemm_nt(dy, Wt[lp + "mlp.fc2.weight"], EPI_DGELU, aux=L["z"])
+            dz = ops.gemm_nt(dy, Wt[lp + "mlp.fc2.weight"], EPI_DGELU, aux=L["z"], colsum=g.get(lp + "mlp.fc1.bias"))
             ops.gemm_wgrad(dz, L["a2"], g2(lp + "mlp.fc1.weight"))
-            if lp + "mlp.fc1.bias" in g:
-                ops.colsum_bf16(dz, g2(lp + "mlp.fc1.bias"))
             da2 = ops.gemm_nt(dz, Wt[lp + "mlp.fc1.weight"], EPI_BF16)
             dy = ops.ln_bwd(da2, L["x3"], L["st2"], 1, dx, gamma=p[lp + "norm2.weight"], dgamma=g2(lp + "norm2.weight"),
                             dbeta=g2(lp + "norm2.bias"), want_next=True, colsum_next=g.get(lp + "temporal_attn.proj.bias"))
@@ -441,9 +439,9 @@ class Engine:
                     dmod_bf = ops.cast_bf16(dmod)
                     ops.gemm_wgrad(dmod_bf, L["hmod"], g2(ap + "adaLN_modulation.2.weight"))
                     ops.colsum_f32(dmod, g2(ap + "adaLN_modulation.2.bias"))
-                    dzm = ops.gemm_nt(dmod_bf, Wt[ap + "adaLN_modulation.2.weight"], EPI_DSILU, aux=L["zmod"])
+                    dzm = ops.gemm_nt(dmod_bf, Wt[ap + "adaLN_modulation.2.weight"], EPI_DSILU, aux=L["zmod"],
+                                      colsum=g2(ap + "adaLN_modulation.0.bias"))
                     ops.gemm_wgrad(dzm, sv["c_bf"], g2(ap + "adaLN_modulation.0.weight"))
-                    ops.colsum_bf16(dzm, g2(ap + "adaLN_modulation.0.bias"))
                     ops.gemm_nt(dzm, Wt[ap + "adaLN_modulation.0.weight"], EPI_RESID, resid=dact, out=dact)
                     side_keep.append((dmod, dmod_bf, dzm))  # alive until the side stream has been joined
             else:

@@ -64,7 +64,8 @@ def _p(t: Optional[torch.Tensor]):
 
 def gemm_nt(A: torch.Tensor, B: torch.Tensor, epi: int, *, out: Optional[torch.Tensor] = None,
             bias: Optional[torch.Tensor] = None, resid: Optional[torch.Tensor] = None,
-            aux: Optional[torch.Tensor] = None, out2: Optional[torch.Tensor] = None, alpha: float = 1.0) -> torch.Tensor:
+            aux: Optional[torch.Tensor] = None, out2: Optional[torch.Tensor] = None, alpha: float = 1.0,
+            colsum: Optional[torch.Tensor] = None) -> torch.Tensor:
     """out[M,N] = epi(A[M,K] @ B[N,K]^T); A, B bf16 (row stride arbitrary, unit column stride)."""
     M, K = A.shape
     N = B.shape[0]
@@ -74,7 +75,7 @@ def gemm_nt(A: torch.Tensor, B: torch.Tensor, epi: int, *, out: Optional[torch.T
     _call(f"gemm_nt[N={N},K={K},epi={epi}]", 2.0 * M * N * K, "hma_gemm_nt", A.data_ptr(), A.stride(0), B.data_ptr(), B.stride(0), M, N, K, epi, out.data_ptr(),
               out.stride(0), _p(out2), out2.stride(0) if out2 is not None else 0, _p(bias), _p(resid),
               resid.stride(0) if resid is not None else 0, _p(aux), aux.stride(0) if aux is not None else 0,
-              float(alpha), _s())
+              float(alpha), _p(colsum), _s())
     return out
 
 

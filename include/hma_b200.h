@@ -43,13 +43,15 @@ int hma_device_check(void);
 #define HMA_EPI_RESID_F32 3  /* out(fp32)  = resid(fp32, optional) + alpha*acc + bias          */
 #define HMA_EPI_SILU_BF16 4  /* as GELU_BF16 with SiLU (adaLN_modulation, st_mask_git.py:61-63) */
 #define HMA_EPI_DSILU_BF16 5 /* out(bf16)  = (alpha*acc) * silu'(aux)                          */
+/* DGELU / DSILU only: if colsum != NULL, colsum[N] (fp32) += column sums of out — the bias gradient of the Linear whose
+ * pre-activation gradient this is (accumulated in registers across the CTA's row tiles; a few atomics per CTA). */
 
 /* out[M,N] = epi(A[M,K] . B[N,K]^T). A, B bf16 row-major. Replaces nn.Linear forward
  * (attention.py:141,154; st_transformer.py:24-27; st_mask_git.py:70-75,681-683) and, with B a
  * pre-transposed weight, its input-gradient. K % 64 == 0, N % 128 == 0. */
 int hma_gemm_nt(const void* A, long long lda, const void* B, long long ldb, int M, int N, int K, int epi,
                 void* out, long long ldo, void* out2, long long ldo2, const float* bias, const float* resid,
-                long long ldr, const void* aux, long long ldaux, float alpha, void* stream);
+                long long ldr, const void* aux, long long ldaux, float alpha, float* colsum, void* stream);
 
 /* dW[Mw,Nw] (fp32) += G[tokens,Mw]^T . X[tokens,Nw]; G, X bf16 row-major. The weight gradient of
  * the same Linears. Mw % 128 == 0, Nw % 128 == 0. Accumulates (caller zeroes dW). */

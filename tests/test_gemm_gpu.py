@@ -22,7 +22,7 @@ def _report(name, got, ref):
     return rel
 
 
-def gemm_nt(A, B, epi, bias=None, resid=None, aux=None, alpha=1.0, want_z=False):
+def gemm_nt(A, B, epi, bias=None, resid=None, aux=None, alpha=1.0, want_z=False, colsum=None):
     M, K = A.shape
     N = B.shape[0]
     out_dtype = torch.float32 if epi == EPI_RESID else torch.bfloat16
@@ -31,7 +31,7 @@ def gemm_nt(A, B, epi, bias=None, resid=None, aux=None, alpha=1.0, want_z=False)
     _lib.call(
         "hma_gemm_nt", A.data_ptr(), A.stride(0), B.data_ptr(), B.stride(0), M, N, K, epi, out.data_ptr(),
         out.stride(0), _lib.ptr(out2), N, _lib.ptr(bias), _lib.ptr(resid), N, _lib.ptr(aux), N, alpha,
-        _lib.current_stream(),
+        _lib.ptr(colsum), _lib.current_stream(),
     )
     return out, out2
 
@@ -68,6 +68,15 @@ def test_gemm_nt_epilogues():
     zz = aux.float().requires_grad_(True)
     torch.nn.functional.gelu(zz).sum().backward()
     assert _report("dgelu", g, (A.float() @ B.float().t()) * zz.grad) < 1e-2
+    # fused bias gradient: colsum += column sums of the d-activation output (accumulates into the caller's buffer)
+    for Mc in (777, 5000):
+        Ac = torch.randn(Mc, K, device="cuda").bfloat16()
+        auxc = torch.randn(Mc, N, device="cuda").bfloat16()
+        cs = torch.full((N,), 3.0, device="cuda")
+        gc, _ = gemm_nt(Ac, B, EPI_DGELU, aux=auxc, colsum=cs)
+        torch.cuda.synchronize()
+        ref_cs = 3.0 + gc.float().sum(0)
+        assert ((cs - ref_cs).abs().max() / ref_cs.abs().max()).item() < 5e-3
 
     # fp32 residual
     resid = torch.randn(M, N, device="cuda")
