@@ -47,22 +47,33 @@ __device__ __forceinline__ uint64_t desc_sw64(uint32_t saddr, uint32_t lbo, uint
   return d;
 }
 
-// one key block: stats + P for the calling thread's row. kFull: ncols is a multiple of 32.
+// One key block of one query row is shared by TWO threads (warps w and w + 4 own the same TMEM lane quarter): each
+// takes half of the block's 32-column chunks, [c_lo, c_hi). Pass 1: maximum over the own columns.
 template <bool kFull>
-__device__ __forceinline__ void softmax_block_t(uint32_t tmem_row_s, int ncols, float scale_log2, uint32_t p_smem,
-                                                int row, float& m_out, float& l_out) {
-  float m = -INFINITY;
-  for (int c = 0; c < ncols; c += 32) {
+__device__ __forceinline__ float block_max_t(uint32_t tmem_row_s, int c_lo, int c_hi, int ncols) {
+  float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+  for (int c = c_lo; c < c_hi; c += 32) {
     uint32_t r[32];
     tmem_ld_x32(tmem_row_s + c, r);
     tmem_ld_wait();
 #pragma unroll
-    for (int j = 0; j < 32; ++j)
-      if (kFull || c + j < ncols) m = fmaxf(m, __uint_as_float(r[j]));
+    for (int j = 0; j < 32; j += 4) {
+      if (kFull || c + j < ncols) {  // ncols is a multiple of 16: groups of four never straddle
+        m0 = fmaxf(m0, __uint_as_float(r[j]));
+        m1 = fmaxf(m1, __uint_as_float(r[j + 1]));
+        m2 = fmaxf(m2, __uint_as_float(r[j + 2]));
+        m3 = fmaxf(m3, __uint_as_float(r[j + 3]));
+      }
+    }
   }
-  const float mb = m * scale_log2;
+  return fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+}
+// Pass 2: P = exp2(scale * s - mb) of the own columns as bf16 into the 128-byte-swizzled tile; returns their sum.
+template <bool kFull>
+__device__ __forceinline__ float block_exp_t(uint32_t tmem_row_s, int c_lo, int c_hi, int ncols, float scale_log2, float mb,
+                                             uint32_t p_smem, int row) {
   float l0 = 0.f, l1 = 0.f;
-  for (int c = 0; c < ncols; c += 32) {
+  for (int c = c_lo; c < c_hi; c += 32) {
     uint32_t r[32];
     tmem_ld_x32(tmem_row_s + c, r);
     tmem_ld_wait();
@@ -71,7 +82,7 @@ __device__ __forceinline__ void softmax_block_t(uint32_t tmem_row_s, int ncols, 
     for (int j = 0; j < 32; j += 2) {
       float p0 = fast_ex2(fmaf(__uint_as_float(r[j]), scale_log2, -mb));
       float p1 = fast_ex2(fmaf(__uint_as_float(r[j + 1]), scale_log2, -mb));
-      if (!kFull && c + j >= ncols) { p0 = 0.f; p1 = 0.f; }  // ncols is a multiple of 16: pairs never straddle
+      if (!kFull && c + j >= ncols) { p0 = 0.f; p1 = 0.f; }
       l0 += p0;
       l1 += p1;
       pk[j >> 1] = pack_bf16(p0, p1);
@@ -86,20 +97,22 @@ __device__ __forceinline__ void softmax_block_t(uint32_t tmem_row_s, int ncols, 
                    : "memory");
     }
   }
-  m_out = m;
-  l_out = l0 + l1;
+  return l0 + l1;
 }
-__device__ __forceinline__ void softmax_block(uint32_t tmem_row_s, int ncols, float scale_log2, uint32_t p_smem,
-                                              int row, float& m_out, float& l_out) {
-  if ((ncols & 31) == 0) softmax_block_t<true>(tmem_row_s, ncols, scale_log2, p_smem, row, m_out, l_out);
-  else softmax_block_t<false>(tmem_row_s, ncols, scale_log2, p_smem, row, m_out, l_out);
+// barrier between the two warps that share a TMEM lane quarter (named barriers 1..4)
+__device__ __forceinline__ void pair_sync(int quarter) {
+  asm volatile("bar.sync %0, 64;" ::"r"(quarter + 1) : "memory");
 }
 
-__global__ void __launch_bounds__(160, 2)
+constexpr int kSoftmaxWarps = 8;
+constexpr int kFwdThreads = kSoftmaxWarps * 32 + 32;
+
+__global__ void __launch_bounds__(kFwdThreads, 2)
 attn_spatial_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnFwdParams p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar_load, bar_s, bar_p, bar_o, bar_oread;
   __shared__ uint32_t tmem_base_slot;
+  __shared__ float s_xm[2][128], s_xl[2][128];  // per-row partial max / sum of the two column halves
 
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sQ = smem_base;
@@ -118,12 +131,12 @@ attn_spatial_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnFwd
   if (threadIdx.x == 0) {
     mbar_init(smem_u32(&bar_load), 1);
     mbar_init(smem_u32(&bar_s), 1);
-    mbar_init(smem_u32(&bar_p), 128);
+    mbar_init(smem_u32(&bar_p), kSoftmaxWarps * 32);
     mbar_init(smem_u32(&bar_o), 1);
     mbar_init(smem_u32(&bar_oread), 128);
     fence_barrier_init();
   }
-  if (warp == 4) {
+  if (warp == kSoftmaxWarps) {
     tmem_alloc(smem_u32(&tmem_base_slot), 256);
     tmem_relinquish();
   }
@@ -136,7 +149,7 @@ attn_spatial_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnFwd
   const uint32_t tOa = tmem_base + 192;
   const uint32_t tOb = tmem_base + 224;
 
-  if (warp == 4) {
+  if (warp == kSoftmaxWarps) {
     if (elect_one()) {
       // ------------------------------------------------ loads
       const uint32_t bl = smem_u32(&bar_load);
@@ -184,30 +197,54 @@ attn_spatial_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnFwd
       }
     }
   } else {
-    // -------------------------------------------------- softmax + epilogue (warps 0-3)
-    const int row = warp * 32 + lane;  // row inside the 128-query tile == TMEM lane
-    const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
+    // -------------------------------------------------- softmax (warps 0-7) + epilogue (warps 0-3)
+    // Warps w and w + 4 share the query rows of TMEM lane quarter w % 4 and split the key columns of every block:
+    // with one row per thread and 320 keys the arithmetic of a single warp per quarter was latency-bound.
+    const int quarter = warp & 3, half = warp >> 2;
+    const int row = quarter * 32 + lane;  // row inside the 128-query tile == TMEM lane
+    const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+    auto softmax_half = [&](int ncols, float& m_out, float& l_out, bool live) {
+      const int chunks = (ncols + 31) >> 5;
+      const int c_lo = half == 0 ? 0 : ((chunks + 1) >> 1) * 32;
+      const int c_hi = half == 0 ? ((chunks + 1) >> 1) * 32 : chunks * 32;
+      const bool full = (ncols & 31) == 0;
+      float m_part = -INFINITY;
+      if (live) m_part = full ? block_max_t<true>(tS + lane_addr, c_lo, c_hi, ncols) : block_max_t<false>(tS + lane_addr, c_lo, c_hi, ncols);
+      s_xm[half][row] = m_part;
+      pair_sync(quarter);
+      const float m = fmaxf(s_xm[0][row], s_xm[1][row]);
+      float l_part = 0.f;
+      if (live) {
+        const float mb = m * p.scale_log2;
+        l_part = full ? block_exp_t<true>(tS + lane_addr, c_lo, c_hi, ncols, p.scale_log2, mb, sP, row)
+                      : block_exp_t<false>(tS + lane_addr, c_lo, c_hi, ncols, p.scale_log2, mb, sP, row);
+      }
+      s_xl[half][row] = l_part;
+      pair_sync(quarter);
+      m_out = m;
+      l_out = s_xl[0][row] + s_xl[1][row];
+    };
     uint32_t ps = 0, po = 0;
     for (int t = 0; t < ntiles; ++t) {
       float ma, la, mb = -INFINITY, lb = 0.f;
       // rows past the frame (second half of the last query tile) are never stored: their warps skip the
-      // exp work (the MUFU pipe is the bottleneck of this kernel) and leave stale, finite P rows behind
-      const bool live = t * 128 + warp * 32 < n;  // warp-uniform
+      // exp work and leave stale, finite-or-not P rows behind (a P row only feeds its own O row)
+      const bool live = t * 128 + quarter * 32 < n;  // warp-uniform, same for both warps of a pair
       mbar_wait(smem_u32(&bar_s), ps); ps ^= 1u;
       tc_fence_after();
-      ma = -INFINITY; la = 0.f;
-      if (live) softmax_block(tS + lane_addr, na, p.scale_log2, sP, row, ma, la);
+      softmax_half(na, ma, la, live);
       fence_proxy_async();
       tc_fence_before();
       mbar_arrive(smem_u32(&bar_p));
       if (nb > 0) {
         mbar_wait(smem_u32(&bar_s), ps); ps ^= 1u;
         tc_fence_after();
-        if (live) softmax_block(tS + lane_addr, nb, p.scale_log2, sP, row, mb, lb);
+        softmax_half(nb, mb, lb, live);
         fence_proxy_async();
         tc_fence_before();
         mbar_arrive(smem_u32(&bar_p));
       }
+      if (half != 0) continue;  // the epilogue of a row is done by its first thread
       mbar_wait(smem_u32(&bar_o), po); po ^= 1u;
       tc_fence_after();
       uint32_t oa[32], ob[32];
@@ -245,7 +282,7 @@ attn_spatial_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnFwd
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == kSoftmaxWarps) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 256);
   }
@@ -281,7 +318,7 @@ extern "C" int hma_attn_spatial_fwd(const void* qkv, long long ld_qkv, int frame
     HMA_CHECK_CUDA(cudaFuncSetAttribute(attn_spatial_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_done = true;
   }
-  HMA_CHECK_CUDA(hma_host::launch_pdl(attn_spatial_fwd_kernel, dim3(frames * heads), dim3(160), smem,
+  HMA_CHECK_CUDA(hma_host::launch_pdl(attn_spatial_fwd_kernel, dim3(frames * heads), dim3(kFwdThreads), smem,
                                       static_cast<cudaStream_t>(stream_), tm, p));
   return 0;
 }
