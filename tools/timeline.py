@@ -1,6 +1,7 @@
 #!/usr/bin/env python
-"""Per-CTA event timeline of one kernel (development aid). Build with HMA_B200_TIMELINE=1, then e.g.
-    HMA_B200_TIMELINE=1 python -m hma_b200.build --force && python tools/timeline.py attn_spatial_bwd
+"""Per-CTA event timeline of one kernel (development aid). The HMA_TL(ev, i) stamps are added to a kernel by the
+patch scripts in tools/instr/ (apply, build with HMA_B200_TIMELINE=1, run this on the GPU, `git checkout` the .cu):
+    python tools/instr/gemm_nt.py && HMA_B200_TIMELINE=1 python -m hma_b200.build --force && python tools/timeline.py gemm_nt
 Prints clock64() stamps of CTA 0 relative to its first event, one row per loop iteration."""
 import ctypes, sys, os
 import numpy as np
@@ -43,6 +44,12 @@ def run_gemm_nt():
     for i in range(4):
         ops.gemm_nt(As[i], W, epi, out=outs[i % 2], bias=bias, out2=out2[i % 2] if epi == 1 else None,
                     aux=out2[i % 2] if epi == 2 else None, resid=outs[(i + 1) % 2] if epi == 3 else None)
+
+def run_attn_spatial_fwd():
+    frames, n, H = 128, 320, 8
+    qkvs = [torch.randn(frames * n, 768, device="cuda").bfloat16() for _ in range(4)]  # rotate: operands come from HBM
+    for i in range(4):
+        ops.attn_spatial_fwd(qkvs[i], frames, n, H, 0.17, True)
 
 def main():
     name = sys.argv[1]
