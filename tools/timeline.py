@@ -10,6 +10,9 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from hma_b200 import ops, _lib
 
 KERNELS = {
+    "attn_spatial_fwd": dict(names={0: "start", 11: "loaded", 1: "top", 2: "Sa_ready", 3: "Pa_arrived", 4: "Sb_ready", 5: "Pb_arrived",
+                                    6: "O_ready", 7: "stored", 10: "end", 12: "i:Sa_issued", 13: "i:Pa_seen", 14: "i:PVa+Sb_issued",
+                                    15: "i:Pb_seen"}, single=(0, 10, 11)),
     "gemm_nt": dict(single=(0, 10), names={0: "start", 10: "end", 1: "mma:top", 2: "mma:tmem_free", 3: "mma:committed", 4: "epi:top",
                                            5: "epi:acc_ready", 6: "epi:done"}),
     "gemm_wgrad": dict(single=(0, 3, 4, 5), names={0: "start", 3: "mma_done", 4: "red_issued", 5: "end", 1: "tma_issued", 2: "full"}),
