@@ -60,24 +60,26 @@ __device__ __forceinline__ uint4 lds_v4(uint32_t addr) {
   return v;
 }
 
-// erf to ~2.5e-5 absolute (Abramowitz-Stegun 7.1.25) sharing e = exp(-x^2) with the Gaussian pdf;
-// far below the bf16 resolution of every consumer. x = z / sqrt(2).
+// Phi(z) = 0.5 (1 + erf(z / sqrt 2)) as a logistic of an odd polynomial: Phi(z) ~= 1 / (1 + 2^(z (a1 + a3 z^2 + a5 z^4))),
+// coefficients fitted to logit(Phi) on |z| <= 5.5 (max |error| 3.7e-5 on Phi, 3.0e-5 on z Phi(z): below the bf16
+// resolution of every consumer). 8 instructions (2 MUFU) against 14 for the Abramowitz-Stegun erf it replaces; the
+// GELU epilogue is instruction-bound (ncu: 22.8 instructions per output element, 56 % issue utilisation).
+// z^2 is clamped for the polynomial so that the quartic term cannot turn the logit around for |z| > 11.
+__device__ __forceinline__ float gelu_cdf(float z, float zz) {
+  const float z2 = fminf(zz, 64.0f);
+  float t = fmaf(0.00099209175f, z2, -0.10660493f);
+  t = fmaf(t, z2, -2.3013592f);
+  return fast_rcp(1.0f + fast_ex2(t * z));
+}
 __device__ __forceinline__ void gelu_parts(float z, float& cdf, float& pdf) {
-  const float x = z * 0.70710678118654752f;
-  const float ax = fabsf(x);
-  const float t = fast_rcp(fmaf(0.47047f, ax, 1.0f));
-  const float e = fast_ex2(-1.4426950408889634f * x * x);
-  const float poly = ((0.7478556f * t - 0.0958798f) * t + 0.3480242f) * t;
-  const float erf_abs = fmaf(-poly, e, 1.0f);
-  cdf = 0.5f + 0.5f * copysignf(erf_abs, x);
-  pdf = 0.3989422804014327f * e;
+  const float zz = z * z;
+  cdf = gelu_cdf(z, zz);
+  pdf = 0.3989422804014327f * fast_ex2(-0.72134752044448170f * zz);
 }
 template <int EPI>
 __device__ __forceinline__ float act_fwd(float z) {
   if constexpr (EPI == HMA_EPI_GELU_BF16) {
-    float cdf, pdf;
-    gelu_parts(z, cdf, pdf);
-    return z * cdf;
+    return z * gelu_cdf(z, z * z);
   } else {
     return silu(z);
   }
