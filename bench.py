@@ -257,9 +257,9 @@ def main() -> None:
     sampler = ClockSampler(local)
     sampler.start()
     launches0 = ops.LAUNCHES
-    dominant = "gemm_nt[N=1024,K=256,epi=1]"  # fc1 + GELU: see DESIGN.md "roofline kernel"
+    dominant = "attn_spatial_bwd"  # largest share of the step (profiles/r01b_launches_summary.txt); DESIGN.md §3.2
     if not step_fn.cuda_graphs:
-        ops.PROFILER = ops.Profiler(kinds={dominant})
+        ops.PROFILER = ops.Profiler()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.profiler.start()  # no-op unless run as `ncu --profile-from-start off ...` (profiles/ recipes)
     e0.record()
@@ -277,7 +277,7 @@ def main() -> None:
         # launched from the host, right after the timed region, in this process (clock sampler still running)
         roofline_pass = "the same steps re-run without graph replay right after the timed region"
         step_fn.cuda_graphs = False
-        ops.PROFILER = ops.Profiler(kinds={dominant})
+        ops.PROFILER = ops.Profiler()
         for i in range(args.warmup, total):
             run_resident(i, resident[i])
         step_fn.cuda_graphs = True
@@ -337,12 +337,27 @@ def main() -> None:
     peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)"
     traffic = None
     try:
-        with open(os.path.join(ROOT, "profiles", "r01_roofline_kernel.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r01b_roofline_kernel.json")) as f:
             traffic = json.load(f).get("traffic_bytes")  # dram read+write of one launch, from the committed ncu capture
     except Exception:
         pass
     rec = prof.get(dominant, {"launches": 0, "total_ms": 0.0, "work": 0.0})
     achieved = rec["work"] / (rec["total_ms"] / 1e3) / 1e12 if rec["total_ms"] else 0.0
+    # every stage of the step, for context: share of the summed kernel time and achieved rate on its own bound
+    # (work = algorithmic FLOPs for the contractions, algorithmic bytes for the streaming stages; hma_b200/ops.py)
+    hbm_gbs = peaks.get("hbm_gbs", 6650.0)
+    tot_ms = sum(v["total_ms"] for v in prof.values() if v["launches"] and v["work"] / v["launches"] >= 1e8) or 1.0
+    stages = []
+    main_stream = {k: v for k, v in prof.items() if v["launches"] and v["work"] / v["launches"] >= 1e8}  # drop the
+    # one-tile adaLN chain: it runs on a side stream, where event pairs also time its waits on the main stream
+    for kind, v in sorted(main_stream.items(), key=lambda kv: -kv[1]["total_ms"])[:12]:
+        is_flops = kind.startswith(("gemm", "attn_spatial"))
+        rate = v["work"] / (v["total_ms"] / 1e3) if v["total_ms"] else 0.0
+        stages.append({"stage": kind, "share": round(v["total_ms"] / tot_ms, 4), "launches": v["launches"],
+                       "avg_us": round(v["total_ms"] / max(v["launches"], 1) * 1e3, 1),
+                       "achieved": round(rate / 1e12, 1) if is_flops else round(rate / 1e9, 0),
+                       "unit": "TFLOP/s" if is_flops else "GB/s",
+                       "frac_of_peak": round(rate / 1e12 / peak_tf, 3) if is_flops else round(rate / 1e9 / hbm_gbs, 3)})
     step_tf = (B_PER_GPU * train_flops_per_sample() * (args.layers / L)) / (ms_resident / args.steps / 1e3) / 1e12
 
     line = {
@@ -362,10 +377,11 @@ def main() -> None:
                 "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": launches,
         "clocks": clocks,
-        "roofline": {"bound": "tensor", "kernel": "gemm_nt_kernel<256,GELU,stationary> (MLP fc1: LN2(x) @ W1^T + b1, GELU)",
+        "roofline": {"bound": "tensor", "kernel": "attn_spatial_bwd_kernel (per-frame attention backward, 128 frames x 8 heads x 320 tokens, "
+                                                    "head_dim 32: 33.55 algorithmic GFLOP and 168 MB per launch, AI ~ the ridge)",
                      "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf if peak_tf else None,
                      "traffic": traffic, "traffic_unit": "bytes/launch (ncu dram read+write)", "launches_timed": rec["launches"], "timed_in": roofline_pass, "avg_launch_us": (rec["total_ms"] / max(rec["launches"], 1)) * 1e3,
-                     "peak_source": peak_src},
+                     "peak_source": peak_src, "stages": stages},
     }
     if gen_fps is not None:
         line["generation"] = {
