@@ -135,7 +135,10 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const LnBwdParams p) {
 #pragma unroll
   for (int j = 0; j < 8; ++j) { acc_w[j] = 0.f; acc_b[j] = 0.f; acc_c[j] = 0.f; }
   float mult[8];
-  if (p.mode == 1) {
+  if (p.mode == 0) {  // Identity "norm" (qk_norm=True, st_transformer.py:50,75): dx += dy, plus the bf16 copy / column sums
+#pragma unroll
+    for (int j = 0; j < 8; ++j) mult[j] = 0.f;
+  } else if (p.mode == 1) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) mult[j] = __ldg(p.gamma + col_of(lane, j));
   } else {
@@ -146,9 +149,11 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const LnBwdParams p) {
   for (int i = warp; i < p.rows_per_cta; i += 8) {
     const int row = r0 + i;
     if (row >= p.rows) break;
-    const RowLoad x = load_row_f32(p.x + (size_t)row * p.ldx, lane);
     const RowLoad dy = load_row_bf16(p.dy + (size_t)row * p.lddy, lane);
     RowLoad dx = load_row_f32(p.dx + (size_t)row * p.lddx, lane);
+    float o[8];
+    if (p.mode != 0) {
+    const RowLoad x = load_row_f32(p.x + (size_t)row * p.ldx, lane);
     const float mean = __ldg(p.stats + (size_t)row * 2);
     const float rstd = __ldg(p.stats + (size_t)row * 2 + 1);
     float xh[8], g[8];
@@ -164,9 +169,12 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const LnBwdParams p) {
     }
     s1 = warp_sum(s1) * (1.0f / kC);
     s2 = warp_sum(s2) * (1.0f / kC);
-    float o[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) o[j] = dx.v[j] + rstd * (g[j] - s1 - xh[j] * s2);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = dx.v[j] + dy.v[j];
+    }
     store_row_f32(p.dx + (size_t)row * p.lddx, lane, o);
     if (p.dy_next != nullptr) {
       const uint2 a = make_uint2(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]));
@@ -183,7 +191,7 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const LnBwdParams p) {
     red[warp][kC + col_of(lane, j)] = acc_w[j];   // gamma | scale
   }
   __syncthreads();
-  for (int c = threadIdx.x; c < 2 * kC; c += 256) {
+  for (int c = threadIdx.x; p.mode != 0 && c < 2 * kC; c += 256) {
     float s = 0.f;
 #pragma unroll
     for (int w = 0; w < 8; ++w) s += red[w][c];
@@ -269,7 +277,7 @@ extern "C" int hma_ln_bwd(const void* dy, long long lddy, const float* x, long l
                           float* colsum_next, void* stream_) {
   using namespace hma;
   if (rows == 0) return 0;
-  HMA_REQUIRE(mode == 1 || mode == 2, "ln_bwd: bad mode %d", mode);
+  HMA_REQUIRE(mode == 0 || mode == 1 || mode == 2, "ln_bwd: bad mode %d", mode);
   HMA_REQUIRE(mode != 1 || (gamma && dgamma && dbeta), "ln_bwd: affine mode needs gamma and grad buffers");
   HMA_REQUIRE(mode != 2 || (mod && dmod && rows_per_group > 0 && rows_per_group % 16 == 0),
               "ln_bwd: modulate mode needs shift/scale and rows_per_group %% 16 == 0");

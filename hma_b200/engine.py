@@ -61,8 +61,6 @@ def check_config(cfg) -> None:
     """Reject, loudly, what the CUDA path does not implement (no silent fallback)."""
     if cfg.d_model != 256 or cfg.num_heads != 8:
         raise NotImplementedError(f"hma_b200 kernels are built for d_model=256, num_heads=8 (got {cfg.d_model}, {cfg.num_heads})")
-    if cfg.qk_norm:
-        raise NotImplementedError("qk_norm=True (per-head q/k LayerNorm, attention.py:32-35) is not implemented on the CUDA path yet")
     if int(cfg.d_model * cfg.mlp_ratio) != 1024:
         raise NotImplementedError("mlp_ratio must be 4.0")
     if cfg.jointly_predict_actions or not cfg.jointly_predict_states:
@@ -269,12 +267,20 @@ class Engine:
                 side.wait_event(fork)
                 hmods, zmods, mods, mod_events = self.modulation_all_layers(p, c_bf, dom, d.num_layers, training)
         layers = []
+        qk = bool(self.cfg.qk_norm)  # norm1 / norm2 are Identity and q, k get a shared per-head LayerNorm (attention.py:32-35)
         for i in range(d.num_layers):
             lp = f"decoder.layers.{i}."
             L = {}
             # ---- spatial attention, pre-norm (st_transformer.py:85-86)
-            a1, st1 = ops.ln_fwd(x, 1, gamma=p[lp + "norm1.weight"], beta=p[lp + "norm1.bias"], eps=1e-5, want_stats=True)
+            if qk:
+                a1, st1 = ops.ln_fwd(x, 0), None
+            else:
+                a1, st1 = ops.ln_fwd(x, 1, gamma=p[lp + "norm1.weight"], beta=p[lp + "norm1.bias"], eps=1e-5, want_stats=True)
             qkv_s = ops.gemm_nt(a1, Wp[lp + "spatial_attn.qkv.weight"], EPI_BF16, bias=p.get(lp + "spatial_attn.qkv.bias"))
+            qkv_s_raw = qkv_t_raw = None
+            if qk:
+                qkv_s_raw = qkv_s
+                qkv_s = ops.qk_norm_fwd(qkv_s_raw, p[lp + "spatial_attn.norm.weight"], p[lp + "spatial_attn.norm.bias"])
             att_s, lse = ops.attn_spatial_fwd(qkv_s, M, n, d.heads, d.scale, want_lse=training)
             x1 = ops.gemm_nt(att_s, Wp[lp + "spatial_attn.proj.weight"], EPI_RESID, bias=p.get(lp + "spatial_attn.proj.bias"),
                              resid=x, out=None if training else x)
@@ -296,6 +302,9 @@ class Engine:
             # ---- causal temporal attention, no pre-norm (st_transformer.py:111)
             at = ops.ln_fwd(x2, 0)
             qkv_t = ops.gemm_nt(at, Wp[lp + "temporal_attn.qkv.weight"], EPI_BF16, bias=p.get(lp + "temporal_attn.qkv.bias"))
+            if qk:
+                qkv_t_raw = qkv_t
+                qkv_t = ops.qk_norm_fwd(qkv_t_raw, p[lp + "temporal_attn.norm.weight"], p[lp + "temporal_attn.norm.bias"])
             if mode in ("step", "commit"):
                 lse_t = None
                 att_t = ops.attn_temporal_cached(qkv_t, kv[i], t0, d.heads, d.scale)
@@ -308,14 +317,17 @@ class Engine:
             x3 = ops.gemm_nt(att_t, Wp[lp + "temporal_attn.proj.weight"], EPI_RESID, bias=p.get(lp + "temporal_attn.proj.bias"),
                              resid=x2, out=None if training else x2)
             # ---- MLP, pre-norm, erf-GELU (st_transformer.py:24-27,112)
-            a2, st2 = ops.ln_fwd(x3, 1, gamma=p[lp + "norm2.weight"], beta=p[lp + "norm2.bias"], eps=1e-5, want_stats=True)
+            if qk:
+                a2, st2 = ops.ln_fwd(x3, 0), None
+            else:
+                a2, st2 = ops.ln_fwd(x3, 1, gamma=p[lp + "norm2.weight"], beta=p[lp + "norm2.bias"], eps=1e-5, want_stats=True)
             z = torch.empty(N, 1024, device=x.device, dtype=torch.bfloat16) if training else None
             h = ops.gemm_nt(a2, Wp[lp + "mlp.fc1.weight"], EPI_GELU, bias=p.get(lp + "mlp.fc1.bias"), out2=z)
             x4 = ops.gemm_nt(h, Wp[lp + "mlp.fc2.weight"], EPI_RESID, bias=p.get(lp + "mlp.fc2.bias"), resid=x3,
                              out=None if training else x3)
             if training:
                 L.update(x0=x, a1=a1, st1=st1, qkv_s=qkv_s, att_s=att_s, lse=lse, x1=x1, at=at, qkv_t=qkv_t, att_t=att_t,
-                         x3=x3, a2=a2, st2=st2, z=z, h=h, lse_t=lse_t)
+                         x3=x3, a2=a2, st2=st2, z=z, h=h, lse_t=lse_t, qkv_s_raw=qkv_s_raw, qkv_t_raw=qkv_t_raw)
                 layers.append(L)
             x = x4
         # ---- head on the video tokens only (st_mask_git.py:681-683)
@@ -334,8 +346,10 @@ class Engine:
         for i in range(d.num_layers):
             lp = f"decoder.layers.{i}."
             for k in ("norm1.weight", "norm1.bias", "spatial_attn.qkv.weight", "spatial_attn.qkv.bias",
+                      "spatial_attn.norm.weight", "spatial_attn.norm.bias",
                       "spatial_attn.proj.weight", "spatial_attn.proj.bias", "temporal_attn.qkv.weight",
-                      "temporal_attn.qkv.bias", "temporal_attn.proj.weight", "temporal_attn.proj.bias", "norm2.weight",
+                      "temporal_attn.qkv.bias", "temporal_attn.norm.weight", "temporal_attn.norm.bias",
+                      "temporal_attn.proj.weight", "temporal_attn.proj.bias", "norm2.weight",
                       "norm2.bias", "mlp.fc1.weight", "mlp.fc1.bias", "mlp.fc2.weight", "mlp.fc2.bias"):
                 if lp + k in p:
                     names.append(lp + k)
@@ -402,6 +416,7 @@ class Engine:
             side.wait_event(fork)
         dy = None  # bf16 copy of dx whose column sums are already in the consumer's bias gradient
         side_keep = []
+        qk = bool(self.cfg.qk_norm)
         for i in reversed(range(d.num_layers)):
             L = sv["layers"][i]
             lp = f"decoder.layers.{i}."
@@ -412,12 +427,18 @@ class Engine:
             dz = ops.gemm_nt(dy, Wt[lp + "mlp.fc2.weight"], EPI_DGELU, aux=L["z"], colsum=g.get(lp + "mlp.fc1.bias"))
             ops.gemm_wgrad(dz, L["a2"], g2(lp + "mlp.fc1.weight"))
             da2 = ops.gemm_nt(dz, Wt[lp + "mlp.fc1.weight"], EPI_BF16)
-            dy = ops.ln_bwd(da2, L["x3"], L["st2"], 1, dx, gamma=p[lp + "norm2.weight"], dgamma=g2(lp + "norm2.weight"),
-                            dbeta=g2(lp + "norm2.bias"), want_next=True, colsum_next=g.get(lp + "temporal_attn.proj.bias"))
+            if qk:
+                dy = ops.ln_bwd(da2, None, None, 0, dx, want_next=True, colsum_next=g.get(lp + "temporal_attn.proj.bias"))
+            else:
+                dy = ops.ln_bwd(da2, L["x3"], L["st2"], 1, dx, gamma=p[lp + "norm2.weight"], dgamma=g2(lp + "norm2.weight"),
+                                dbeta=g2(lp + "norm2.bias"), want_next=True, colsum_next=g.get(lp + "temporal_attn.proj.bias"))
             # ---- temporal attention
             ops.gemm_wgrad(dy, L["att_t"], g2(lp + "temporal_attn.proj.weight"))
             datt = ops.gemm_nt(dy, Wt[lp + "temporal_attn.proj.weight"], EPI_BF16)
             dqkv = ops.attn_temporal_bwd(L["qkv_t"], L["att_t"], datt, L["lse_t"], B, T, n, d.heads, d.scale)
+            if qk:
+                ops.qk_norm_bwd(L["qkv_t_raw"], p[lp + "temporal_attn.norm.weight"], dqkv, g2(lp + "temporal_attn.norm.weight"),
+                                g2(lp + "temporal_attn.norm.bias"))
             ops.gemm_wgrad(dqkv, L["at"], g2(lp + "temporal_attn.qkv.weight"))
             if lp + "temporal_attn.qkv.bias" in g:
                 ops.colsum_bf16(dqkv, g2(lp + "temporal_attn.qkv.bias"))
@@ -450,13 +471,19 @@ class Engine:
             ops.gemm_wgrad(dy, L["att_s"], g2(lp + "spatial_attn.proj.weight"))
             datt = ops.gemm_nt(dy, Wt[lp + "spatial_attn.proj.weight"], EPI_BF16)
             dqkv = ops.attn_spatial_bwd(L["qkv_s"], L["att_s"], datt, L["lse"], M, n, d.heads, d.scale)
+            if qk:
+                ops.qk_norm_bwd(L["qkv_s_raw"], p[lp + "spatial_attn.norm.weight"], dqkv, g2(lp + "spatial_attn.norm.weight"),
+                                g2(lp + "spatial_attn.norm.bias"))
             ops.gemm_wgrad(dqkv, L["a1"], g2(lp + "spatial_attn.qkv.weight"))
             if lp + "spatial_attn.qkv.bias" in g:
                 ops.colsum_bf16(dqkv, g2(lp + "spatial_attn.qkv.bias"))
             da1 = ops.gemm_nt(dqkv, Wt[lp + "spatial_attn.qkv.weight"], EPI_BF16)
             nxt = f"decoder.layers.{i - 1}.mlp.fc2.bias" if i > 0 else None
-            dy = ops.ln_bwd(da1, L["x0"], L["st1"], 1, dx, gamma=p[lp + "norm1.weight"], dgamma=g2(lp + "norm1.weight"),
-                            dbeta=g2(lp + "norm1.bias"), want_next=i > 0, colsum_next=g.get(nxt) if nxt else None)
+            if qk:
+                dy = ops.ln_bwd(da1, None, None, 0, dx, want_next=i > 0, colsum_next=g.get(nxt) if nxt else None)
+            else:
+                dy = ops.ln_bwd(da1, L["x0"], L["st1"], 1, dx, gamma=p[lp + "norm1.weight"], dgamma=g2(lp + "norm1.weight"),
+                                dbeta=g2(lp + "norm1.bias"), want_next=i > 0, colsum_next=g.get(nxt) if nxt else None)
             sv["layers"][i] = None  # release this layer's activations
         if d.modulate:
             join = torch.cuda.Event()

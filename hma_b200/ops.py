@@ -106,12 +106,28 @@ def ln_bwd(dy: torch.Tensor, x: torch.Tensor, stats: torch.Tensor, mode: int, dx
            mod=None, rows_per_group: int = 0, dgamma=None, dbeta=None, dmod=None, want_next: bool = False,
            colsum_next=None):
     """dx += LN backward; optionally returns bf16(dx) for the next stage and accumulates its column sums."""
-    dy_next = torch.empty(x.shape[0], 256, device=x.device, dtype=BF16) if want_next else None
-    _call(f"ln_bwd[mode={mode}]", x.shape[0] * 256 * (16.0 if want_next else 14.0), "hma_ln_bwd", dy.data_ptr(),
-          dy.stride(0), x.data_ptr(), x.stride(0), stats.data_ptr(), x.shape[0], mode, _p(gamma), _p(mod),
+    rows = dy.shape[0]
+    dy_next = torch.empty(rows, 256, device=dy.device, dtype=BF16) if want_next else None
+    _call(f"ln_bwd[mode={mode}]", rows * 256 * (16.0 if want_next else 14.0), "hma_ln_bwd", dy.data_ptr(),
+          dy.stride(0), _p(x), x.stride(0) if x is not None else 0, _p(stats), rows, mode, _p(gamma), _p(mod),
           rows_per_group, dx.data_ptr(), dx.stride(0), _p(dgamma), _p(dbeta), _p(dmod), _p(dy_next),
           _p(colsum_next) if want_next else None, _s())
     return dy_next
+
+
+def qk_norm_fwd(qkv: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float = 1e-5) -> torch.Tensor:
+    """[LN32(q) | LN32(k) | v] of the bf16 projection output qkv [rows, 768] (qk_norm=True)."""
+    out = torch.empty_like(qkv)
+    _call("qk_norm_fwd", qkv.numel() * 4.0, "hma_qk_norm_fwd", qkv.data_ptr(), qkv.stride(0), qkv.shape[0], gamma.data_ptr(),
+          beta.data_ptr(), float(eps), out.data_ptr(), out.stride(0), _s())
+    return out
+
+
+def qk_norm_bwd(qkv: torch.Tensor, gamma: torch.Tensor, dqkv: torch.Tensor, dgamma: torch.Tensor, dbeta: torch.Tensor,
+                eps: float = 1e-5) -> None:
+    """dqkv (w.r.t. the normalised matrix) -> gradient w.r.t. the raw qkv, in place; dgamma / dbeta accumulated."""
+    _call("qk_norm_bwd", qkv.numel() * 6.0, "hma_qk_norm_bwd", qkv.data_ptr(), qkv.stride(0), qkv.shape[0], gamma.data_ptr(),
+          float(eps), dqkv.data_ptr(), dqkv.stride(0), dgamma.data_ptr(), dbeta.data_ptr(), _s())
 
 
 def colsum_bf16(G: torch.Tensor, out: torch.Tensor) -> None:

@@ -97,6 +97,14 @@ int hma_attn_temporal_cached(const void* qkv, long long ld_qkv, int q_col, int k
                              long long frame_stride, int rows, int n_prev, int heads, float scale, void* out,
                              long long ldo, void* stream);
 
+/* Per-head LayerNorm of q and k (qk_norm=True, attention.py:32-35,47-52): out = [LN32(q) | LN32(k) | v] from the bf16
+ * projection output qkv [rows, >= 768]; one affine LayerNorm(32, eps) shared by all heads of q and k. The backward
+ * converts dqkv (gradient w.r.t. `out`) into the gradient w.r.t. qkv in place and accumulates dgamma[32], dbeta[32]. */
+int hma_qk_norm_fwd(const void* qkv, long long ld, int rows, const float* gamma, const float* beta, float eps, void* out,
+                    long long ldo, void* stream);
+int hma_qk_norm_bwd(const void* qkv, long long ld, int rows, const float* gamma, float eps, void* dqkv, long long ldd,
+                    float* dgamma, float* dbeta, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Row-wise stages (d_model = 256): fp32 residual stream -> bf16 operand
  * ------------------------------------------------------------------------------------------- */
@@ -111,7 +119,8 @@ int hma_ln_fwd(const float* x, long long ldx, int rows, int mode, const float* g
                int dst_group, void* stream);
 /* dst[(f*n + s), :] = s < S ? src[(f*S + s), :] : 0 — fp32 rows of 256 (inverse of the remap above). */
 int hma_rows_scatter(const float* src, float* dst, int frames, int S, int n, void* stream);
-/* dx (fp32, accumulated in place) += LayerNorm backward of dy (bf16). mode 1 accumulates dgamma/dbeta,
+/* dx (fp32, accumulated in place) += LayerNorm backward of dy (bf16). mode 0 = identity norm (dx += dy; x, stats
+ * unused: qk_norm=True makes norm1 / norm2 nn.Identity, st_transformer.py:50,75); mode 1 accumulates dgamma/dbeta,
  * mode 2 accumulates dmod [groups, 512] = dshift|dscale. Optionally also writes dy_next = bf16(dx) [rows,256]
  * and colsum_next[256] += its column sums (operand and bias gradient of the next backward stage). */
 int hma_ln_bwd(const void* dy, long long lddy, const float* x, long long ldx, const float* stats, int rows, int mode,

@@ -289,3 +289,32 @@ def test_attn_spatial_bwd(frames, n):
     for name, sl in (("dq", slice(0, C)), ("dk", slice(C, 2 * C)), ("dv", slice(2 * C, 3 * C))):
         e = relerr(dqkv[:, sl], g[:, sl])
         assert e < 3e-2, (name, e)
+
+
+# ------------------------------------------------------------------------------------------------
+def test_qk_norm_fwd_bwd():
+    """Per-head LayerNorm(32) of q and k with one shared affine (attention.py:32-35,47-52), v passed through."""
+    from hma_b200 import ops
+    torch.manual_seed(9)
+    rows, H, hd = 1000, 8, 32
+    C = H * hd
+    qkv = (torch.randn(rows, 3 * C, device="cuda") * 1.7 + 0.4).bfloat16()
+    gamma = 1 + 0.2 * torch.randn(hd, device="cuda")
+    beta = 0.1 * torch.randn(hd, device="cuda")
+    out = ops.qk_norm_fwd(qkv, gamma, beta)
+    x = qkv.float().requires_grad_(True)
+    q, k, v = x[:, :C], x[:, C:2 * C], x[:, 2 * C:]
+    g, b = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    ln = lambda t: F.layer_norm(t.reshape(rows, H, hd), (hd,), g, b, 1e-5).reshape(rows, C)
+    ref = torch.cat([ln(q), ln(k), v], dim=1)
+    assert relerr(out, ref) < 1e-2
+    assert torch.equal(out[:, 2 * C:], qkv[:, 2 * C:])
+    dout = torch.randn(rows, 3 * C, device="cuda").bfloat16()
+    ref.backward(dout.float())
+    dqkv = dout.clone()
+    dg = torch.zeros(hd, device="cuda")
+    db = torch.zeros(hd, device="cuda")
+    ops.qk_norm_bwd(qkv, gamma, dqkv, dg, db)
+    torch.cuda.synchronize()
+    assert relerr(dqkv, x.grad) < 1.5e-2
+    assert relerr(dg, g.grad) < 5e-3 and relerr(db, b.grad) < 5e-3

@@ -15,7 +15,7 @@ import pytest
 import torch
 
 from oracle import stmaskgit_oracle as O
-from tests._util import build_cuda_model, golden
+from tests._util import GOLDEN as GOLDEN_DIR, build_cuda_model, golden
 
 pytestmark = pytest.mark.gpu
 
@@ -208,3 +208,43 @@ def test_config5_long_context_T32_heterogeneous_domains():
         other = [x for x in domains if x != dom][0]
         go = named[f"action_mlp.{other}.model.0.weight"].grad
         assert go is None or go.abs().max().item() == 0.0
+
+
+def test_mup_qknorm_qkvbias_variant_vs_reference_fixture():
+    """use_mup=True (attention scale 8/head_dim, FixedMuReadout), qk_norm=True (Identity norm1/norm2 + per-head q/k
+    LayerNorm) and qkv_bias=True against outputs of the real reference (tests/golden/tiny_mup_qknorm.pt)."""
+    from hma_b200 import GenieConfig, STMaskGIT
+
+    rec = torch.load(GOLDEN_DIR / "tiny_mup_qknorm.pt", weights_only=False)
+    kw = dict(num_layers=2, num_heads=8, d_model=256, T=4, S=256, use_mup=True, qk_norm=True, qkv_bias=True,
+              action_network="concat+modulate")
+    ocfg = O.OracleConfig(num_factored_vocabs=2, **kw)
+    sd = O.make_state_dict(ocfg, rec["domains"], rec["d_actions"], seed=rec["seed"], action_dims=rec["action_dims"])
+    model = STMaskGIT(GenieConfig(num_factored_vocabs=2, **kw))
+    model.init_action_projectors(rec["domains"], rec["d_actions"], [[[0.0] * a, [1.0] * a] for a in rec["action_dims"]],
+                                 "concat+modulate")
+    model.load_state_dict(sd, strict=True)
+    model = model.cuda()
+    dom = rec["domains"][0]
+    r = rec[dom]
+    out = model(r["input_ids"].cuda(), r["labels"].cuda(), action_ids=r["actions"].cuda(), domain=[dom, dom])
+    assert abs(out.loss.item() - r["loss"].item()) <= 1e-2 * abs(r["loss"].item()), (out.loss.item(), r["loss"].item())
+    d = out.logits.float().cpu()[:, :, :, ::4, ::4] - r["logits_sub"]
+    assert d.abs().max() <= 1e-2 * r["logits_sub"].abs().max(), d.abs().max()
+    out.loss.backward()
+    named = dict(model.named_parameters())
+    worst = 0.0
+    for k, gn in r["grad_norms"].items():
+        g = named[k].grad
+        assert g is not None, k
+        rel = abs(g.norm().item() - gn) / max(gn, 1e-12)
+        worst = max(worst, rel)
+        assert rel < 5e-2, (k, rel)
+    print("worst grad-norm rel err", worst)
+    # greedy 1-step decode through the incremental path on this variant too
+    B, T = 2, 4
+    prompt = r["labels"].reshape(B, T, 16, 16).clone().cuda()
+    prompt[:, -1] = 262144
+    s1, _, _ = model.maskgit_generate(prompt, T - 1, maskgit_steps=1, temperature=0.0, action_ids=r["actions"].cuda(),
+                                      domain=[dom, dom])
+    assert (s1.cpu() == r["gen_greedy1_samples"]).float().mean().item() > 0.9
