@@ -16,17 +16,17 @@ KERNELS = {
     "gemm_nt": dict(single=(0, 10), names={0: "start", 10: "end", 1: "mma:top", 2: "mma:tmem_free", 3: "mma:committed", 4: "epi:top",
                                            5: "epi:acc_ready", 6: "epi:done"}),
     "gemm_wgrad": dict(single=(0, 3, 4, 5), names={0: "start", 3: "mma_done", 4: "red_issued", 5: "end", 1: "tma_issued", 2: "full"}),
-    "attn_spatial_bwd": dict(names={0: "start", 11: "loaded", 1: "SdP_issued", 6: "sdp_ready", 5: "c:top", 7: "c:tmem_freed", 8: "c:pds_arrived",
-                                    2: "dVdK:go", 3: "dVdK:done", 4: "dQ:done", 9: "final", 10: "end"}),
+    "attn_spatial_bwd": dict(names={0: "start", 11: "loaded", 1: "SdP_issued", 5: "c:top", 2: "c:buf_free", 6: "c:sdp_ready",
+                                    7: "c:tmem_freed", 8: "c:pds_arrived", 3: "dVdK:issued", 4: "dQ:issued", 9: "final", 10: "end"}),
 }
 
 def run_attn_spatial_bwd():
     frames, n, H = 128, 320, 8
-    qkv = torch.randn(frames * n, 768, device="cuda").bfloat16()
-    out, lse = ops.attn_spatial_fwd(qkv, frames, n, H, 0.17, True)
-    dout = torch.randn_like(out)
-    for _ in range(3):
-        ops.attn_spatial_bwd(qkv, out, dout, lse, frames, n, H, 0.17)
+    qkvs = [torch.randn(frames * n, 768, device="cuda").bfloat16() for _ in range(4)]  # rotate: operands come from HBM
+    outs = [ops.attn_spatial_fwd(q, frames, n, H, 0.17, True) for q in qkvs]
+    douts = [torch.randn_like(o[0]) for o in outs]
+    for i in range(4):
+        ops.attn_spatial_bwd(qkvs[i], outs[i][0], douts[i], outs[i][1], frames, n, H, 0.17)
 
 def run_gemm_wgrad():
     N = 40960
