@@ -16,8 +16,8 @@ KERNELS = {
     "gemm_nt": dict(single=(0, 10), names={0: "start", 10: "end", 1: "mma:top", 2: "mma:tmem_free", 3: "mma:committed", 4: "epi:top",
                                            5: "epi:acc_ready", 6: "epi:done"}),
     "gemm_wgrad": dict(single=(0, 3, 4, 5), names={0: "start", 3: "mma_done", 4: "red_issued", 5: "end", 1: "tma_issued", 2: "full"}),
-    "attn_spatial_bwd": dict(names={0: "start", 11: "loaded", 1: "SdP_issued", 5: "c:top", 2: "c:buf_free", 6: "c:sdp_ready",
-                                    7: "c:tmem_freed", 8: "c:pds_arrived", 3: "dVdK:issued", 4: "dQ:issued", 9: "final", 10: "end"}),
+    "attn_spatial_bwd": dict(names={0: "start", 11: "loaded", 1: "SdP_issued", 5: "c:top", 6: "c:sdp_ready", 7: "c:tmem_freed",
+                                    8: "c:pds_arrived", 2: "dVdK:go", 3: "dVdK:issued", 4: "dQ:issued", 9: "final", 10: "end"}),
 }
 
 def run_attn_spatial_bwd():
