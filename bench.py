@@ -258,8 +258,6 @@ def main() -> None:
     sampler.start()
     launches0 = ops.LAUNCHES
     dominant = "attn_spatial_bwd"  # largest share of the step (profiles/r01b_launches_summary.txt); DESIGN.md §3.2
-    if not step_fn.cuda_graphs:
-        ops.PROFILER = ops.Profiler()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.profiler.start()  # no-op unless run as `ncu --profile-from-start off ...` (profiles/ recipes)
     e0.record()
@@ -271,16 +269,17 @@ def main() -> None:
     ms_resident = e0.elapsed_time(e1)
     launches = ops.LAUNCHES - launches0
     loss_val = float(out[0].item())
-    roofline_pass = "the timed region"
-    if step_fn.cuda_graphs:
-        # graph replays cannot carry per-launch timing events: the roofline kernel is timed over the same steps
-        # launched from the host, right after the timed region, in this process (clock sampler still running)
-        roofline_pass = "the same steps re-run without graph replay right after the timed region"
-        step_fn.cuda_graphs = False
-        ops.PROFILER = ops.Profiler()
-        for i in range(args.warmup, total):
-            run_resident(i, resident[i])
-        step_fn.cuda_graphs = True
+    # Per-launch CUDA events cannot ride inside graph replays, and between host launches they break the programmatic
+    # dependent launch overlap: the roofline kernel (and every other stage) is timed over the SAME steps re-launched
+    # from the host with an event pair around each launch, right after the timed region, in this process, with the
+    # clock sampler still running.
+    roofline_pass = "the same steps re-run with per-launch events right after the timed region"
+    was_graph = step_fn.cuda_graphs
+    step_fn.cuda_graphs = False
+    ops.PROFILER = ops.Profiler()
+    for i in range(args.warmup, total):
+        run_resident(i, resident[i])
+    step_fn.cuda_graphs = was_graph
     prof = ops.PROFILER.summary()
     ops.PROFILER = None
 
