@@ -136,3 +136,37 @@ def test_incremental_decode_matches_oracle_logits(setup):
     want = ref.view(1, 2, 512, 16, 16).permute(0, 2, 1, 3, 4)
     d = (fl.float().cpu() - want).abs().max().item()
     assert d <= 1e-2 * want.abs().max().item(), d
+
+
+def test_interactive_sliding_window_graph_prefill_matches_eager(setup):
+    """The simulator loop (sim/simulator.py:233-372): B=1, sliding window, one maskgit_generate per step. From the third
+    call on the prefill itself is a graph replay; tokens must equal the eager incremental path step by step."""
+    rec, cfg, sd, model = setup
+    dom = rec["domains"][0]
+    P, T = cfg.T - 1, cfg.T
+    g = torch.Generator().manual_seed(8)
+    frames0 = torch.randint(0, 262144, (P, 16, 16), generator=g).cuda()
+    acts_all = torch.randn(6 + P + 1, rec["d_actions"][0], generator=g).cuda()
+    outs = {}
+    try:
+        for graphs in (False, True):
+            model.decode_cuda_graphs = graphs
+            model._sessions.clear()
+            frames = frames0.clone()
+            seq = []
+            for it in range(6):
+                window = torch.cat([frames, torch.zeros_like(frames[:1])]).unsqueeze(0).contiguous()
+                window[:, -1] = cfg.mask_token_id
+                acts = acts_all[it: it + P + 1].unsqueeze(0).contiguous()
+                nxt = model.maskgit_generate(window, out_t=P, maskgit_steps=2, temperature=0.0, unmask_mode="greedy", action_ids=acts,
+                                             domain=[dom])[0].squeeze(0)
+                assert (nxt != cfg.mask_token_id).all()
+                seq.append(nxt.clone())
+                frames = torch.cat([frames[1:], nxt.unsqueeze(0)])
+            outs[graphs] = torch.stack(seq)
+        assert torch.equal(outs[False], outs[True])
+        sess = next(iter(model._sessions.values()))
+        assert len(sess._prefill) == 1  # the prefill of the sliding window was captured once and replayed
+    finally:
+        model.decode_cuda_graphs = True
+        model._sessions.clear()
