@@ -34,6 +34,8 @@ D_ACTION_CYCLE = [2, 4, 7, 14, 35, 24, 14, 30, 70, 10]
 ACTION_DIM_CYCLE = [2, 4, 7, 7, 7, 8, 14, 2, 7, 10]
 L, HEADS, D_MODEL, T, S, B_PER_GPU = 32, 8, 256, 16, 256, 8
 N_TOK_FRAME = S + 64
+WORKLOAD = ("HMA-MagVit (magvit_n32_h8_d256_action, 40 domains) training step: 16 frames x 16x16 tokens + 64 action "
+            "tokens/frame, batch 8/GPU; fwd + fused CE + bwd + grad exchange + clip + AdamW")
 
 
 def train_flops_per_sample() -> float:
@@ -126,8 +128,9 @@ def run_reference_arm(args) -> None:
         "impl": "reference", "metric": "train_video_tokens_per_s", "value": tps, "unit": "tokens/s",
         "n_gpus": args.gpus, "steps": steps, "warmup": 1, "ms_per_step": sec * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "HMA-MagVit 32L d256 h8, T=16, 16x16 tokens + 64 action tokens/frame, training step "
-                               "(fwd+bwd), reference algorithm on host cores", "batch": 1, "domains": 1},
+        "config": {"workload": WORKLOAD, "layers": L, "parallelism": "host cores of rank 0",
+                   "sample": "bounded sample of that workload: 1 sample (4096 video tokens) per step, full 32 layers, fwd + loss + "
+                             "bwd of the reference algorithm (fp32 oracle port, math attention), 1 action domain"},
         "cpu_baseline": {"value": tps, "unit": "tokens/s", "cores": threads, "kind": "port",
                          "sample": "1 sample (4096 video tokens) of the config-2 shape per step, full 32 layers, fwd+bwd"},
         "e2e": {"value": tps, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -135,13 +138,13 @@ def run_reference_arm(args) -> None:
     print(json.dumps(line), flush=True)
 
 
-def generation_leg(model, dev, world, rank, domains, d_actions, sync_all, reps: int = 3):
+def generation_leg(model, dev, world, rank, domains, d_actions, sync_all, reps: int = 3, per_gpu: bool = True):
     """BASELINE configs[2]: 8 prompt frames -> 8 generated frames, 16x16 tokens, batch 64 split over the GPUs (replicas,
     no collective), maskgit_steps 2, temperature 1, through the public STMaskGIT.generate API. Host prompt in, host
     tokens out inside the timed region. Returns (frames/s over all ranks, ms per generate call)."""
     import torch.distributed as dist
     Tp, Tn, K = 8, T - 8, 2
-    Bg = max(1, 64 // world)
+    Bg = 64 if per_gpu else max(1, 64 // world)
     g = torch.Generator().manual_seed(4321 + rank)
     prompt = torch.randint(0, 262144, (Bg, Tp * S), generator=g).pin_memory()
     actions = torch.randn(Bg, T, d_actions[1], generator=g).pin_memory()
@@ -310,6 +313,9 @@ def main() -> None:
     gen_fps = None
     if not args.no_generation:
         gen_fps, gen_ms, gen_b = generation_leg(model, dev, world, rank, domains, d_actions, sync_all)
+        gen_strong = None
+        if world > 1:  # the same 64 samples split over the GPUs (strong scaling), for reference
+            gen_strong = generation_leg(model, dev, world, rank, domains, d_actions, sync_all, per_gpu=False)
 
     # ---------------- optional per-stage breakdown (one extra, untimed step)
     if args.breakdown and rank == 0:
@@ -363,9 +369,7 @@ def main() -> None:
         "metric": "train_video_tokens_per_s", "value": value, "unit": "tokens/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_resident / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": "HMA-MagVit (magvit_n32_h8_d256_action, 40 domains) training step: 16 frames x 16x16 "
-                               "tokens + 64 action tokens/frame, batch 8/GPU; fwd + fused CE + bwd + grad exchange + "
-                               "clip + AdamW", "layers": args.layers, "params": n_params,
+        "config": {"workload": WORKLOAD, "layers": args.layers, "params": n_params,
                    "global_batch": world * B_PER_GPU, "tokens_per_step": tokens_per_step, "parallelism": f"dp{world}",
                    "l2": "per-step working set (~19 GB of activations) >> 126 MB L2; no explicit flush needed",
                    "loss": loss_val, "model_tflops_per_gpu": step_tf,
@@ -390,7 +394,11 @@ def main() -> None:
                        "global_batch": gen_b * world, "layers": args.layers, "parallelism": f"replicas x{world} (no collective)",
                        "algorithm": "frame-incremental decode: per-layer temporal K/V cache + CUDA-graph replay of the "
                                     "one-frame pass (reference algorithm recomputes the 16-frame window per MaskGIT step)",
-                       "io": "pinned host prompt/actions in, host tokens out, inside the timed region"}}
+                       "io": "pinned host prompt/actions in, host tokens out, inside the timed region",
+                       "scaling": "weak (batch 64 per GPU)"}}
+        if gen_strong is not None:
+            line["generation"]["strong_scaling_total_batch_64"] = {"value": gen_strong[0], "unit": "frames/s",
+                                                                    "ms_per_generate_call": gen_strong[1], "batch_per_gpu": gen_strong[2]}
     if not args.no_cpu_baseline and world == 1:
         tps, sec, threads = cpu_oracle_train_tokens_per_s(2, 1)
         line["cpu_baseline"] = {"value": tps, "unit": "tokens/s", "cores": threads, "kind": "port",
