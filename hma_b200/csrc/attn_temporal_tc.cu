@@ -144,19 +144,6 @@ __device__ __forceinline__ void zero_smem(uint32_t addr, int bytes, int tid, int
     asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(addr + (uint32_t)i), "r"(0u) : "memory");
 }
 
-// Non-blocking mbarrier phase test (the UMMA issuer polls several barriers instead of blocking on one).
-__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
-  uint32_t done;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}\n"
-      : "=r"(done)
-      : "r"(bar), "r"(parity)
-      : "memory");
-  return done != 0;
-}
-
 __device__ __forceinline__ float max32(const float (&s)[32]) {
   float a = fmaxf(s[0], s[1]), b = fmaxf(s[2], s[3]), c = fmaxf(s[4], s[5]), d = fmaxf(s[6], s[7]);
 #pragma unroll

@@ -1,3 +1,4 @@
+"""Host time to enqueue one training step without CUDA graphs vs the GPU time of the step (why TrainStep replays graphs)."""
 import sys, time, torch
 sys.path.insert(0, '/root/repo')
 import bench
