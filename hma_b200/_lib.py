@@ -61,6 +61,8 @@ _SIGNATURES = {
                       c_void_p],
     "hma_embed_bwd": [c_void_p, c_fp, c_int, c_int, c_int, c_int, c_int, c_int, c_ll, c_fp, c_fp, c_fp, c_fp, c_fp,
                       c_void_p],
+    "hma_collate_maskgit": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_ll, c_fp, c_float, c_void_p,
+                            c_int, c_fp, c_fp, c_fp, c_fp, c_void_p],
     "hma_ce_fwd": [c_fp, c_ll, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_ll, c_float, c_fp, c_fp, c_fp,
                    c_void_p],
     "hma_ce_bwd": [c_fp, c_ll, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_ll, c_float, c_fp, c_fp, c_fp,

@@ -268,6 +268,17 @@ def embed_bwd(ids, dx, pos_n, B, T, S, A, vs, mask_id, dE0, dE1, dmask, dact, dp
               dmask.data_ptr(), _p(dact), dpos.data_ptr(), _s())
 
 
+def collate_maskgit(tokens, B, T, S, nv, vs, mask_id, corrupt_r, corrupt_thresh, rand_vals, first_masked_frame, frame_rates,
+                    frame_r, mask_prob, mask_r):
+    """One pass of the training collator (hma/data.py:28-98) given its random draws. Returns (input_ids, labels)."""
+    input_ids = torch.empty_like(tokens)
+    labels = torch.empty_like(tokens)
+    _call("collate_maskgit", tokens.numel() * 24.0, "hma_collate_maskgit", tokens.data_ptr(), input_ids.data_ptr(), labels.data_ptr(),
+          B, T, S, nv, vs, mask_id, _p(corrupt_r), float(corrupt_thresh), _p(rand_vals), first_masked_frame, _p(frame_rates),
+          _p(frame_r), _p(mask_prob), _p(mask_r), _s())
+    return input_ids, labels
+
+
 def ce_fwd(logits, labels, input_ids, B, T, S, nv, vs, mask_id, smoothing):
     rows = B * T * S
     lse = torch.empty(rows, nv, device=logits.device, dtype=F32)

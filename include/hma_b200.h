@@ -155,6 +155,18 @@ int hma_embed_bwd(const long long* ids, const float* dx, int pos_n, int B, int T
                   long long mask_id, float* dE0, float* dE1, float* dmask, float* dact, float* dpos, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Training collator on device (hma/data.py:28-98 get_maskgit_collator): token corruption of the factorised ids, the
+ * non-MLM progressive corruption of frames >= first_masked_frame, and cosine-rate masking, given the caller's random
+ * draws (same tensors as the reference draws). tokens/input_ids/labels: i64 [B,T,S]. Optional inputs may be NULL:
+ * corrupt_r f32 [B,T,S,nv] (+ corrupt_thresh = max_corrupt_rate*u01), rand_vals i64 [B,T,S,nv], frame_rates f32 [T-fmf]
+ * and frame_r f32 [B,T-fmf,S,nv], mask_prob f32 [B,T-fmf] and mask_r f32 [B,T-fmf,S].
+ * ------------------------------------------------------------------------------------------- */
+int hma_collate_maskgit(const long long* tokens, long long* input_ids, long long* labels, int B, int T, int S, int nv,
+                        int vs, long long mask_id, const float* corrupt_r, float corrupt_thresh,
+                        const long long* rand_vals, int first_masked_frame, const float* frame_rates,
+                        const float* frame_r, const float* mask_prob, const float* mask_r, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Factorised cross-entropy (st_mask_git.py:603-630)
  * ------------------------------------------------------------------------------------------- */
 /* sums[3] = sum(mask*loss), sum(mask*acc), sum(mask); loss_acc[2] = loss, acc; lse: [rows, nv]. */
