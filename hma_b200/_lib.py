@@ -45,6 +45,8 @@ _SIGNATURES = {
     "hma_qk_norm_bwd": [c_void_p, c_ll, c_int, c_fp, c_float, c_void_p, c_ll, c_fp, c_fp, c_void_p],
     "hma_ln_fwd": [c_fp, c_ll, c_int, c_int, c_fp, c_fp, c_fp, c_int, c_float, c_void_p, c_ll, c_fp, c_int, c_int,
                    c_void_p],
+    "hma_group_add": [c_fp, c_fp, c_fp, c_int, c_int, c_void_p],
+    "hma_group_colsum": [c_fp, c_fp, c_int, c_int, c_void_p],
     "hma_rows_scatter": [c_fp, c_fp, c_int, c_int, c_int, c_void_p],
     "hma_ln_bwd": [c_void_p, c_ll, c_fp, c_ll, c_fp, c_int, c_int, c_fp, c_fp, c_int, c_fp, c_ll, c_fp, c_fp, c_fp,
                    c_void_p, c_fp, c_void_p],

@@ -634,3 +634,65 @@ extern "C" int hma_colsum_bf16(const void* G, long long ld, int rows, int C, flo
   HMA_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
+
+// ------------------------------------------------------------------------------------------------
+// Additive action conditioning (action_network containing "mlp", st_transformer.py:93-97): the per-(b, t) action
+// embedding is added to every token of its frame in every layer. Forward: y[r] = x[r] + v[r / rows_per_group];
+// backward: dv[g] += sum of the group's rows of dx (dx itself passes through unchanged).
+// ------------------------------------------------------------------------------------------------
+namespace hma {
+__global__ void __launch_bounds__(256) group_add_kernel(const float* x, const float* v, float* y, int rows, int rows_per_group) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (long long row = (long long)blockIdx.x * 8 + warp; row < rows; row += (long long)gridDim.x * 8) {
+    const RowLoad a = load_row_f32(x + row * kC, lane);
+    const RowLoad b = load_row_f32(v + (row / rows_per_group) * kC, lane);
+    float o[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = a.v[j] + b.v[j];
+    store_row_f32(y + row * kC, lane, o);
+  }
+}
+__global__ void __launch_bounds__(256) group_colsum_kernel(const float* dx, float* dv, int rows_per_group) {
+  pdl_wait();
+  pdl_launch_dependents();
+  __shared__ float red[8][kC];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float* base = dx + (size_t)blockIdx.x * rows_per_group * kC;
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  for (int r = warp; r < rows_per_group; r += 8) {
+    const RowLoad a = load_row_f32(base + (size_t)r * kC, lane);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] += a.v[j];
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) red[warp][col_of(lane, j)] = acc[j];
+  __syncthreads();
+  float s = 0.f;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) s += red[w][threadIdx.x];
+  dv[(size_t)blockIdx.x * kC + threadIdx.x] += s;  // one CTA per group: no atomics
+}
+}  // namespace hma
+
+extern "C" int hma_group_add(const float* x, const float* v, float* y, int rows, int rows_per_group, void* stream_) {
+  using namespace hma;
+  if (rows == 0) return 0;
+  HMA_REQUIRE(rows_per_group > 0 && rows % rows_per_group == 0, "group_add: rows=%d is not a multiple of rows_per_group=%d", rows, rows_per_group);
+  int grid = (rows + 7) / 8;
+  const int cap = hma_host::sm_count() * 8;
+  if (grid > cap) grid = cap;
+  HMA_CHECK_CUDA(hma_host::launch_pdl(group_add_kernel, dim3(grid), dim3(256), 0, static_cast<cudaStream_t>(stream_), x, v, y, rows, rows_per_group));
+  return 0;
+}
+
+extern "C" int hma_group_colsum(const float* dx, float* dv, int groups, int rows_per_group, void* stream_) {
+  using namespace hma;
+  if (groups == 0) return 0;
+  HMA_REQUIRE(rows_per_group > 0, "group_colsum: bad rows_per_group");
+  HMA_CHECK_CUDA(hma_host::launch_pdl(group_colsum_kernel, dim3(groups), dim3(256), 0, static_cast<cudaStream_t>(stream_), dx, dv, rows_per_group));
+  return 0;
+}

@@ -43,6 +43,7 @@ class Dims:
     num_layers: int
     modulate: bool
     readout_alpha: float
+    additive: bool = False  # action_network containing "mlp": the action embedding is added to every token of its frame
 
     @property
     def n(self) -> int:
@@ -66,8 +67,9 @@ def check_config(cfg) -> None:
     if cfg.jointly_predict_actions or not cfg.jointly_predict_states:
         raise NotImplementedError("jointly_predict_actions / jointly_predict_states=False are not implemented")
     net = cfg.action_network
-    if "cross_attention" in net or ("mlp" in net and "modulate" not in net and net != "concat"):
-        raise NotImplementedError(f"action_network={net!r} is not implemented (supported: concat, modulate, concat+modulate)")
+    if "cross_attention" in net and "mlp" not in net:
+        raise NotImplementedError(f"action_network={net!r} is not implemented (supported: mlp, concat, modulate and their "
+                                  "combinations; st_transformer.py:93-104 checks 'mlp' first, then 'cross_attention', then 'modulate')")
     if cfg.num_factored_vocabs not in (1, 2) or cfg.factored_vocab_size % 256 != 0 or \
             cfg.num_factored_vocabs * cfg.factored_vocab_size > 1024:
         raise NotImplementedError("unsupported factorised vocabulary")
@@ -155,8 +157,9 @@ class Engine:
         scale = 8.0 / hd if cfg.use_mup else hd ** -0.5  # attention.py:27
         return Dims(B=B, T=T, S=S, A=A, heads=cfg.num_heads, nv=cfg.num_factored_vocabs, vs=cfg.factored_vocab_size,
                     mask_id=cfg.image_vocab_size, scale=scale, num_layers=cfg.num_layers,
-                    modulate=with_actions and "modulate" in net,
-                    readout_alpha=(256.0 / cfg.d_model) if cfg.use_mup else 1.0)  # st_mask_git.py:755-760,788-789
+                    modulate=with_actions and "modulate" in net and "mlp" not in net and "cross_attention" not in net,
+                    readout_alpha=(256.0 / cfg.d_model) if cfg.use_mup else 1.0,  # st_mask_git.py:755-760,788-789
+                    additive=with_actions and "mlp" in net)
 
     def _prepare(self, p: Dict[str, Tensor], d: Dims, dom: Optional[str], training: bool) -> None:
         names = ["out_x_proj.weight"]
@@ -297,6 +300,8 @@ class Engine:
                                  out=None if training else x1)
                 if training:
                     L.update(zmod=zmod, hmod=hmod, mod=mod, am=am, stm=stm)
+            elif d.additive:  # st_transformer.py:93-97: x += action embedding of the frame, broadcast over its tokens
+                x2 = ops.group_add(x1, act, n, out=None if training else x1)
             else:
                 x2 = x1
             # ---- causal temporal attention, no pre-norm (st_transformer.py:111)
@@ -359,7 +364,7 @@ class Engine:
     def domain_param_names(self, p: Dict[str, Tensor], d: Dims, dom: Optional[str], has_actions: bool) -> List[str]:
         """Parameters only batches of domain `dom` touch (action stem + per-layer ModulateLayers)."""
         names: List[str] = []
-        if not has_actions or dom is None or not (d.A or d.modulate):
+        if not has_actions or dom is None or not (d.A or d.modulate or d.additive):
             return names
         q = f"action_mlp.{dom}.model."
         names += [q + k for k in ("0.weight", "0.bias", "1.weight", "1.bias", "3.weight", "3.bias")]
@@ -466,6 +471,8 @@ class Engine:
                     ops.gemm_nt(dzm, Wt[ap + "adaLN_modulation.0.weight"], EPI_RESID, resid=dact, out=dact)
                     side_keep.append((dmod, dmod_bf, dzm))  # alive until the side stream has been joined
             else:
+                if d.additive:
+                    ops.group_colsum(dx, dact, n)
                 dy = ops.cast_colsum(dx, g.get(lp + "spatial_attn.proj.bias"))
             # ---- spatial attention
             ops.gemm_wgrad(dy, L["att_s"], g2(lp + "spatial_attn.proj.weight"))
@@ -496,7 +503,7 @@ class Engine:
                       g["token_embed.factored_embeds.0.weight"], g.get("token_embed.factored_embeds.1.weight"),
                       g["token_embed.mask_token_embed"], dact if d.A else None, g["pos_embed_TSC"])
         # ---- action stem backward
-        if sv["has_actions"] and (d.A or d.modulate):
+        if sv["has_actions"] and (d.A or d.modulate or d.additive):
             q = f"action_mlp.{dom}.model."
             dact_bf = ops.cast_bf16(dact)
             ops.gemm_wgrad(dact_bf, sv["h1n"], g2(q + "3.weight"))

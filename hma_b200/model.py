@@ -218,7 +218,8 @@ class STMaskGIT(nn.Module, PyTorchModelHubMixin):
         for layer in self.decoder.layers:
             layer.action_projectors = nn.ModuleDict()
             for dom in domains:
-                if "modulate" in action_network:
+                # same precedence as st_mask_git.py:240-251: "mlp" (additive, Identity projector) wins over "modulate"
+                if "modulate" in action_network and "mlp" not in action_network and "cross_attention" not in action_network:
                     layer.action_projectors[dom] = _ModulateLayer(cfg.d_model)
                 else:
                     layer.action_projectors[dom] = nn.Identity()

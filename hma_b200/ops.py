@@ -193,6 +193,20 @@ def ln_relu_bwd(dy, x, stats, gamma, beta, dgamma, dbeta) -> torch.Tensor:
     return dx
 
 
+def group_add(x: torch.Tensor, v: torch.Tensor, rows_per_group: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """x[r] + v[r // rows_per_group] for fp32 rows of 256 (additive action conditioning)."""
+    if out is None:
+        out = torch.empty_like(x)
+    _call("group_add", x.numel() * 8.0, "hma_group_add", x.data_ptr(), v.data_ptr(), out.data_ptr(), x.shape[0], rows_per_group, _s())
+    return out
+
+
+def group_colsum(dx: torch.Tensor, dv: torch.Tensor, rows_per_group: int) -> None:
+    """dv[g] += column sums of the rows of group g of dx (fp32 rows of 256)."""
+    _call("group_colsum", dx.numel() * 4.0, "hma_group_colsum", dx.data_ptr(), dv.data_ptr(), dx.shape[0] // rows_per_group,
+          rows_per_group, _s())
+
+
 def rows_scatter(src: torch.Tensor, frames: int, S: int, n: int) -> torch.Tensor:
     dst = torch.empty(frames * n, 256, device=src.device, dtype=F32)
     _call("rows_scatter", frames * n * 256 * 8.0, "hma_rows_scatter", src.data_ptr(), dst.data_ptr(), frames, S, n, _s())

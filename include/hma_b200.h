@@ -117,6 +117,10 @@ int hma_qk_norm_bwd(const void* qkv, long long ld, int rows, const float* gamma,
 int hma_ln_fwd(const float* x, long long ldx, int rows, int mode, const float* gamma, const float* beta,
                const float* mod, int rows_per_group, float eps, void* y, long long ldy, float* stats, int src_group,
                int dst_group, void* stream);
+/* Additive action conditioning (action_network containing "mlp", st_transformer.py:93-97), fp32 rows of 256:
+ * y[r] = x[r] + v[r / rows_per_group] (y may alias x); backward: dv[g] += sum of the rows of group g of dx. */
+int hma_group_add(const float* x, const float* v, float* y, int rows, int rows_per_group, void* stream);
+int hma_group_colsum(const float* dx, float* dv, int groups, int rows_per_group, void* stream);
 /* dst[(f*n + s), :] = s < S ? src[(f*S + s), :] : 0 — fp32 rows of 256 (inverse of the remap above). */
 int hma_rows_scatter(const float* src, float* dst, int frames, int S, int n, void* stream);
 /* dx (fp32, accumulated in place) += LayerNorm backward of dy (bf16). mode 0 = identity norm (dx += dy; x, stats

@@ -248,3 +248,49 @@ def test_mup_qknorm_qkvbias_variant_vs_reference_fixture():
     s1, _, _ = model.maskgit_generate(prompt, T - 1, maskgit_steps=1, temperature=0.0, action_ids=r["actions"].cuda(),
                                       domain=[dom, dom])
     assert (s1.cpu() == r["gen_greedy1_samples"]).float().mean().item() > 0.9
+
+
+@pytest.mark.parametrize("net", ["mlp", "concat+mlp"])
+def test_additive_action_network_vs_oracle(net):
+    """action_network containing "mlp" (the GenieConfig default): the action embedding is added to every token of its
+    frame in every layer (st_transformer.py:93-97), with ("concat+mlp") or without the 64 action tokens."""
+    from hma_b200 import GenieConfig, STMaskGIT
+
+    T = 4
+    domains, d_actions, adims = ["a", "b"], [7, 14], [7, 7]
+    kw = dict(num_layers=2, num_heads=8, d_model=256, T=T, S=256, use_mup=False, qk_norm=False, qkv_bias=False, action_network=net)
+    ocfg = O.OracleConfig(num_factored_vocabs=2, **kw)
+    sd = O.make_state_dict(ocfg, domains, d_actions, seed=5, action_dims=adims)
+    model = STMaskGIT(GenieConfig(num_factored_vocabs=2, **kw))
+    model.init_action_projectors(domains, d_actions, [[[0.0] * a, [1.0] * a] for a in adims], net)
+    model.load_state_dict(sd, strict=True)
+    model = model.cuda()
+    g = torch.Generator().manual_seed(2)
+    labels = torch.randint(0, 262144, (2, T * 256), generator=g)
+    mask = torch.rand(2, T, 256, generator=g) < 0.5
+    mask[:, 0] = False
+    ids = torch.where(mask.view(2, -1), torch.full_like(labels, 262144), labels)
+    acts = torch.randn(2, T, 14, generator=g)
+    params = {k: v.clone().requires_grad_(v.is_floating_point() and "action_preprocessor" not in k) for k, v in sd.items()}
+    loss, acc, logits = O.forward(ids, labels, acts, ["b", "b"], params, ocfg)
+    loss.backward()
+    out = model(ids.cuda(), labels.cuda(), action_ids=acts.cuda(), domain=["b", "b"])
+    out.loss.backward()
+    assert abs(out.loss.item() - loss.item()) <= 1e-2 * abs(loss.item())
+    d = out.logits.float().cpu() - logits.detach()
+    assert d.abs().max() <= 1e-2 * logits.abs().max()
+    named = dict(model.named_parameters())
+    for k in ("action_mlp.b.model.0.weight", "action_mlp.b.model.3.weight", "action_mlp.b.model.3.bias",
+              "decoder.layers.1.temporal_attn.qkv.weight", "pos_embed_TSC"):
+        gr, gc = params[k].grad, named[k].grad.cpu()
+        assert abs(gc.norm().item() - gr.norm().item()) <= 5e-2 * gr.norm().item(), (net, k, gc.norm().item(), gr.norm().item())
+    # incremental decode of the last frame agrees with the full-window forward on this variant too
+    x = labels.reshape(2, T, 16, 16).clone().cuda()
+    x[:, -1] = 262144
+    with torch.no_grad():
+        full, _ = model.compute_logits(x, action_ids=acts.cuda(), domain=["b", "b"])
+    want = full[:, :, -1].permute(0, 2, 3, 1).reshape(2 * 256, -1).float()
+    sess = model._decode_session(x, T - 1, acts.cuda(), ["b", "b"], {})
+    got = sess.step(x[:, -1], T - 1).float()
+    assert (got - want).abs().max() <= 1e-2 * want.abs().max()
+    model._sessions.clear()
