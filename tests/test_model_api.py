@@ -37,7 +37,7 @@ def test_unsupported_configs_fail_loudly():
     from hma_b200 import GenieConfig, STMaskGIT
 
     with pytest.raises(NotImplementedError):
-        STMaskGIT(GenieConfig(num_layers=1, num_heads=8, d_model=256, num_factored_vocabs=2, qk_norm=True))
+        STMaskGIT(GenieConfig(num_layers=1, num_heads=8, d_model=256, num_factored_vocabs=2, action_network="cross_attention"))
     with pytest.raises(NotImplementedError):
         STMaskGIT(GenieConfig(num_layers=1, num_heads=8, d_model=512, num_factored_vocabs=2, qk_norm=False))
 
