@@ -18,6 +18,7 @@ c_int = ctypes.c_int
 c_ll = ctypes.c_longlong
 c_float = ctypes.c_float
 c_fp = ctypes.c_void_p  # float* passed as raw address
+c_u64 = ctypes.c_ulonglong
 
 
 class HmaError(RuntimeError):
@@ -76,6 +77,28 @@ _SIGNATURES = {
                        c_float, c_void_p],
     "hma_umma_probe": [c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_fp, c_void_p],
     "hma_gemm_wgrad": [c_void_p, c_ll, c_void_p, c_ll, c_int, c_int, c_int, c_fp, c_ll, c_void_p],
+    "hma_mar_embed_fwd": [c_fp, c_void_p, c_fp, c_fp, c_fp, c_fp, c_fp, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                          c_int, c_fp, c_fp, c_fp, c_void_p],
+    "hma_mar_embed_bwd": [c_fp, c_fp, c_void_p, c_fp, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_fp, c_fp, c_fp,
+                          c_fp, c_void_p],
+    "hma_mar_ln_fwd": [c_fp, c_int, c_int, c_fp, c_fp, c_float, c_void_p, c_ll, c_int, c_int, c_fp, c_int, c_fp, c_void_p, c_fp,
+                       c_void_p],
+    "hma_mar_ln_bwd": [c_void_p, c_fp, c_fp, c_fp, c_int, c_int, c_fp, c_fp, c_void_p, c_ll, c_int, c_int, c_fp, c_int, c_void_p,
+                       c_fp, c_fp, c_void_p, c_ll, c_fp, c_int, c_void_p],
+    "hma_mar_gate_fwd": [c_fp, c_void_p, c_ll, c_int, c_void_p, c_int, c_int, c_fp, c_void_p],
+    "hma_mar_gate_bwd": [c_fp, c_void_p, c_ll, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p, c_ll, c_void_p],
+    "hma_mar_silu_fwd": [c_fp, c_fp, c_ll, c_int, c_void_p, c_void_p],
+    "hma_mar_silu_bwd": [c_fp, c_fp, c_ll, c_void_p, c_void_p],
+    "hma_mar_q_sample": [c_fp, c_fp, c_void_p, c_fp, c_ll, c_int, c_int, c_void_p, c_void_p],
+    "hma_mar_timestep_embed": [c_void_p, c_ll, c_void_p, c_void_p],
+    "hma_mar_diff_loss_fwd": [c_fp, c_ll, c_fp, c_fp, c_void_p, c_fp, c_fp, c_ll, c_int, c_fp, c_fp, c_fp, c_void_p],
+    "hma_mar_diff_loss_bwd": [c_fp, c_ll, c_fp, c_fp, c_void_p, c_fp, c_fp, c_ll, c_int, c_fp, c_fp, c_void_p, c_ll, c_void_p],
+    "hma_mar_p_sample": [c_fp, c_ll, c_fp, c_fp, c_fp, c_int, c_ll, c_int, c_float, c_int, c_fp, c_void_p, c_int, c_void_p],
+    "hma_mar_gather_rows": [c_fp, c_void_p, c_ll, c_int, c_fp, c_void_p, c_void_p],
+    "hma_mar_scatter_rows": [c_fp, c_void_p, c_ll, c_int, c_fp, c_void_p],
+    "hma_dropout_bf16": [c_void_p, c_ll, c_float, c_u64, c_void_p],
+    "hma_dropout_add_f32": [c_fp, c_fp, c_fp, c_ll, c_float, c_u64, c_void_p],
+    "hma_dropout_cast_bf16": [c_fp, c_void_p, c_ll, c_float, c_u64, c_void_p],
 }
 _RESTYPES = {"hma_last_error": ctypes.c_char_p}
 

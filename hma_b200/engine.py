@@ -136,11 +136,15 @@ class Engine:
     """One engine per model; owns the bf16 weight cache."""
 
     def __init__(self, cfg):
-        check_config(cfg)
+        self.check(cfg)
         self.cfg = cfg
         self.weights = Weights()
         self._stem_w0: Dict[str, tuple] = {}
         self._side: Dict[int, torch.cuda.Stream] = {}
+
+    @staticmethod
+    def check(cfg) -> None:
+        check_config(cfg)
 
     def _side_stream(self, dev) -> "torch.cuda.Stream":
         idx = dev.index if dev.index is not None else torch.cuda.current_device()
@@ -221,7 +225,7 @@ class Engine:
 
     def forward(self, p: Dict[str, Tensor], ids: Tensor, actions: Optional[Tensor], dom: Optional[str], d: Dims,
                 training: bool, skip_normalization: bool = False, *, t0: int = 0, kv=None, mode: str = "full",
-                frame_cond=None):
+                frame_cond=None, front=None, head: bool = True, drop=None):
         """ids: i64 [B, T, S] (contiguous). Returns (logits fp32 [B*T*S, nv*vs], saved or None).
 
         Frame-incremental decode (inference only; `kv` = per-layer K/V cache tensors [Tmax, B*n, 512]):
@@ -231,7 +235,12 @@ class Engine:
           mode "commit" : as "step", but appends this frame's K/V to the cache and skips everything after
                           the last layer's temporal K/V (no logits).
         `frame_cond` (step/commit): precomputed (act fp32 [B,256] or None, mods fp32 [L,B,512] or None) of the frame,
-        replacing the action stem + adaLN chain. `actions`, if given, must hold exactly the T frames computed."""
+        replacing the action stem + adaLN chain. `actions`, if given, must hold exactly the T frames computed.
+
+        Other front ends / heads over the same trunk (STMAR, mar.py): `front(act)` returns the fp32 residual stream
+        [B*T*n, 256] in place of the token embedding (`ids` is then ignored); `head=False` returns the trunk output
+        instead of logits. `drop = (p, seed)`: nn.Dropout(p) after the GELU and after fc2 (st_transformer.py:24-27;
+        training only)."""
         assert mode in ("full", "prefill", "step", "commit")
         assert mode == "full" or (not training and kv is not None)
         W = self.weights
@@ -251,9 +260,15 @@ class Engine:
         pos_n = pos.shape[2]
         if t0:
             pos = pos[:, t0:]
-        E1 = p.get("token_embed.factored_embeds.1.weight") if d.nv == 2 else None
-        x = ops.embed_fwd(ids, p["token_embed.factored_embeds.0.weight"], E1, p["token_embed.mask_token_embed"],
-                          act if d.A else None, pos, pos_n, B, T, S, d.A, d.vs, d.mask_id)
+        if front is not None:
+            x = front(act if d.A else None)
+        else:
+            E1 = p.get("token_embed.factored_embeds.1.weight") if d.nv == 2 else None
+            x = ops.embed_fwd(ids, p["token_embed.factored_embeds.0.weight"], E1, p["token_embed.mask_token_embed"],
+                              act if d.A else None, pos, pos_n, B, T, S, d.A, d.vs, d.mask_id)
+        drop_p = drop[0] if (drop is not None and training) else 0.0
+        if drop_p > 0.0:
+            assert not self.cfg.mlp_bias, "mlp_drop > 0 together with mlp_bias=True is not implemented"
         # adaLN_modulation (Linear -> SiLU -> Linear on the [B*T, 256] action embedding) depends only on the
         # stem output: all layers' shift/scale are produced up-front on a side stream, where these
         # one-tile GEMMs fill the tails of the main stream's kernels instead of serialising with them.
@@ -328,8 +343,12 @@ class Engine:
                 a2, st2 = ops.ln_fwd(x3, 1, gamma=p[lp + "norm2.weight"], beta=p[lp + "norm2.bias"], eps=1e-5, want_stats=True)
             z = torch.empty(N, 1024, device=x.device, dtype=torch.bfloat16) if training else None
             h = ops.gemm_nt(a2, Wp[lp + "mlp.fc1.weight"], EPI_GELU, bias=p.get(lp + "mlp.fc1.bias"), out2=z)
-            x4 = ops.gemm_nt(h, Wp[lp + "mlp.fc2.weight"], EPI_RESID, bias=p.get(lp + "mlp.fc2.bias"), resid=x3,
-                             out=None if training else x3)
+            if drop_p > 0.0:
+                ops.dropout_bf16_(h, drop_p, drop[1] + 2 * i)
+                x4 = ops.dropout_add_f32(ops.gemm_nt(h, Wp[lp + "mlp.fc2.weight"], EPI_RESID), x3, drop_p, drop[1] + 2 * i + 1)
+            else:
+                x4 = ops.gemm_nt(h, Wp[lp + "mlp.fc2.weight"], EPI_RESID, bias=p.get(lp + "mlp.fc2.bias"), resid=x3,
+                                 out=None if training else x3)
             if training:
                 L.update(x0=x, a1=a1, st1=st1, qkv_s=qkv_s, att_s=att_s, lse=lse, x1=x1, at=at, qkv_t=qkv_t, att_t=att_t,
                          x3=x3, a2=a2, st2=st2, z=z, h=h, lse_t=lse_t, qkv_s_raw=qkv_s_raw, qkv_t_raw=qkv_t_raw)
@@ -339,15 +358,14 @@ class Engine:
         ah = ops.ln_fwd(x, 0, rows=M * S, src_group=n, dst_group=S) if d.A else ops.ln_fwd(x, 0)
         logits = ops.gemm_nt(ah, Wp["out_x_proj.weight"], EPI_RESID, bias=p["out_x_proj.bias"], alpha=d.readout_alpha)
         if training:
-            sv.update(layers=layers, ah=ah, ids=ids, dom=dom, dims=d, pos_n=pos_n, has_actions=actions is not None)
+            sv.update(layers=layers, ah=ah, ids=ids, dom=dom, dims=d, pos_n=pos_n, has_actions=actions is not None,
+                      drop=(drop_p, drop[1]) if drop_p > 0.0 else None)
         return logits, (sv if training else None)
 
     # ------------------------------------------------------------------------------------------
     def shared_param_names(self, p: Dict[str, Tensor], d: Dims) -> List[str]:
         """Parameters every batch touches (embeddings, trunk, head), in gradient-buffer order."""
-        names = ["pos_embed_TSC", "token_embed.mask_token_embed", "token_embed.factored_embeds.0.weight"]
-        if d.nv == 2:
-            names.append("token_embed.factored_embeds.1.weight")
+        names = self.front_param_names(p, d)
         for i in range(d.num_layers):
             lp = f"decoder.layers.{i}."
             for k in ("norm1.weight", "norm1.bias", "spatial_attn.qkv.weight", "spatial_attn.qkv.bias",
@@ -359,7 +377,16 @@ class Engine:
                 if lp + k in p:
                     names.append(lp + k)
         names += ["out_x_proj.weight", "out_x_proj.bias"]
+        return names + self.head_param_names(p, d)
+
+    def front_param_names(self, p: Dict[str, Tensor], d: Dims) -> List[str]:
+        names = ["pos_embed_TSC", "token_embed.mask_token_embed", "token_embed.factored_embeds.0.weight"]
+        if d.nv == 2:
+            names.append("token_embed.factored_embeds.1.weight")
         return names
+
+    def head_param_names(self, p: Dict[str, Tensor], d: Dims) -> List[str]:
+        return []
 
     def domain_param_names(self, p: Dict[str, Tensor], d: Dims, dom: Optional[str], has_actions: bool) -> List[str]:
         """Parameters only batches of domain `dom` touch (action stem + per-layer ModulateLayers)."""
@@ -382,15 +409,11 @@ class Engine:
     def padded_numel(t: Tensor) -> int:
         return (t.numel() + 3) // 4 * 4  # keep every tensor 16-byte aligned inside flat buffers
 
-    def backward(self, p: Dict[str, Tensor], sv: dict, dlogits: Tensor, flat: Optional[Tensor] = None) -> Dict[str, Tensor]:
-        """dlogits: bf16 [B*T*S, nv*vs]. Returns fp32 gradients for every active parameter, as views of one
-        flat buffer laid out [shared | domain] (`flat`, if given, must be zeroed and large enough)."""
-        d: Dims = sv["dims"]
-        dom = sv["dom"]
-        Wt = self.weights.trans
-        B, T, S, n, M, N = d.B, d.T, d.S, d.n, d.M, d.N
-        dev = dlogits.device
-        names = self.active_param_names(p, d, dom, sv["has_actions"])
+    def alloc_grads(self, p: Dict[str, Tensor], d: Dims, dom: Optional[str], has_actions: bool, dev,
+                    flat: Optional[Tensor] = None) -> Dict[str, Tensor]:
+        """fp32 gradients for every active parameter, as views of one flat buffer laid out [shared | domain]
+        (`flat`, if given, must be zeroed and large enough)."""
+        names = self.active_param_names(p, d, dom, has_actions)
         sizes = [p[k].numel() for k in names]
         padded = [self.padded_numel(p[k]) for k in names]
         if flat is None:
@@ -401,6 +424,20 @@ class Engine:
         for k, s, ps in zip(names, sizes, padded):
             g[k] = flat[off:off + s].view(p[k].shape)
             off += ps
+        return g
+
+    def backward(self, p: Dict[str, Tensor], sv: dict, dlogits: Tensor, flat: Optional[Tensor] = None, *,
+                 g: Optional[Dict[str, Tensor]] = None, front_bwd=None) -> Dict[str, Tensor]:
+        """dlogits: bf16 [B*T*S, nv*vs] (gradient of the out_x_proj output). Returns the gradient dict of alloc_grads
+        (`g`, if given, is used as is). `front_bwd(dx, dact)` replaces the token-embedding backward (mar.py)."""
+        d: Dims = sv["dims"]
+        dom = sv["dom"]
+        Wt = self.weights.trans
+        B, T, S, n, M, N = d.B, d.T, d.S, d.n, d.M, d.N
+        dev = dlogits.device
+        if g is None:
+            g = self.alloc_grads(p, d, dom, sv["has_actions"], dev, flat)
+        drop = sv.get("drop")
 
         def g2(name):  # gradient viewed as a matrix / vector
             return g[name]
@@ -426,10 +463,14 @@ class Engine:
             L = sv["layers"][i]
             lp = f"decoder.layers.{i}."
             # ---- MLP
-            if dy is None:
+            if drop is not None:  # x4 = x3 + drop(fc2(drop(gelu(z)))): the keep masks are regenerated from the seeds
+                dy = ops.dropout_cast_bf16(dx, drop[0], drop[1] + 2 * i + 1)
+            elif dy is None:
                 dy = ops.cast_colsum(dx, g.get(lp + "mlp.fc2.bias"))
             ops.gemm_wgrad(dy, L["h"], g2(lp + "mlp.fc2.weight"))
             dz = ops.gemm_nt(dy, Wt[lp + "mlp.fc2.weight"], EPI_DGELU, aux=L["z"], colsum=g.get(lp + "mlp.fc1.bias"))
+            if drop is not None:
+                ops.dropout_bf16_(dz, drop[0], drop[1] + 2 * i)
             ops.gemm_wgrad(dz, L["a2"], g2(lp + "mlp.fc1.weight"))
             da2 = ops.gemm_nt(dz, Wt[lp + "mlp.fc1.weight"], EPI_BF16)
             if qk:
@@ -499,9 +540,12 @@ class Engine:
             side_keep.clear()
 
         # ---- embedding / positional / action-token gradients
-        ops.embed_bwd(sv["ids"], dx, sv["pos_n"], B, T, S, d.A, d.vs, d.mask_id,
-                      g["token_embed.factored_embeds.0.weight"], g.get("token_embed.factored_embeds.1.weight"),
-                      g["token_embed.mask_token_embed"], dact if d.A else None, g["pos_embed_TSC"])
+        if front_bwd is not None:
+            front_bwd(dx, dact if d.A else None)
+        else:
+            ops.embed_bwd(sv["ids"], dx, sv["pos_n"], B, T, S, d.A, d.vs, d.mask_id,
+                          g["token_embed.factored_embeds.0.weight"], g.get("token_embed.factored_embeds.1.weight"),
+                          g["token_embed.mask_token_embed"], dact if d.A else None, g["pos_embed_TSC"])
         # ---- action stem backward
         if sv["has_actions"] and (d.A or d.modulate or d.additive):
             q = f"action_mlp.{dom}.model."

@@ -185,16 +185,23 @@ class STMaskGIT(nn.Module, PyTorchModelHubMixin):
         self.mask_token_id = config.image_vocab_size
         self.seq_len = config.S
         self.relevant_action_mask = None
-        self.token_embed = _FactorizedEmbedding(config)
-        self.out_x_proj = nn.Linear(config.d_model, config.factored_vocab_size * config.num_factored_vocabs)
-        _xavier(self.out_x_proj, 0.01) if config.use_mup else None
+        self._build_io(config)
         self.config = config
         self.action_mask_tokens = nn.Parameter(torch.zeros(1, config.T, 1, config.d_model))
-        self._engine = Engine(config)
+        self._engine = self._make_engine(config)
         self._sessions = {}
         self._lazy = None
         if (config.init_actions or config.use_actions) and config.action_domains is not None:
             self.init_action_projectors(config.action_domains, config.d_actions, config.action_stats, config.action_network)
+
+    def _build_io(self, config) -> None:
+        """Token embedding and readout (st_mask_git.py:184-192); STMAR replaces both (st_mar.py:56-66)."""
+        self.token_embed = _FactorizedEmbedding(config)
+        self.out_x_proj = nn.Linear(config.d_model, config.factored_vocab_size * config.num_factored_vocabs)
+        _xavier(self.out_x_proj, 0.01) if config.use_mup else None
+
+    def _make_engine(self, config) -> Engine:
+        return Engine(config)
 
     # ---------------------------------------------------------------- construction (st_mask_git.py:201-251)
     def init_action_projectors(self, domains, d_actions, action_stats, action_network: str = "mlp", use_diffusion: bool = False):
@@ -204,8 +211,7 @@ class STMaskGIT(nn.Module, PyTorchModelHubMixin):
         cfg.init_actions = True
         cfg.action_domains, cfg.d_actions, cfg.action_stats = list(domains), list(d_actions), action_stats
         cfg.action_network = action_network
-        from .engine import check_config
-        check_config(cfg)
+        self._engine.check(cfg)
         dev = self.pos_embed_TSC.device
         self.action_preprocessor = nn.ModuleDict()
         self.action_mlp = nn.ModuleDict()

@@ -329,3 +329,154 @@ def rank_remask(keys, unmasked_u8, samples, frame_view, n_mask: int, mask_id: in
     _call("rank_remask", B * S * 32.0, "hma_rank_remask", _p(keys), unmasked_u8.data_ptr(), samples.data_ptr(), frame_view.data_ptr(),
               frame_view.stride(0), B, S, n_mask, mask_id, out.data_ptr(), _s())
     return out
+
+
+# ----------------------------------------------------------------------------------------------
+# STMAR stages (csrc/mar.cu)
+# ----------------------------------------------------------------------------------------------
+def mar_embed_fwd(lat, mask_u8, mask_token, xp_in, We, act, pos, pos_n: int, B: int, T: int, H: int, W: int, Cv: int, p: int,
+                  A: int, fill_inplace: bool, want_xp: bool, want_rowmask: bool = False):
+    Sp, D = (H // p) * (W // p), Cv * p * p
+    dev = (lat if lat is not None else xp_in).device
+    u = torch.empty(B * T * (Sp + A), 256, device=dev, dtype=F32)
+    xp = torch.empty(B * T * Sp, D, device=dev, dtype=F32) if want_xp else None
+    rowmask = torch.empty(B * T * Sp, device=dev, dtype=F32) if want_rowmask else None
+    _call("mar_embed_fwd", u.numel() * 4.0, "hma_mar_embed_fwd", _p(lat), _p(mask_u8), _p(mask_token), _p(xp_in), We.data_ptr(),
+          _p(act), pos.data_ptr(), pos_n, B, T, H, W, Cv, p, A, int(fill_inplace), u.data_ptr(), _p(xp), _p(rowmask), _s())
+    return u, xp, rowmask
+
+
+def mar_embed_bwd(du, xp, mask_u8, We, pos_n: int, B: int, T: int, H: int, W: int, Cv: int, p: int, A: int, dWe, dmask_token,
+                  dact, dpos) -> None:
+    _call("mar_embed_bwd", du.numel() * 4.0, "hma_mar_embed_bwd", du.data_ptr(), xp.data_ptr(), _p(mask_u8), We.data_ptr(), pos_n,
+          B, T, H, W, Cv, p, A, dWe.data_ptr(), _p(dmask_token), _p(dact), dpos.data_ptr(), _s())
+
+
+def mar_ln_fwd(x: torch.Tensor, *, gamma=None, beta=None, eps: float = 1e-6, mod=None, shift_off: int = 0, scale_off: int = 0,
+               add=None, want32: bool = False, want16: bool = True, want_stats: bool = False):
+    """LayerNorm over the last dim (256 or 1024) of fp32 x, optional affine / bf16 modulation / additive row table."""
+    assert x.dtype == F32 and x.is_contiguous() and x.dim() == 2
+    rows, C = x.shape
+    y32 = torch.empty(rows, C, device=x.device, dtype=F32) if want32 else None
+    y16 = torch.empty(rows, C, device=x.device, dtype=BF16) if want16 else None
+    stats = torch.empty(rows, 2, device=x.device, dtype=F32) if want_stats else None
+    if add is not None:
+        assert add.dtype == F32 and add.is_contiguous() and add.shape[-1] == C
+    _call(f"mar_ln_fwd[{C}]", rows * C * 6.0, "hma_mar_ln_fwd", x.data_ptr(), rows, C, _p(gamma), _p(beta), float(eps), _p(mod),
+          mod.stride(0) if mod is not None else 0, shift_off, scale_off, _p(add),
+          add.numel() // C if add is not None else 0, _p(y32), _p(y16), _p(stats), _s())
+    return y32, y16, stats
+
+
+def mar_ln_bwd(x: torch.Tensor, stats: torch.Tensor, *, dy16=None, dy32=None, gamma=None, beta=None, mod=None, shift_off: int = 0,
+               scale_off: int = 0, dx32=None, accumulate: bool = False, want16: bool = False, dgamma=None, dbeta=None, dmod=None,
+               dadd=None):
+    rows, C = x.shape
+    dx16 = torch.empty(rows, C, device=x.device, dtype=BF16) if want16 else None
+    _call(f"mar_ln_bwd[{C}]", rows * C * 10.0, "hma_mar_ln_bwd", _p(dy16), _p(dy32), x.data_ptr(), stats.data_ptr(), rows, C,
+          _p(gamma), _p(beta), _p(mod), mod.stride(0) if mod is not None else 0, shift_off, scale_off, _p(dx32),
+          int(accumulate), _p(dx16), _p(dgamma), _p(dbeta), _p(dmod), dmod.stride(0) if dmod is not None else 0, _p(dadd),
+          dadd.numel() // C if dadd is not None else 0, _s())
+    return dx16
+
+
+def mar_gate_fwd(x: torch.Tensor, mod: torch.Tensor, gate_off: int, h2: torch.Tensor) -> torch.Tensor:
+    rows, C = x.shape
+    out = torch.empty_like(x)
+    _call("mar_gate_fwd", rows * C * 12.0, "hma_mar_gate_fwd", x.data_ptr(), mod.data_ptr(), mod.stride(0), gate_off, h2.data_ptr(),
+          rows, C, out.data_ptr(), _s())
+    return out
+
+
+def mar_gate_bwd(dx: torch.Tensor, mod: torch.Tensor, gate_off: int, h2: torch.Tensor, dmod: torch.Tensor) -> torch.Tensor:
+    rows, C = dx.shape
+    dh2 = torch.empty(rows, C, device=dx.device, dtype=BF16)
+    _call("mar_gate_bwd", rows * C * 12.0, "hma_mar_gate_bwd", dx.data_ptr(), mod.data_ptr(), mod.stride(0), gate_off,
+          h2.data_ptr(), rows, C, dh2.data_ptr(), dmod.data_ptr(), dmod.stride(0), _s())
+    return dh2
+
+
+def mar_silu_fwd(y: torch.Tensor, rowvec: Optional[torch.Tensor] = None) -> torch.Tensor:
+    rows, C = y.shape
+    out = torch.empty(rows, C, device=y.device, dtype=BF16)
+    _call("mar_silu_fwd", rows * C * 6.0, "hma_mar_silu_fwd", y.data_ptr(), _p(rowvec), rows, C, out.data_ptr(), _s())
+    return out
+
+
+def mar_silu_bwd(dsy: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+    dy = torch.empty(y.shape, device=y.device, dtype=BF16)
+    _call("mar_silu_bwd", y.numel() * 10.0, "hma_mar_silu_bwd", dsy.data_ptr(), y.data_ptr(), y.numel(), dy.data_ptr(), _s())
+    return dy
+
+
+def mar_q_sample(x0: torch.Tensor, noise, t, tables, kpad: int) -> torch.Tensor:
+    N, D = x0.shape
+    out = torch.empty(N, kpad, device=x0.device, dtype=BF16)
+    _call("small", 0.0, "hma_mar_q_sample", x0.data_ptr(), _p(noise), _p(t), _p(tables), N, D, kpad, out.data_ptr(), _s())
+    return out
+
+
+def mar_timestep_embed(t: torch.Tensor) -> torch.Tensor:
+    assert t.dtype == torch.int64 and t.is_contiguous()
+    out = torch.empty(t.numel(), 256, device=t.device, dtype=BF16)
+    _call("small", 0.0, "hma_mar_timestep_embed", t.data_ptr(), t.numel(), out.data_ptr(), _s())
+    return out
+
+
+def mar_diff_loss_fwd(out: torch.Tensor, x0, noise, t, mask, tables, D: int, want_rows: bool = False):
+    N = x0.shape[0]
+    sums = torch.zeros(2, device=x0.device, dtype=F32)
+    loss = torch.empty((), device=x0.device, dtype=F32)
+    rows = torch.empty(N, device=x0.device, dtype=F32) if want_rows else None
+    _call("mar_diff_loss_fwd", N * D * 16.0, "hma_mar_diff_loss_fwd", out.data_ptr(), out.stride(0), x0.data_ptr(), noise.data_ptr(),
+          t.data_ptr(), _p(mask), tables.data_ptr(), N, D, _p(rows), sums.data_ptr(), loss.data_ptr(), _s())
+    return loss, sums, rows
+
+
+def mar_diff_loss_bwd(out: torch.Tensor, x0, noise, t, mask, tables, D: int, sums, dloss, ldd: int) -> torch.Tensor:
+    N = x0.shape[0]
+    dout = torch.empty(N, ldd, device=x0.device, dtype=BF16)
+    _call("mar_diff_loss_bwd", N * D * 16.0, "hma_mar_diff_loss_bwd", out.data_ptr(), out.stride(0), x0.data_ptr(), noise.data_ptr(),
+          t.data_ptr(), _p(mask), tables.data_ptr(), N, D, sums.data_ptr(), _p(dloss), dout.data_ptr(), ldd, _s())
+    return dout
+
+
+def mar_p_sample(out: torch.Tensor, x: torch.Tensor, noise, tables, step: int, temperature: float, clip: bool, x_next: torch.Tensor,
+                 x16: Optional[torch.Tensor]) -> None:
+    N, D = x.shape
+    _call("small", 0.0, "hma_mar_p_sample", out.data_ptr(), out.stride(0), x.data_ptr(), _p(noise), tables.data_ptr(), step, N, D,
+          float(temperature), int(clip), x_next.data_ptr(), _p(x16), x16.shape[1] if x16 is not None else D, _s())
+
+
+def mar_gather_rows(src: torch.Tensor, idx: torch.Tensor, want32: bool, want16: bool):
+    assert src.dtype == F32 and src.is_contiguous() and idx.dtype == torch.int32
+    n, C = idx.numel(), src.shape[-1]
+    d32 = torch.empty(n, C, device=src.device, dtype=F32) if want32 else None
+    d16 = torch.empty(n, C, device=src.device, dtype=BF16) if want16 else None
+    _call("small", 0.0, "hma_mar_gather_rows", src.data_ptr(), idx.data_ptr(), n, C, _p(d32), _p(d16), _s())
+    return d32, d16
+
+
+def mar_scatter_rows(src: torch.Tensor, idx: torch.Tensor, dst: torch.Tensor) -> None:
+    assert src.dtype == F32 and dst.dtype == F32 and src.is_contiguous() and dst.is_contiguous() and idx.dtype == torch.int32
+    _call("small", 0.0, "hma_mar_scatter_rows", src.data_ptr(), idx.data_ptr(), idx.numel(), src.shape[-1], dst.data_ptr(), _s())
+
+
+def dropout_bf16_(x: torch.Tensor, p: float, seed: int) -> None:
+    assert x.dtype == BF16 and x.is_contiguous()
+    _call("dropout", x.numel() * 4.0, "hma_dropout_bf16", x.data_ptr(), x.numel(), float(p), seed, _s())
+
+
+def dropout_add_f32(a: torch.Tensor, resid: torch.Tensor, p: float, seed: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    assert a.dtype == F32 and resid.dtype == F32 and a.is_contiguous() and resid.is_contiguous()
+    if out is None:
+        out = torch.empty_like(resid)
+    _call("dropout", a.numel() * 12.0, "hma_dropout_add_f32", a.data_ptr(), resid.data_ptr(), out.data_ptr(), a.numel(), float(p), seed, _s())
+    return out
+
+
+def dropout_cast_bf16(a: torch.Tensor, p: float, seed: int) -> torch.Tensor:
+    assert a.dtype == F32 and a.is_contiguous()
+    out = torch.empty(a.shape, device=a.device, dtype=BF16)
+    _call("dropout", a.numel() * 6.0, "hma_dropout_cast_bf16", a.data_ptr(), out.data_ptr(), a.numel(), float(p), seed, _s())
+    return out
