@@ -56,6 +56,102 @@ def synthetic_batch(gen: torch.Generator, batch: int, d_action: int):
     return ids, labels, actions
 
 
+def mar_leg(dev, world: int, rank: int, sync_all, layers: int, steps: int = 6, warmup: int = 3):
+    """BASELINE.json configs[3]: HMA-MAR (hma/configs/mar_n32_h8_d256_action.json, 30 action domains, ~1 B parameters):
+    12 frames x 16x16 latents of 4 channels (64 patch tokens + 64 action tokens per frame), batch 8 per GPU.
+    (i) training step (forward, diffusion loss, backward, gradient exchange, clip, AdamW) fed from pinned host memory,
+    (ii) generate(): 6 prompt frames -> 2 new frames, maskgit_steps 16, 100-step ancestral sampler (the reference algorithm:
+    a full-window trunk pass per MaskGIT step). Device-event timed, max over ranks."""
+    import torch.distributed as dist
+    from hma_b200 import ops
+    from hma_b200.mar import STMAR, DiffusionGenieConfig, MarTrainStep
+
+    nd, Tm, Bm, Hh = 30, 12, 8, 16
+    domains = [f"dom{i:02d}" for i in range(nd)]
+    d_actions = [D_ACTION_CYCLE[i % 10] for i in range(nd)]
+    stats = [[[0.0] * a, [1.0] * a] for a in (ACTION_DIM_CYCLE[i % 10] for i in range(nd))]
+    cfg = DiffusionGenieConfig(num_layers=layers, num_heads=HEADS, d_model=D_MODEL, T=Tm, S=256, num_factored_vocabs=2,
+                               use_mup=False, qkv_bias=True, proj_bias=True, qk_norm=False, mlp_bias=False, mlp_drop=0.05,
+                               attn_drop=0.1, patch_size=2, action_network="concat+modulate")
+    torch.manual_seed(0)
+    with torch.device(dev):
+        model = STMAR(cfg)
+        model.init_action_projectors(domains, d_actions, stats, "concat+modulate")
+    n_params = sum(p.numel() for p in model.parameters())
+    step_fn = MarTrainStep(model, lr=2e-4, weight_decay=0.01, max_grad_norm=10.0, cuda_graphs=True)  # run_30datasets_mar_waction.sh
+    gen = torch.Generator().manual_seed(4321 + rank)
+    total = warmup + steps
+    host, sched = [], []
+    for i in range(total):
+        di = (rank + i) % 2  # two domains alternate (each needs one graph capture; training revisits them for ever)
+        lat = (torch.randn(Bm, Tm * Hh * Hh, 4, generator=gen) * 0.18215 * 5).pin_memory()
+        rate = torch.cos(math.pi / 2 * torch.rand(Bm, Tm, 1, 1, generator=gen))
+        rate[:, 0] = 0.0
+        mask = (torch.rand(Bm, Tm, Hh, Hh, generator=gen) < rate).pin_memory()
+        host.append((lat, mask, torch.randn(Bm, Tm, d_actions[di], generator=gen).pin_memory(), domains[di]))
+        sched.append([domains[(r + i) % 2] for r in range(world)])
+    for i in range(2):
+        lat, mask, act, dname = host[i]
+        step_fn.precapture(lat.to(dev), lat.to(dev), act.to(dev), [dname] * Bm, mask.to(dev))
+    sync_all()
+
+    def one(i):
+        lat, mask, act, dname = host[i]
+        x = lat.to(dev, non_blocking=True)
+        return step_fn(x, x.clone(), act.to(dev, non_blocking=True), [dname] * Bm, mask.to(dev, non_blocking=True),
+                       rank_domains=sched[i])
+
+    for i in range(warmup):
+        one(i)
+    sync_all()
+    n0 = ops.LAUNCHES
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(warmup, total):
+        loss = one(i).cpu()
+    e1.record()
+    sync_all()
+    ms_train = e0.elapsed_time(e1)
+    launches = ops.LAUNCHES - n0
+    # generation: 6 prompt frames -> 2 new ones
+    model.eval()
+    Tp, Tn = 6, 2
+    prompt = (torch.randn(Bm, Tp * Hh * Hh, 4, generator=gen) * 0.9).pin_memory()
+    acts = torch.randn(Bm, Tm, d_actions[0], generator=gen).pin_memory()
+
+    def gen_once():
+        return model.generate(prompt.to(dev, non_blocking=True), None, Tn * Hh * Hh, temperature=1.0,
+                              action_ids=acts.to(dev, non_blocking=True), domain=[domains[0]] * Bm, h=[Hh], w=[Hh]).cpu()
+
+    gen_once()  # captures the sampler graphs (one per MaskGIT-step row count)
+    sync_all()
+    e0.record()
+    out = gen_once()
+    e1.record()
+    sync_all()
+    ms_gen = e0.elapsed_time(e1)
+    times = torch.tensor([ms_train, ms_gen], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    ms_train, ms_gen = times.tolist()
+    del step_fn, model
+    torch.cuda.empty_cache()
+    return {
+        "workload": "HMA-MAR (mar_n32_h8_d256_action, 30 domains): 12 frames x 16x16x4 latents, patch 2 -> 64 + 64 action tokens "
+                    "per frame, batch 8/GPU, diffusion-MLP head (depth 4, width 1024), mlp_drop 0.05",
+        "layers": layers, "params": n_params,
+        "train": {"metric": "train_latent_tokens_per_s", "value": world * Bm * Tm * 256 * steps / (ms_train / 1e3), "unit": "tokens/s",
+                  "ms_per_step": ms_train / steps, "steps": steps, "warmup": warmup, "gpu_launches": launches,
+                  "loss": float(loss), "io": "latents/mask/actions from pinned host memory, loss read back, every step",
+                  "cuda_graph": "forward+loss+backward replayed per action domain; dropout seed on the device"},
+        "generate": {"metric": "mar_generated_frames_per_s", "value": world * Bm * Tn / (ms_gen / 1e3), "unit": "frames/s",
+                     "ms_per_generate_call": ms_gen, "batch_per_gpu": Bm, "prompt_frames": Tp, "new_frames": Tn,
+                     "maskgit_steps": 16, "num_sampling_steps": 100, "finite": bool(torch.isfinite(out).all()),
+                     "algorithm": "reference algorithm (full-window trunk pass per MaskGIT step); the 100-step ancestral "
+                                  "sampler of each step is one CUDA-graph replay"},
+    }
+
+
 class ClockSampler(threading.Thread):
     FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -186,6 +282,7 @@ def main() -> None:
     ap.add_argument("--breakdown", default=None, help="write a per-stage CUDA-event breakdown JSON here")
     ap.add_argument("--no-graphs", action="store_true", help="launch every kernel from the host instead of replaying CUDA graphs")
     ap.add_argument("--no-generation", action="store_true", help="skip the MaskGIT generation leg (BASELINE configs[2])")
+    ap.add_argument("--no-mar", action="store_true", help="skip the HMA-MAR leg (BASELINE configs[3])")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)
@@ -327,6 +424,15 @@ def main() -> None:
         with open(args.breakdown, "w") as f:
             json.dump({k: v for k, v in sorted(bd.items(), key=lambda kv: -kv[1]["total_ms"])}, f, indent=1)
 
+    # ---------------- HMA-MAR (continuous tokens + diffusion head): training step and sampling, BASELINE configs[3]
+    graphs_on = step_fn.cuda_graphs
+    mar = None
+    if not args.no_mar:
+        del step_fn, run_resident
+        model = None
+        torch.cuda.empty_cache()
+        mar = mar_leg(dev, world, rank, sync_all, args.layers)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -375,7 +481,7 @@ def main() -> None:
                    "loss": loss_val, "model_tflops_per_gpu": step_tf,
                    "cuda_graph": ("forward+loss+backward replayed from one CUDA graph per action domain (captured before the "
                                   "timed region); gradient exchange, clip and AdamW launched from the host")
-                   if step_fn.cuda_graphs else "off"},
+                   if graphs_on else "off"},
         "e2e": {"value": e2e, "unit": "tokens/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8,
                 "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": launches,
@@ -399,6 +505,8 @@ def main() -> None:
         if gen_strong is not None:
             line["generation"]["strong_scaling_total_batch_64"] = {"value": gen_strong[0], "unit": "frames/s",
                                                                     "ms_per_generate_call": gen_strong[1], "batch_per_gpu": gen_strong[2]}
+    if mar is not None:
+        line["mar"] = mar
     if not args.no_cpu_baseline and world == 1:
         tps, sec, threads = cpu_oracle_train_tokens_per_s(2, 1)
         line["cpu_baseline"] = {"value": tps, "unit": "tokens/s", "cores": threads, "kind": "port",

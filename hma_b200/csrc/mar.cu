@@ -643,8 +643,9 @@ __device__ __forceinline__ bool drop_keep(unsigned long long seed, long long i, 
 // mode 0: x16 in place; 1: out32 = resid + drop(a32); 2: out16 = bf16(drop(a32))
 __global__ void __launch_bounds__(256) dropout_kernel(int mode, __nv_bfloat16* x16, const float* a32, const float* resid,
                                                       float* out32, long long count, uint32_t thresh, float keep_scale,
-                                                      unsigned long long seed) {
+                                                      unsigned long long seed, const unsigned long long* seed_dev) {
   pdl_wait();
+  if (seed_dev != nullptr) seed += *seed_dev * 0xD1342543DE82EF95ull;  // per-step seed that a CUDA-graph replay can change
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (long long)gridDim.x * blockDim.x) {
     const float k = drop_keep(seed, i, thresh) ? keep_scale : 0.f;
     if (mode == 0) {
@@ -858,24 +859,25 @@ extern "C" int hma_mar_scatter_rows(const float* src, const int* idx, long long 
 }
 
 static int launch_dropout(int mode, void* x16, const float* a32, const float* resid, float* out32, long long count, float p,
-                          unsigned long long seed, cudaStream_t stream) {
+                          unsigned long long seed, const unsigned long long* seed_dev, cudaStream_t stream) {
   if (count == 0) return 0;
   HMA_REQUIRE(p >= 0.f && p < 1.f, "dropout: p=%f out of range", p);
   const uint32_t thresh = (uint32_t)fmin(4294967295.0, (double)p * 4294967296.0);
   HMA_CHECK_CUDA(hma_host::launch_pdl(dropout_kernel, dim3(grid_for(count, 256)), dim3(256), 0, stream, mode,
                                       static_cast<__nv_bfloat16*>(x16), a32, resid, out32, count, thresh, 1.f / (1.f - p),
-                                      seed));
+                                      seed, seed_dev));
   return 0;
 }
 
-extern "C" int hma_dropout_bf16(void* x, long long count, float p, unsigned long long seed, void* stream_) {
-  return launch_dropout(0, x, nullptr, nullptr, nullptr, count, p, seed, STREAM);
+extern "C" int hma_dropout_bf16(void* x, long long count, float p, unsigned long long seed,
+                                const unsigned long long* seed_dev, void* stream_) {
+  return launch_dropout(0, x, nullptr, nullptr, nullptr, count, p, seed, seed_dev, STREAM);
 }
 extern "C" int hma_dropout_add_f32(const float* a, const float* resid, float* out, long long count, float p,
-                                   unsigned long long seed, void* stream_) {
-  return launch_dropout(1, nullptr, a, resid, out, count, p, seed, STREAM);
+                                   unsigned long long seed, const unsigned long long* seed_dev, void* stream_) {
+  return launch_dropout(1, nullptr, a, resid, out, count, p, seed, seed_dev, STREAM);
 }
 extern "C" int hma_dropout_cast_bf16(const float* a, void* out16, long long count, float p, unsigned long long seed,
-                                     void* stream_) {
-  return launch_dropout(2, out16, a, nullptr, nullptr, count, p, seed, STREAM);
+                                     const unsigned long long* seed_dev, void* stream_) {
+  return launch_dropout(2, out16, a, nullptr, nullptr, count, p, seed, seed_dev, STREAM);
 }

@@ -239,8 +239,8 @@ class Engine:
 
         Other front ends / heads over the same trunk (STMAR, mar.py): `front(act)` returns the fp32 residual stream
         [B*T*n, 256] in place of the token embedding (`ids` is then ignored); `head=False` returns the trunk output
-        instead of logits. `drop = (p, seed)`: nn.Dropout(p) after the GELU and after fc2 (st_transformer.py:24-27;
-        training only)."""
+        instead of logits. `drop = (p, seed, seed_dev)`: nn.Dropout(p) after the GELU and after fc2
+        (st_transformer.py:24-27; training only); seed_dev is an optional device u64 mixed into the seed at run time."""
         assert mode in ("full", "prefill", "step", "commit")
         assert mode == "full" or (not training and kv is not None)
         W = self.weights
@@ -344,8 +344,9 @@ class Engine:
             z = torch.empty(N, 1024, device=x.device, dtype=torch.bfloat16) if training else None
             h = ops.gemm_nt(a2, Wp[lp + "mlp.fc1.weight"], EPI_GELU, bias=p.get(lp + "mlp.fc1.bias"), out2=z)
             if drop_p > 0.0:
-                ops.dropout_bf16_(h, drop_p, drop[1] + 2 * i)
-                x4 = ops.dropout_add_f32(ops.gemm_nt(h, Wp[lp + "mlp.fc2.weight"], EPI_RESID), x3, drop_p, drop[1] + 2 * i + 1)
+                ops.dropout_bf16_(h, drop_p, drop[1] + 2 * i, drop[2])
+                x4 = ops.dropout_add_f32(ops.gemm_nt(h, Wp[lp + "mlp.fc2.weight"], EPI_RESID), x3, drop_p, drop[1] + 2 * i + 1,
+                                         seed_dev=drop[2])
             else:
                 x4 = ops.gemm_nt(h, Wp[lp + "mlp.fc2.weight"], EPI_RESID, bias=p.get(lp + "mlp.fc2.bias"), resid=x3,
                                  out=None if training else x3)
@@ -359,7 +360,7 @@ class Engine:
         logits = ops.gemm_nt(ah, Wp["out_x_proj.weight"], EPI_RESID, bias=p["out_x_proj.bias"], alpha=d.readout_alpha)
         if training:
             sv.update(layers=layers, ah=ah, ids=ids, dom=dom, dims=d, pos_n=pos_n, has_actions=actions is not None,
-                      drop=(drop_p, drop[1]) if drop_p > 0.0 else None)
+                      drop=(drop_p, drop[1], drop[2]) if drop_p > 0.0 else None)
         return logits, (sv if training else None)
 
     # ------------------------------------------------------------------------------------------
@@ -464,13 +465,13 @@ class Engine:
             lp = f"decoder.layers.{i}."
             # ---- MLP
             if drop is not None:  # x4 = x3 + drop(fc2(drop(gelu(z)))): the keep masks are regenerated from the seeds
-                dy = ops.dropout_cast_bf16(dx, drop[0], drop[1] + 2 * i + 1)
+                dy = ops.dropout_cast_bf16(dx, drop[0], drop[1] + 2 * i + 1, drop[2])
             elif dy is None:
                 dy = ops.cast_colsum(dx, g.get(lp + "mlp.fc2.bias"))
             ops.gemm_wgrad(dy, L["h"], g2(lp + "mlp.fc2.weight"))
             dz = ops.gemm_nt(dy, Wt[lp + "mlp.fc2.weight"], EPI_DGELU, aux=L["z"], colsum=g.get(lp + "mlp.fc1.bias"))
             if drop is not None:
-                ops.dropout_bf16_(dz, drop[0], drop[1] + 2 * i)
+                ops.dropout_bf16_(dz, drop[0], drop[1] + 2 * i, drop[2])
             ops.gemm_wgrad(dz, L["a2"], g2(lp + "mlp.fc1.weight"))
             da2 = ops.gemm_nt(dz, Wt[lp + "mlp.fc1.weight"], EPI_BF16)
             if qk:

@@ -417,20 +417,30 @@ class MarEngine(Engine):
         h = ops.gemm_nt(temb, Wp[n + "time_embed.mlp.0.weight"], EPI_SILU, bias=p[n + "time_embed.mlp.0.bias"])
         return ops.gemm_nt(h, Wp[n + "time_embed.mlp.2.weight"], EPI_RESID, bias=p[n + "time_embed.mlp.2.bias"])
 
+    def sample_cond(self, p, z16: Tensor) -> Tensor:
+        """cond_embed(z) (diffloss.py:223), constant over the diffusion steps: fp32 [n, w]."""
+        n = self.NET
+        return ops.gemm_nt(z16, self.weights.plain[n + "cond_embed.weight"], EPI_RESID, bias=p[n + "cond_embed.bias"])
+
+    def sample_step(self, p, c: Tensor, te_tab: Tensor, tb: Tensor, i: int, x: Tensor, x16: Tensor, noise_i: Tensor,
+                    temperature: float, clip: bool, x_next: Tensor, x16_next: Tensor) -> None:
+        """p_sample at spaced step i (gaussian_diffusion.py:358-392): network on (x, timestep_map[i], z), then the
+        ancestral update into x_next / x16_next."""
+        sy = ops.mar_silu_fwd(c, te_tab[i])
+        out = self._mlp(p, x16, sy, None)
+        ops.mar_p_sample(out, x, noise_i, tb, i, temperature, clip, x_next, x16_next)
+
     def sample(self, p, z16: Tensor, x_init: Tensor, noise: Tensor, te_tab: Tensor, respacing: str, temperature: float,
                clip: bool) -> Tensor:
         """p_sample_loop for every row. x_init fp32 [n, D]; noise fp32 [steps, n, D] (noise[i] is the draw used at spaced
         step i). Returns fp32 [n, D]."""
-        n, Wp = self.NET, self.weights.plain
         tb, _, steps = self.tables(respacing, z16.device)
-        c = ops.gemm_nt(z16, Wp[n + "cond_embed.weight"], EPI_RESID, bias=p[n + "cond_embed.bias"])
+        c = self.sample_cond(p, z16)
         x = x_init.contiguous()
         x16 = ops.mar_q_sample(x, None, None, None, KPAD)
         nxt, nxt16 = torch.empty_like(x), torch.empty_like(x16)
         for i in reversed(range(steps)):
-            sy = ops.mar_silu_fwd(c, te_tab[i])
-            out = self._mlp(p, x16, sy, None)
-            ops.mar_p_sample(out, x, noise[i], tb, i, temperature, clip, nxt, nxt16)
+            self.sample_step(p, c, te_tab, tb, i, x, x16, noise[i], temperature, clip, nxt, nxt16)
             x, nxt = nxt, x
             x16, nxt16 = nxt16, x16
         return x
@@ -468,6 +478,18 @@ class _MarForwardLoss(torch.autograd.Function):
 # ------------------------------------------------------------------------------------------------
 # model
 # ------------------------------------------------------------------------------------------------
+def _mar_fwd_bwd(eng: MarEngine, p, lat, mask_u8, tgt, actions, dom, d: Dims, H: int, W: int, t, noise, drop, dloss, dev,
+                 flat: Optional[Tensor] = None):
+    """Forward, diffusion loss and the whole backward. Returns (loss, z32, gradient dict)."""
+    eng.prepare_diffloss(p, True)
+    z32, z16, rowmask, sv = eng.latents(p, lat, mask_u8, None, actions, dom, d, H, W, True, drop=drop, fill_inplace=True)
+    loss, dsv = eng.diffloss_forward(p, z16, tgt, rowmask, t, noise, True)
+    g = eng.alloc_grads(p, d, dom, actions is not None, dev, flat)
+    dz = eng.diffloss_backward(p, dsv, dloss, g)
+    eng.latents_backward(p, sv, dz, g)
+    return loss, z32, g
+
+
 class STMAR(STMaskGIT):
     """Spatial-time MAR (st_mar.py:38). See the module docstring."""
 
@@ -590,7 +612,7 @@ class STMAR(STMaskGIT):
         t, noise = self._train_draws(tgt, kwargs.get("_t"), kwargs.get("_noise"))
         drop = None
         if self.training and cfg.mlp_drop > 0.0:
-            drop = (float(cfg.mlp_drop), int(torch.randint(0, 2 ** 62, ()).item()))
+            drop = (float(cfg.mlp_drop), int(torch.randint(0, 2 ** 62, ()).item()), None)
         if torch.is_grad_enabled():
             named = list(self.named_parameters())
             names = [k for k, _ in named]
@@ -750,3 +772,84 @@ class STMAR(STMaskGIT):
         if return_logits:
             return out, torch.stack(all_latents, dim=3)
         return out
+
+
+# ------------------------------------------------------------------------------------------------
+# training step without autograd in the loop (the STMAR counterpart of train.TrainStep)
+# ------------------------------------------------------------------------------------------------
+from .train import TrainStep  # noqa: E402
+
+
+class MarTrainStep(TrainStep):
+    """One optimisation step of STMAR (train_multi.py:556-598 with the continuous model): forward + diffusion loss +
+    backward into the flat gradient buffer, then the shared gradient exchange / clip / AdamW tail of TrainStep.
+    With cuda_graphs=True the forward+loss+backward of a (domain, shape) is replayed from static buffers; the dropout
+    keep masks change per replay through a device-side seed."""
+
+    def __init__(self, model: STMAR, **kw):
+        super().__init__(model, **kw)
+        self._seed_dev = torch.zeros(1, device=self.arena.flat.device, dtype=torch.int64)
+
+    def _eager(self, p, lat, mask_u8, tgt, actions, dom, d, H, W, t, noise):
+        cfg = self.model.config
+        drop = (float(cfg.mlp_drop), 0x5EED, self._seed_dev) if cfg.mlp_drop > 0.0 else None
+        self.grad.zero_()
+        loss, _, _ = _mar_fwd_bwd(self.engine, p, lat, mask_u8, tgt, actions, dom, d, H, W, t, noise, drop, None,
+                                  lat.device, flat=self.grad)
+        return loss
+
+    def precapture(self, *a, **kw):
+        self.__call__(*a, _apply=False, **kw)
+        self.__call__(*a, _apply=False, **kw)
+
+    def __call__(self, input_ids: Tensor, labels: Tensor, action_ids: Optional[Tensor], domain, masked_tokens_indicator: Tensor,
+                 h: Optional[int] = None, w: Optional[int] = None, rank_domains=None, _t=None, _noise=None, _apply: bool = True):
+        model, eng, cfg = self.model, self.engine, self.model.config
+        B, T = input_ids.shape[0], cfg.T
+        H, W = (h or model.h), (w or model.w)
+        lat = input_ids.view(B, T, H, W, -1)
+        mask_u8 = masked_tokens_indicator.reshape(B, T, H, W).to(torch.uint8).contiguous()
+        tgt = model.patchify(labels.reshape(B, T, H, W, -1).to(torch.float32)).reshape(B * T * model.seq_len_for(H, W), -1).contiguous()
+        dom = model._domain0(domain, action_ids)
+        if action_ids is not None:
+            action_ids = action_ids[:, :T].to(torch.float32).contiguous()
+        d = eng.mar_dims(B, T, H, W, action_ids is not None)
+        t, noise = model._train_draws(tgt, _t, _noise)
+        self._seed_dev.random_()  # new dropout masks every step
+        p = self._params()
+        if not self.cuda_graphs:
+            loss = self._eager(p, lat, mask_u8, tgt, action_ids, dom, d, H, W, t, noise)
+        else:
+            key = (dom, B, T, H, W, None if action_ids is None else tuple(action_ids.shape[1:]))
+            rec = self._graphs.get(key)
+            if rec is None and key not in self._warm:
+                self._warm.add(key)
+                loss = self._eager(p, lat, mask_u8, tgt, action_ids, dom, d, H, W, t, noise)
+            else:
+                if rec is None:
+                    rec = dict(lat=lat.clone(), mask=mask_u8.clone(), tgt=tgt.clone(), t=t.clone(), noise=noise.clone(),
+                               actions=None if action_ids is None else action_ids.clone())
+                    torch.cuda.synchronize()
+                    graph = torch.cuda.CUDAGraph()
+                    if self._pool is None:
+                        self._pool = torch.cuda.graph_pool_handle()
+                    n0 = ops.LAUNCHES
+                    with torch.cuda.graph(graph, pool=self._pool):
+                        rec["out"] = self._eager(p, rec["lat"], rec["mask"], rec["tgt"], rec["actions"], dom, d, H, W, rec["t"],
+                                                 rec["noise"])
+                    rec["launches"] = ops.LAUNCHES - n0
+                    ops.LAUNCHES = n0
+                    rec["graph"] = graph
+                    self._graphs[key] = rec
+                else:
+                    for name, src in (("lat", lat), ("mask", mask_u8), ("tgt", tgt), ("t", t), ("noise", noise)):
+                        rec[name].copy_(src)
+                    if action_ids is not None:
+                        rec["actions"].copy_(action_ids)
+                rec["graph"].replay()
+                ops.LAUNCHES += rec["launches"]
+                loss = rec["out"]
+        if _apply:
+            self._apply(dom, rank_domains)
+            eng._pad.pop("ver", None)
+        return loss

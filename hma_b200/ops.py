@@ -462,21 +462,22 @@ def mar_scatter_rows(src: torch.Tensor, idx: torch.Tensor, dst: torch.Tensor) ->
     _call("small", 0.0, "hma_mar_scatter_rows", src.data_ptr(), idx.data_ptr(), idx.numel(), src.shape[-1], dst.data_ptr(), _s())
 
 
-def dropout_bf16_(x: torch.Tensor, p: float, seed: int) -> None:
+def dropout_bf16_(x: torch.Tensor, p: float, seed: int, seed_dev: Optional[torch.Tensor] = None) -> None:
     assert x.dtype == BF16 and x.is_contiguous()
-    _call("dropout", x.numel() * 4.0, "hma_dropout_bf16", x.data_ptr(), x.numel(), float(p), seed, _s())
+    _call("dropout", x.numel() * 4.0, "hma_dropout_bf16", x.data_ptr(), x.numel(), float(p), seed, _p(seed_dev), _s())
 
 
-def dropout_add_f32(a: torch.Tensor, resid: torch.Tensor, p: float, seed: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+def dropout_add_f32(a: torch.Tensor, resid: torch.Tensor, p: float, seed: int, out: Optional[torch.Tensor] = None,
+                    seed_dev: Optional[torch.Tensor] = None) -> torch.Tensor:
     assert a.dtype == F32 and resid.dtype == F32 and a.is_contiguous() and resid.is_contiguous()
     if out is None:
         out = torch.empty_like(resid)
-    _call("dropout", a.numel() * 12.0, "hma_dropout_add_f32", a.data_ptr(), resid.data_ptr(), out.data_ptr(), a.numel(), float(p), seed, _s())
+    _call("dropout", a.numel() * 12.0, "hma_dropout_add_f32", a.data_ptr(), resid.data_ptr(), out.data_ptr(), a.numel(), float(p), seed, _p(seed_dev), _s())
     return out
 
 
-def dropout_cast_bf16(a: torch.Tensor, p: float, seed: int) -> torch.Tensor:
+def dropout_cast_bf16(a: torch.Tensor, p: float, seed: int, seed_dev: Optional[torch.Tensor] = None) -> torch.Tensor:
     assert a.dtype == F32 and a.is_contiguous()
     out = torch.empty(a.shape, device=a.device, dtype=BF16)
-    _call("dropout", a.numel() * 6.0, "hma_dropout_cast_bf16", a.data_ptr(), out.data_ptr(), a.numel(), float(p), seed, _s())
+    _call("dropout", a.numel() * 6.0, "hma_dropout_cast_bf16", a.data_ptr(), out.data_ptr(), a.numel(), float(p), seed, _p(seed_dev), _s())
     return out

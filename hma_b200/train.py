@@ -206,6 +206,12 @@ class TrainStep:
         d = eng.dims(B, T, S, action_ids is not None)
         p = self._params()
         loss_acc = self._fwd_bwd(p, ids, labels, action_ids, dom, d)
+        self._apply(dom, rank_domains)
+        return loss_acc
+
+    def _apply(self, dom: Optional[str], rank_domains: Optional[Sequence[str]] = None) -> None:
+        """Gradient exchange, global-norm clip and AdamW on self.grad = [shared | domain block of `dom`]."""
+        eng = self.engine
         self.step_count += 1
         shared = self.arena.shared_size
         dom_lo, dom_n = self.arena.dom_range.get(dom, (0, 0)) if dom is not None else (0, 0)
@@ -236,4 +242,3 @@ class TrainStep:
         # parameters changed underneath torch's version counters: drop the cached bf16 inference copies
         eng.weights._versions.clear()
         eng._stem_w0.clear()
-        return loss_acc

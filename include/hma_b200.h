@@ -270,11 +270,14 @@ int hma_mar_p_sample(const float* out, long long ldo, const float* x, const floa
 int hma_mar_gather_rows(const float* src, const int* idx, long long n, int C, float* dst32, void* dst16, void* stream);
 int hma_mar_scatter_rows(const float* src, const int* idx, long long n, int C, float* dst, void* stream);
 /* nn.Dropout(p) with a counter-based generator keyed by (seed, element index): the backward regenerates the same keep
- * mask from the same seed (st_transformer.py:24-27). In place on bf16; out = resid + drop(a); out16 = bf16(drop(a)). */
-int hma_dropout_bf16(void* x, long long count, float p, unsigned long long seed, void* stream);
+ * mask from the same seed (st_transformer.py:24-27). seed_dev (optional, DEVICE u64) is mixed into the seed at run time,
+ * so a captured CUDA graph draws a new mask per replay. In place on bf16; out = resid + drop(a); out16 = bf16(drop(a)). */
+int hma_dropout_bf16(void* x, long long count, float p, unsigned long long seed, const unsigned long long* seed_dev,
+                     void* stream);
 int hma_dropout_add_f32(const float* a, const float* resid, float* out, long long count, float p, unsigned long long seed,
-                        void* stream);
-int hma_dropout_cast_bf16(const float* a, void* out16, long long count, float p, unsigned long long seed, void* stream);
+                        const unsigned long long* seed_dev, void* stream);
+int hma_dropout_cast_bf16(const float* a, void* out16, long long count, float p, unsigned long long seed,
+                          const unsigned long long* seed_dev, void* stream);
 
 /* Test-only: single-CTA tcgen05 descriptor probe (see csrc/probe.cu; params is a HOST int[18]). */
 int hma_umma_probe(const void* A, long long lda, const void* B, long long ldb, const int* params, float* out,

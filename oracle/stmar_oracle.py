@@ -264,9 +264,11 @@ def forward(input_ids: Tensor, labels: Tensor, masked_tokens_indicator: Tensor, 
 # sampling (diffloss.py:37-59; gaussian_diffusion.py:237-314,358-392,443-490)
 # --------------------------------------------------------------------------------------------
 def p_sample_loop(z: Tensor, x: Tensor, step_noise: Callable[[int], Tensor], sd: SD, cfg: MarConfig, tb: Tables,
-                  temperature: float = 1.0, clip_denoised: bool = True, prefix: str = "diffloss.net.") -> Tensor:
+                  temperature: float = 1.0, clip_denoised: bool = True, prefix: str = "diffloss.net.",
+                  trace: Optional[list] = None) -> Tensor:
     """x: initial noise [N, C]; step_noise(i) returns the randn_like(x) drawn at spaced step i (drawn for every step,
-    also i == 0 where it is multiplied by zero, gaussian_diffusion.py:386-387)."""
+    also i == 0 where it is multiplied by zero, gaussian_diffusion.py:386-387). `trace`, if given, receives
+    (i, x_t, noise_i, x_{t-1}) per step (for step-wise, teacher-forced comparisons)."""
     N, Cc = x.shape
     for i in reversed(range(tb.num_timesteps)):
         t = torch.full((N,), i, dtype=torch.long)
@@ -279,7 +281,10 @@ def p_sample_loop(z: Tensor, x: Tensor, step_noise: Callable[[int], Tensor], sd:
             px0 = px0.clamp(-10, 10)  # gaussian_diffusion.py:296-298
         mean = _ex(tb.coef1, t) * px0 + _ex(tb.coef2, t) * x
         nz = step_noise(i)
+        x_prev = x
         x = mean + (0.0 if i == 0 else 1.0) * torch.exp(0.5 * lv) * nz * temperature
+        if trace is not None:
+            trace.append((i, x_prev, nz, x))
     return x
 
 
