@@ -96,6 +96,8 @@ _SIGNATURES = {
     "hma_mar_p_sample": [c_fp, c_ll, c_fp, c_fp, c_fp, c_int, c_ll, c_int, c_float, c_int, c_fp, c_void_p, c_int, c_void_p],
     "hma_mar_gather_rows": [c_fp, c_void_p, c_ll, c_int, c_fp, c_void_p, c_void_p],
     "hma_mar_scatter_rows": [c_fp, c_void_p, c_ll, c_int, c_fp, c_void_p],
+    "hma_gather_token_windows": [c_void_p, c_int, c_ll, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p],
+    "hma_gather_rows_f32": [c_fp, c_ll, c_ll, c_void_p, c_int, c_ll, c_fp, c_void_p],
     "hma_dropout_bf16": [c_void_p, c_ll, c_float, c_u64, c_void_p, c_void_p],
     "hma_dropout_add_f32": [c_fp, c_fp, c_fp, c_ll, c_float, c_u64, c_void_p, c_void_p],
     "hma_dropout_cast_bf16": [c_fp, c_void_p, c_ll, c_float, c_u64, c_void_p, c_void_p],

@@ -1,0 +1,153 @@
+"""RawTokenDataset: the reference's memmap token dataset (hma/data.py:159-294) with a device-resident fast path.
+
+On-disk format (written by datasets/encode_openx_dataset.py:340-388): `metadata.json` (num_images, h, w, token_dtype,
+action_dim, hz, name, ...), `video.bin` (token_dtype [num_images, h, w]), `segment_ids.bin` (int32 [num_images]),
+`actions/*.bin` (float32 [num_images, action_dim] each, concatenated along the last axis).
+
+Same constructor arguments, `valid_start_inds`, `__len__`, `__getitem__` dict (CPU tensors) and `action_stat` as the
+reference, so it can stand behind a torch DataLoader unchanged. The B200 path is `to_device()` + `gather(indices)`: the
+token and action tables are uploaded once (a 1 M-frame dataset is 1 GB of the 180 GB), and a batch is one index gather
+on the device (csrc/dataset.cu) that feeds the on-device collator (hma_b200/data.py) — no per-sample host work, no
+dataloader workers.
+
+Stride: the reference looks the dataset name up in DATA_FREQ_TABLE (datasets/encode_openx_dataset.py:51-108) and uses
+max(hz // natural_hz, 1). The writer stores that same table entry in metadata.json as "hz" (:374), so it is read from
+there; pass `freq_table` to override (e.g. when `name` differs from the directory's own name).
+"""
+from __future__ import annotations
+
+import json
+import os
+from pathlib import Path
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib, ops
+
+
+def normalize_actions(actions: np.ndarray):
+    """data.py:18-24: statistics only; the normalisation itself happens inside the network (ActionStat)."""
+    return actions, [np.mean(actions, axis=0).tolist(), np.std(actions, axis=0).tolist()]
+
+
+class RawTokenDataset(torch.utils.data.Dataset):
+    def __init__(self, data_dir, window_size, stride=1, filter_interrupts=True, filter_overlaps=False, use_actions=False, name="",
+                 max_traj_num=1000000, compute_stride_from_freq_table=True, natural_hz=2, drop_action_ratio=0.0,
+                 freq_table: Optional[Dict[str, int]] = None):
+        data_dir = Path(data_dir)
+        with open(data_dir / "metadata.json") as f:
+            self.metadata = json.load(f)
+        n_img = self.metadata["num_images"]
+        shape = (n_img, self.metadata["h"], self.metadata["w"])
+        token_dtype = np.dtype(self.metadata.get("token_dtype", "uint32"))
+        self.data = np.memmap(data_dir / "video.bin", dtype=token_dtype, mode="r", shape=shape)
+        self.window_size, self.stride = window_size, stride
+        self.name = name if len(name) else self.metadata["name"]
+        if compute_stride_from_freq_table:
+            if freq_table is not None:
+                hz = freq_table.get(self.name, 1)
+            else:
+                hz = self.metadata.get("hz", 1) if self.name == self.metadata.get("name", self.name) else 1
+            self.stride = max(hz // natural_hz, 1)
+        self.n_action = self.metadata.get("action_dim", 1) * self.stride
+        self.drop_action_ratio = drop_action_ratio
+        if use_actions:
+            parts = [np.memmap(fn, dtype=np.float32, mode="r").reshape(len(self.data), -1)
+                     for fn in sorted((data_dir / "actions").iterdir())]
+            self.actions, self.action_stat = normalize_actions(np.concatenate(parts, axis=-1))
+        seg_path = data_dir / "segment_ids.bin"
+        if os.path.isfile(seg_path):
+            self.segment_ids = np.memmap(seg_path, dtype=np.int32, mode="r", shape=(n_img,))
+        else:
+            self.segment_ids = None
+            if filter_interrupts:
+                raise NotImplementedError("Cannot filter interrupted sequences without segment ids.")
+        self.video_len = (self.window_size - 1) * self.stride
+        self.valid_start_inds = self._valid_starts(filter_interrupts, max_traj_num)
+        if filter_overlaps:
+            self.valid_start_inds = self._drop_overlaps(self.valid_start_inds)
+        self.num_videos = len(np.unique(self.valid_start_inds))
+        self._dev: Optional[dict] = None
+
+    # ------------------------------------------------------------------ data.py:235-244, vectorised
+    def _valid_starts(self, filter_interrupts: bool, max_traj_num: int) -> List[int]:
+        n = max(len(self.data) - self.video_len - self.stride, 0)
+        seg = None if self.segment_ids is None else np.asarray(self.segment_ids)
+        if seg is not None and n:
+            # the reference loop stops AFTER processing the first start whose segment id reaches max_traj_num
+            over = np.nonzero(seg[:n] >= max_traj_num)[0]
+            if len(over):
+                n = int(over[0]) + 1
+        starts = np.arange(n)
+        if filter_interrupts and n:
+            starts = starts[seg[:n] == seg[self.video_len: self.video_len + n]]
+        return starts.tolist()
+
+    def _drop_overlaps(self, starts: Sequence[int]) -> List[int]:
+        """data.py:246-260: greedy in order; a start is dropped if an already kept start lies exactly i*stride before it
+        (i < window_size), looking only at the last window_size*stride kept starts, as the reference does."""
+        kept: List[int] = []
+        for s in starts:
+            clash = {s - i * self.stride for i in range(1, self.window_size)}
+            if not any(k in clash for k in kept[-self.window_size * self.stride:]):
+                kept.append(s)
+        return kept
+
+    def __len__(self):
+        return len(self.valid_start_inds)
+
+    # ------------------------------------------------------------------ data.py:265-294 (host path, CPU tensors)
+    def __getitem__(self, idx):
+        start = self.valid_start_inds[idx]
+        x = torch.from_numpy(self.data[start: start + self.video_len + 1: self.stride].astype(np.int64)).flatten()
+        out = {"input_ids": x, "labels": x, "attention_mask": torch.ones_like(x), "h": self.metadata["h"], "w": self.metadata["w"]}
+        if hasattr(self, "actions") and np.random.uniform() > self.drop_action_ratio:
+            a = self.actions[start: start + self.video_len + self.stride].reshape(self.window_size, -1)
+            out["action_ids"] = torch.from_numpy(a.astype(np.float32))
+        out["domain"] = self.name
+        return out
+
+    # ------------------------------------------------------------------ device path
+    def to_device(self, device="cuda") -> "RawTokenDataset":
+        """Upload the token table (in its stored dtype), the action table and the start indices to HBM."""
+        dev = torch.device(device)
+        if dev.type != "cuda":
+            raise RuntimeError("RawTokenDataset.to_device needs a CUDA device (the host path is __getitem__)")
+        if self.data.dtype.itemsize not in (2, 4):
+            raise NotImplementedError(f"token dtype {self.data.dtype} (uint16 / uint32 tables are supported on the device)")
+        view = np.ascontiguousarray(self.data).view(np.int16 if self.data.dtype.itemsize == 2 else np.int32)
+        d = {"video": torch.from_numpy(view).to(dev), "starts": torch.tensor(self.valid_start_inds, dtype=torch.int64, device=dev)}
+        if hasattr(self, "actions"):
+            d["actions"] = torch.from_numpy(np.ascontiguousarray(self.actions, dtype=np.float32)).to(dev)
+        self._dev = d
+        return self
+
+    def gather(self, indices) -> Dict[str, object]:
+        """The batch `[self[i] for i in indices]` stacked, on the device: input_ids / labels i64 [B, window*h*w] (one tensor,
+        as in the reference where labels is input_ids), action_ids f32 [B, window, stride*action_dim], domain, h, w lists.
+        Every sample carries its actions (drop_action_ratio is a host-path, per-sample decision)."""
+        if self._dev is None:
+            raise RuntimeError("call to_device() first (there is no CPU fallback for gather; use __getitem__ on the host)")
+        d = self._dev
+        dev = d["video"].device
+        idx = torch.as_tensor(indices, dtype=torch.int64, device=dev)
+        starts = d["starts"][idx].contiguous()
+        B = starts.numel()
+        h, w = self.metadata["h"], self.metadata["w"]
+        tokens = torch.empty(B, self.window_size * h * w, device=dev, dtype=torch.int64)
+        _lib.call("hma_gather_token_windows", d["video"].data_ptr(), self.data.dtype.itemsize, len(self.data), starts.data_ptr(), B,
+                  self.window_size, self.stride, h * w, tokens.data_ptr(), ops._s())
+        out: Dict[str, object] = {"input_ids": tokens, "labels": tokens}
+        if "actions" in d:
+            adim = d["actions"].shape[1]
+            rows = self.video_len + self.stride
+            act = torch.empty(B, self.window_size, rows * adim // self.window_size, device=dev, dtype=torch.float32)
+            _lib.call("hma_gather_rows_f32", d["actions"].data_ptr(), d["actions"].shape[0], adim, starts.data_ptr(), B, rows,
+                      act.data_ptr(), ops._s())
+            out["action_ids"] = act
+        out["domain"] = [self.name] * B
+        out["h"] = [h] * B
+        out["w"] = [w] * B
+        return out

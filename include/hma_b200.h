@@ -279,6 +279,17 @@ int hma_dropout_add_f32(const float* a, const float* resid, float* out, long lon
 int hma_dropout_cast_bf16(const float* a, void* out16, long long count, float p, unsigned long long seed,
                           const unsigned long long* seed_dev, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Device-resident token dataset (hma/data.py:159-294 RawTokenDataset.__getitem__ + the stack in the collator):
+ * out[b, t, :] = (i64) video[starts[b] + t*stride, :] for a u16/u32 token table [num_images, frame_elems];
+ * out[b, :] = table[starts[b] .. starts[b] + rows_per_sample, :] for the f32 action table [num_rows, row_elems]
+ * (reshaped by the caller to [window, stride*action_dim], data.py:286).
+ * ------------------------------------------------------------------------------------------- */
+int hma_gather_token_windows(const void* video, int elem_bytes, long long num_images, const long long* starts, int B,
+                             int window, int stride, int frame_elems, long long* out, void* stream);
+int hma_gather_rows_f32(const float* table, long long num_rows, long long row_elems, const long long* starts, int B,
+                        long long rows_per_sample, float* out, void* stream);
+
 /* Test-only: single-CTA tcgen05 descriptor probe (see csrc/probe.cu; params is a HOST int[18]). */
 int hma_umma_probe(const void* A, long long lda, const void* B, long long ldb, const int* params, float* out,
                    void* stream);

@@ -1,0 +1,74 @@
+"""hma_b200.dataset.RawTokenDataset against outputs of the reference class (tests/golden/rawtoken.pt, made by
+oracle/make_rawtoken_golden.py) on the regenerated synthetic directory; the device gather against the host path."""
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+from tests import _rawdata
+
+GOLDEN = Path(__file__).parent / "golden" / "rawtoken.pt"
+
+
+@pytest.fixture(scope="module")
+def root(tmp_path_factory):
+    return _rawdata.write(tmp_path_factory.mktemp("rawtoken") / "ds", seed=0)
+
+
+@pytest.mark.parametrize("case", list(_rawdata.CASES))
+def test_matches_reference_fixture(root, case):
+    from hma_b200.dataset import RawTokenDataset
+
+    ref = torch.load(GOLDEN, weights_only=False)[case]
+    ds = RawTokenDataset(root, **_rawdata.CASES[case])
+    assert ds.stride == ref["stride"] and ds.n_action == ref["n_action"] and ds.num_videos == ref["num_videos"]
+    assert len(ds) == ref["len"] and list(ds.valid_start_inds) == ref["valid_start_inds"]
+    np.random.seed(0)
+    items = [ds[i] for i in ref["idx"]]
+    assert torch.equal(torch.stack([it["input_ids"] for it in items]), ref["input_ids"])
+    assert items[0]["domain"] == ref["domain"] and items[0]["h"] == 16 and items[0]["labels"] is items[0]["input_ids"]
+    if ref["action_ids"] is not None:
+        assert torch.equal(torch.stack([it["action_ids"] for it in items]), ref["action_ids"])
+        assert ds.action_stat == ref["action_stat"]
+    else:
+        assert "action_ids" not in items[0]
+
+
+def test_edge_cases(tmp_path):
+    from hma_b200.dataset import RawTokenDataset
+
+    # a table shorter than one window: empty dataset, no error (the reference's range() is empty too)
+    r = _rawdata.write(tmp_path / "short", seed=1, num_images=10)
+    assert len(RawTokenDataset(r, window_size=16)) == 0
+    # no segment ids: only usable without interrupt filtering (data.py:225-227)
+    (r / "segment_ids.bin").unlink()
+    with pytest.raises(NotImplementedError):
+        RawTokenDataset(r, window_size=2)
+    assert len(RawTokenDataset(r, window_size=2, filter_interrupts=False)) == 10 - 3 - 3
+    with pytest.raises(RuntimeError, match="to_device"):
+        RawTokenDataset(r, window_size=2, filter_interrupts=False).gather([0])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", ["uint32", "uint16"])
+def test_device_gather_equals_host_items(tmp_path, dtype):
+    from hma_b200.dataset import RawTokenDataset
+
+    r = _rawdata.write(tmp_path / dtype, seed=2, num_images=300, token_dtype=dtype)
+    ds = RawTokenDataset(r, window_size=4, use_actions=True).to_device("cuda")
+    g = torch.Generator().manual_seed(0)
+    idx = torch.randint(0, len(ds), (33,), generator=g)
+    out = ds.gather(idx)
+    items = [ds[int(i)] for i in idx]
+    assert torch.equal(out["input_ids"].cpu(), torch.stack([it["input_ids"] for it in items]))
+    assert torch.equal(out["action_ids"].cpu(), torch.stack([it["action_ids"] for it in items]))
+    assert out["labels"] is out["input_ids"] and out["domain"] == ["synthetic_robot"] * 33 and out["h"] == [16] * 33
+    # feeds the on-device collator unchanged
+    from hma_b200 import GenieConfig
+    from hma_b200.data import collate_from_draws, draw_on_device
+
+    cfg = GenieConfig(num_layers=1, num_heads=8, d_model=256, T=4, S=256, num_factored_vocabs=2)
+    if dtype == "uint32":
+        ids, labels = collate_from_draws(out["input_ids"], draw_on_device(cfg, 33, 16, 16, torch.device("cuda")), cfg, 16, 16)
+        assert torch.equal(labels, out["input_ids"]) and (ids == cfg.image_vocab_size).any()
