@@ -436,7 +436,10 @@ extern "C" int hma_gemm_nt(const void* A, long long lda, const void* B, long lon
   HMA_REQUIRE(N % 128 == 0, "gemm_nt: N=%d must be a multiple of 128", N);
   HMA_REQUIRE(out != nullptr, "gemm_nt: out is null");
   HMA_REQUIRE(ldo % 8 == 0 && ldo2 % 8 == 0 && ldr % 4 == 0 && ldaux % 4 == 0, "gemm_nt: leading dimensions must keep rows 16-byte aligned");
-  const int bn = (N % 256 == 0 && N >= 512) ? 256 : 128;
+  int bn = (N % 256 == 0 && N >= 512) ? 256 : 128;
+  // Few rows (decode / sampler shapes, M <= a few hundred): 256-wide tiles would occupy a fraction of the SMs and each
+  // CTA's k-loop is latency-bound, so halve the tile width to double the CTAs in flight.
+  if (bn == 256 && (long long)((M + kBM - 1) / kBM) * (N / 256) * 2 <= hma_host::sm_count()) bn = 128;
   CUtensorMap tmA, tmB;
   int rc = hma_host::make_tmap_bf16_2d(&tmA, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda * 2, kBK, kBM);
   if (rc) return rc;

@@ -640,20 +640,41 @@ __device__ __forceinline__ bool drop_keep(unsigned long long seed, long long i, 
   return (uint32_t)(z >> 32) >= thresh;
 }
 
-// mode 0: x16 in place; 1: out32 = resid + drop(a32); 2: out16 = bf16(drop(a32))
+// mode 0: x16 in place; 1: out32 = resid + drop(a32); 2: out16 = bf16(drop(a32)). Four elements per thread per iteration
+// (8- and 16-byte accesses); the keep decision is a function of (seed, element index) only.
 __global__ void __launch_bounds__(256) dropout_kernel(int mode, __nv_bfloat16* x16, const float* a32, const float* resid,
                                                       float* out32, long long count, uint32_t thresh, float keep_scale,
                                                       unsigned long long seed, const unsigned long long* seed_dev) {
   pdl_wait();
   if (seed_dev != nullptr) seed += *seed_dev * 0xD1342543DE82EF95ull;  // per-step seed that a CUDA-graph replay can change
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (long long)gridDim.x * blockDim.x) {
-    const float k = drop_keep(seed, i, thresh) ? keep_scale : 0.f;
+  const long long n4 = count / 4;
+  for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < n4; q += (long long)gridDim.x * blockDim.x) {
+    float k[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) k[e] = drop_keep(seed, q * 4 + e, thresh) ? keep_scale : 0.f;
     if (mode == 0) {
-      x16[i] = __float2bfloat16(bf16_to_f(x16[i]) * k);
-    } else if (mode == 1) {
-      out32[i] = resid[i] + a32[i] * k;
+      uint2 v = reinterpret_cast<uint2*>(x16)[q];
+      v.x = pack_bf16(bf16_lo(v.x) * k[0], bf16_hi(v.x) * k[1]);
+      v.y = pack_bf16(bf16_lo(v.y) * k[2], bf16_hi(v.y) * k[3]);
+      reinterpret_cast<uint2*>(x16)[q] = v;
     } else {
-      x16[i] = __float2bfloat16(a32[i] * k);
+      const float4 a = reinterpret_cast<const float4*>(a32)[q];
+      if (mode == 1) {
+        const float4 r = reinterpret_cast<const float4*>(resid)[q];
+        reinterpret_cast<float4*>(out32)[q] = make_float4(fmaf(a.x, k[0], r.x), fmaf(a.y, k[1], r.y), fmaf(a.z, k[2], r.z),
+                                                          fmaf(a.w, k[3], r.w));
+      } else {
+        reinterpret_cast<uint2*>(x16)[q] = make_uint2(pack_bf16(a.x * k[0], a.y * k[1]), pack_bf16(a.z * k[2], a.w * k[3]));
+      }
+    }
+  }
+  // tail (count % 4 elements), one thread
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    for (long long i = n4 * 4; i < count; ++i) {
+      const float k = drop_keep(seed, i, thresh) ? keep_scale : 0.f;
+      if (mode == 0) x16[i] = __float2bfloat16(bf16_to_f(x16[i]) * k);
+      else if (mode == 1) out32[i] = resid[i] + a32[i] * k;
+      else x16[i] = __float2bfloat16(a32[i] * k);
     }
   }
 }
@@ -863,7 +884,9 @@ static int launch_dropout(int mode, void* x16, const float* a32, const float* re
   if (count == 0) return 0;
   HMA_REQUIRE(p >= 0.f && p < 1.f, "dropout: p=%f out of range", p);
   const uint32_t thresh = (uint32_t)fmin(4294967295.0, (double)p * 4294967296.0);
-  HMA_CHECK_CUDA(hma_host::launch_pdl(dropout_kernel, dim3(grid_for(count, 256)), dim3(256), 0, stream, mode,
+  HMA_REQUIRE(((reinterpret_cast<uintptr_t>(x16) | reinterpret_cast<uintptr_t>(a32) | reinterpret_cast<uintptr_t>(resid) |
+                reinterpret_cast<uintptr_t>(out32)) & 15) == 0, "dropout: buffers must be 16-byte aligned");
+  HMA_CHECK_CUDA(hma_host::launch_pdl(dropout_kernel, dim3(grid_for((count + 3) / 4, 256)), dim3(256), 0, stream, mode,
                                       static_cast<__nv_bfloat16*>(x16), a32, resid, out32, count, thresh, 1.f / (1.f - p),
                                       seed, seed_dev));
   return 0;
