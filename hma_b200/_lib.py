@@ -88,6 +88,7 @@ _SIGNATURES = {
     "hma_mar_gate_fwd": [c_fp, c_void_p, c_ll, c_int, c_void_p, c_int, c_int, c_fp, c_void_p],
     "hma_mar_gate_bwd": [c_fp, c_void_p, c_ll, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p, c_ll, c_void_p],
     "hma_mar_silu_fwd": [c_fp, c_fp, c_ll, c_int, c_void_p, c_void_p],
+    "hma_mar_silu_steps": [c_fp, c_fp, c_ll, c_int, c_int, c_void_p, c_void_p],
     "hma_mar_silu_bwd": [c_fp, c_fp, c_ll, c_void_p, c_void_p],
     "hma_mar_q_sample": [c_fp, c_fp, c_void_p, c_fp, c_ll, c_int, c_int, c_void_p, c_void_p],
     "hma_mar_timestep_embed": [c_void_p, c_ll, c_void_p, c_void_p],

@@ -430,6 +430,22 @@ __global__ void __launch_bounds__(256) mar_silu_fwd_kernel(const float* y, const
   }
 }
 
+// out[(i*n + r), :] = SiLU(c[r, :] + te[i, :]) for every spaced step i: the conditioning of ALL sampler steps at once
+__global__ void __launch_bounds__(256) mar_silu_steps_kernel(const float* c, const float* te, long long n, int steps, int C,
+                                                            __nv_bfloat16* out) {
+  pdl_wait();
+  const long long per = n * (C / 4);
+  const long long total = per * steps;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long rem = i % per;
+    const int col = (int)(rem % (C / 4)) * 4;
+    const float4 v = reinterpret_cast<const float4*>(c)[rem];
+    const float4 a = *reinterpret_cast<const float4*>(te + (i / per) * C + col);
+    reinterpret_cast<uint2*>(out)[i] = make_uint2(pack_bf16(silu_exact(v.x + a.x), silu_exact(v.y + a.y)),
+                                                 pack_bf16(silu_exact(v.z + a.z), silu_exact(v.w + a.w)));
+  }
+}
+
 __global__ void __launch_bounds__(256) mar_silu_bwd_kernel(const float* dsy, const float* y, long long n4, __nv_bfloat16* dy) {
   pdl_wait();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
@@ -803,6 +819,14 @@ extern "C" int hma_mar_silu_fwd(const float* y, const float* rowvec, long long r
   HMA_REQUIRE(C % 4 == 0, "mar_silu_fwd: C must be a multiple of 4");
   HMA_CHECK_CUDA(hma_host::launch_pdl(mar_silu_fwd_kernel, dim3(grid_for(rows * C / 4, 256)), dim3(256), 0, STREAM, y, rowvec,
                                       rows, C, static_cast<__nv_bfloat16*>(out16)));
+  return 0;
+}
+
+extern "C" int hma_mar_silu_steps(const float* c, const float* te, long long n, int steps, int C, void* out16, void* stream_) {
+  if (n == 0 || steps == 0) return 0;
+  HMA_REQUIRE(C % 4 == 0, "mar_silu_steps: C must be a multiple of 4");
+  HMA_CHECK_CUDA(hma_host::launch_pdl(mar_silu_steps_kernel, dim3(grid_for(n * steps * (C / 4), 256)), dim3(256), 0, STREAM, c, te,
+                                      n, steps, C, static_cast<__nv_bfloat16*>(out16)));
   return 0;
 }
 

@@ -245,7 +245,7 @@ class MarEngine(Engine):
         n = self.NET
         w_in, w_fl, b_fl = p[n + "input_proj.weight"], p[n + "final_layer.linear.weight"], p[n + "final_layer.linear.bias"]
         ver = (w_in._version, w_fl._version, b_fl._version, w_in.data_ptr())
-        if training or self._pad.get("ver") != ver:
+        if training or self._pad.get("ver") != ver or "ada_w" not in self._pad:
             D2 = w_fl.shape[0]
             fl = torch.zeros(KPAD, w_fl.shape[1], device=w_fl.device, dtype=torch.float32)
             fl[:D2].copy_(w_fl)
@@ -254,6 +254,11 @@ class MarEngine(Engine):
             bias[:D2].copy_(b_fl)
             self._pad = {"ver": ver, "in": ops.action_prep(w_in.detach().contiguous(), KPAD), "fl": fl_b, "fl_t": fl_t,
                          "fl_bias": bias}
+            if not training:  # sampler: every adaLN Linear stacked into one [3w*depth + 2w, w] operand
+                ada = [n + f"res_blocks.{i}.adaLN_modulation.1." for i in range(self.cfg.diffloss_d)]
+                ada.append(n + "final_layer.adaLN_modulation.1.")
+                self._pad["ada_w"] = torch.cat([self.weights.plain[a + "weight"] for a in ada], dim=0).contiguous()
+                self._pad["ada_b"] = torch.cat([p[a + "bias"].detach().to(torch.float32) for a in ada], dim=0).contiguous()
 
     # ---------------------------------------------------------------- trunk with the continuous front end and latent head
     def latents(self, p, lat: Optional[Tensor], mask_u8: Optional[Tensor], xp_in: Optional[Tensor], actions: Optional[Tensor],
@@ -302,14 +307,19 @@ class MarEngine(Engine):
         self.backward(p, sv, do16, g=g, front_bwd=front_bwd)
 
     # ---------------------------------------------------------------- SimpleMLPAdaLN (diffloss.py:212-233)
-    def _mlp(self, p, x16: Tensor, sy: Tensor, keep: Optional[list]) -> Tensor:
-        """x16: bf16 [N, KPAD] padded input; sy: bf16 [N, w] = SiLU(t_emb + c_emb). Returns fp32 [N, KPAD] = eps | v | 0."""
+    def _mlp(self, p, x16: Tensor, sy: Optional[Tensor], keep: Optional[list], mods: Optional[Tensor] = None) -> Tensor:
+        """x16: bf16 [N, KPAD] padded input; sy: bf16 [N, w] = SiLU(t_emb + c_emb). Returns fp32 [N, KPAD] = eps | v | 0.
+        `mods` (sampler): bf16 [N, 3w*depth + 2w], the adaLN modulations of every block and of the final layer already
+        computed for these rows (column blocks in layer order), replacing the per-layer GEMMs on sy."""
         n, Wp, cfg = self.NET, self.weights.plain, self.cfg
         w = cfg.diffloss_w
         x = ops.gemm_nt(x16, self._pad["in"], EPI_RESID, bias=p[n + "input_proj.bias"])
         for i in range(cfg.diffloss_d):
             q = n + f"res_blocks.{i}."
-            mod = ops.gemm_nt(sy, Wp[q + "adaLN_modulation.1.weight"], EPI_BF16, bias=p[q + "adaLN_modulation.1.bias"])
+            if mods is not None:
+                mod = mods[:, 3 * w * i: 3 * w * (i + 1)]
+            else:
+                mod = ops.gemm_nt(sy, Wp[q + "adaLN_modulation.1.weight"], EPI_BF16, bias=p[q + "adaLN_modulation.1.bias"])
             _, u16, st = ops.mar_ln_fwd(x, gamma=p[q + "in_ln.weight"], beta=p[q + "in_ln.bias"], eps=1e-6, mod=mod, shift_off=0,
                                         scale_off=w, want_stats=keep is not None)
             za = torch.empty(x.shape[0], w, device=x.device, dtype=torch.bfloat16) if keep is not None else None
@@ -320,7 +330,10 @@ class MarEngine(Engine):
                 keep.append(dict(x=x, mod=mod, u16=u16, st=st, za=za, a=a, h2=h2))
             x = xn
         q = n + "final_layer."
-        modf = ops.gemm_nt(sy, Wp[q + "adaLN_modulation.1.weight"], EPI_BF16, bias=p[q + "adaLN_modulation.1.bias"])
+        if mods is not None:
+            modf = mods[:, 3 * w * cfg.diffloss_d:]
+        else:
+            modf = ops.gemm_nt(sy, Wp[q + "adaLN_modulation.1.weight"], EPI_BF16, bias=p[q + "adaLN_modulation.1.bias"])
         _, uf16, stf = ops.mar_ln_fwd(x, eps=1e-6, mod=modf, shift_off=0, scale_off=w, want_stats=keep is not None)
         out = ops.gemm_nt(uf16, self._pad["fl"], EPI_RESID, bias=self._pad["fl_bias"])
         if keep is not None:
@@ -430,19 +443,36 @@ class MarEngine(Engine):
         out = self._mlp(p, x16, sy, None)
         ops.mar_p_sample(out, x, noise_i, tb, i, temperature, clip, x_next, x16_next)
 
+    MOD_CHUNK_BYTES = 2 << 30
+
     def sample(self, p, z16: Tensor, x_init: Tensor, noise: Tensor, te_tab: Tensor, respacing: str, temperature: float,
                clip: bool) -> Tensor:
         """p_sample_loop for every row. x_init fp32 [n, D]; noise fp32 [steps, n, D] (noise[i] is the draw used at spaced
-        step i). Returns fp32 [n, D]."""
+        step i). Returns fp32 [n, D].
+
+        The adaLN modulations depend on (z, timestep) only, not on x_t: they are computed for ALL spaced steps by one GEMM
+        over steps*n rows against the stacked adaLN weights (in chunks of <= 2 GB of output), which takes the five widest
+        GEMMs out of the sequential per-step chain and runs them at full-size tiles instead of n-row slivers. Same values
+        as sample_step (an output element's k-loop does not depend on the tiling)."""
         tb, _, steps = self.tables(respacing, z16.device)
+        n = x_init.shape[0]
         c = self.sample_cond(p, z16)
+        sy_all = ops.mar_silu_steps(c, te_tab)
+        ada_w, ada_b = self._pad["ada_w"], self._pad["ada_b"]
+        per = max(1, min(steps, self.MOD_CHUNK_BYTES // max(1, n * ada_w.shape[0] * 2)))
         x = x_init.contiguous()
         x16 = ops.mar_q_sample(x, None, None, None, KPAD)
         nxt, nxt16 = torch.empty_like(x), torch.empty_like(x16)
-        for i in reversed(range(steps)):
-            self.sample_step(p, c, te_tab, tb, i, x, x16, noise[i], temperature, clip, nxt, nxt16)
-            x, nxt = nxt, x
-            x16, nxt16 = nxt16, x16
+        hi = steps
+        while hi > 0:
+            lo = max(0, hi - per)
+            mods = ops.gemm_nt(sy_all[lo * n: hi * n], ada_w, EPI_BF16, bias=ada_b)
+            for i in reversed(range(lo, hi)):
+                out = self._mlp(p, x16, None, None, mods=mods[(i - lo) * n: (i - lo + 1) * n])
+                ops.mar_p_sample(out, x, noise[i], tb, i, temperature, clip, nxt, nxt16)
+                x, nxt = nxt, x
+                x16, nxt16 = nxt16, x16
+            hi = lo
         return x
 
 

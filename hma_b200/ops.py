@@ -403,6 +403,15 @@ def mar_silu_fwd(y: torch.Tensor, rowvec: Optional[torch.Tensor] = None) -> torc
     return out
 
 
+def mar_silu_steps(c: torch.Tensor, te: torch.Tensor) -> torch.Tensor:
+    """bf16 [steps*n, C] = SiLU(c[r] + te[i]) in step-major order."""
+    n, C = c.shape
+    steps = te.shape[0]
+    out = torch.empty(steps * n, C, device=c.device, dtype=BF16)
+    _call("mar_silu_fwd", steps * n * C * 2.0, "hma_mar_silu_steps", c.data_ptr(), te.data_ptr(), n, steps, C, out.data_ptr(), _s())
+    return out
+
+
 def mar_silu_bwd(dsy: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
     dy = torch.empty(y.shape, device=y.device, dtype=BF16)
     _call("mar_silu_bwd", y.numel() * 10.0, "hma_mar_silu_bwd", dsy.data_ptr(), y.data_ptr(), y.numel(), dy.data_ptr(), _s())

@@ -245,6 +245,9 @@ int hma_mar_gate_bwd(const float* dx, const void* mod, long long ldmod, int gate
 /* out16 = bf16(SiLU(y + rowvec)) (rowvec fp32 [C], optional); backward dy16 = bf16(dsy * SiLU'(y)). */
 int hma_mar_silu_fwd(const float* y, const float* rowvec, long long rows, int C, void* out16, void* stream);
 int hma_mar_silu_bwd(const float* dsy, const float* y, long long count, void* dy16, void* stream);
+/* out16[(i*n + r), :] = bf16(SiLU(c[r, :] + te[i, :])), i < steps: the conditioning vectors of every sampler step at once
+ * (they do not depend on x_t, so all adaLN modulations of a sampling call are one GEMM over steps*n rows). */
+int hma_mar_silu_steps(const float* c, const float* te, long long n, int steps, int C, void* out16, void* stream);
 /* xt16 (bf16 [N,kpad], zero padded) = tables[t].sqrt_acp * x0 + tables[t].sqrt_1m_acp * noise (gaussian_diffusion.py:200-215);
  * noise == NULL: plain cast of x0. */
 int hma_mar_q_sample(const float* x0, const float* noise, const long long* t, const float* tables, long long N, int D,

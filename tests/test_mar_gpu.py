@@ -419,6 +419,22 @@ def test_mar_sampler_teacher_forced_against_oracle():
             worst = max(worst, err.max().item())
             assert err.max().item() <= 5e-2, (i, err.max().item())
     print("worst well-conditioned teacher-forced step error", worst)
+    # the product loop (adaLN modulations of all steps hoisted into one GEMM) == the step-by-step chain, bit for bit
+    noise = torch.stack([t[2] for t in sorted(trace, key=lambda t: t[0])]).to(DEV)
+    z16 = z.bfloat16().to(DEV)
+    got = eng.sample(p, z16, x0.to(DEV), noise, te_tab, cfg.num_sampling_steps, 0.9, True)
+    x = x0.to(DEV).contiguous()
+    x16 = ops.mar_q_sample(x, None, None, None, KPAD)
+    nxt, nxt16 = torch.empty_like(x), torch.empty_like(x16)
+    for i in reversed(range(steps)):
+        eng.sample_step(p, c, te_tab, tabs, i, x, x16, noise[i], 0.9, True, nxt, nxt16)
+        x, nxt, x16, nxt16 = nxt, x, nxt16, x16
+    assert torch.equal(got, x)
+    eng.MOD_CHUNK_BYTES = 7 * n * eng._pad["ada_w"].shape[0] * 2  # force several chunks (7 steps each)
+    try:
+        assert torch.equal(eng.sample(p, z16, x0.to(DEV), noise, te_tab, cfg.num_sampling_steps, 0.9, True), x)
+    finally:
+        del eng.MOD_CHUNK_BYTES
 
 
 def test_mar_maskgit_generate_matches_reference_fixture():
