@@ -263,10 +263,14 @@ class MarEngine(Engine):
     # ---------------------------------------------------------------- trunk with the continuous front end and latent head
     def latents(self, p, lat: Optional[Tensor], mask_u8: Optional[Tensor], xp_in: Optional[Tensor], actions: Optional[Tensor],
                 dom: Optional[str], d: Dims, H: int, W: int, training: bool, skip_normalization: bool = False, drop=None,
-                fill_inplace: bool = False):
-        """st_mar.py:146-197. Returns (z32 fp32 [B*T*Sp, 256], z16 bf16, rowmask or None, saved or None)."""
+                fill_inplace: bool = False, *, t0: int = 0, kv=None, mode: str = "full", frame_cond=None):
+        """st_mar.py:146-197. Returns (z32 fp32 [B*T*Sp, 256], z16 bf16, rowmask or None, saved or None).
+        t0 / kv / mode / frame_cond: frame-incremental decode as in Engine.forward (the d.T frames given are window frames
+        [t0, t0 + T); "prefill" returns no latents)."""
         cfg = self.cfg
         pos = p["pos_embed_TSC"]
+        if t0:
+            pos = pos[:, t0:]
         fs = {}
 
         def front(act):
@@ -278,9 +282,11 @@ class MarEngine(Engine):
             fs.update(u=u, xp=xp, st=st, rowmask=rowmask)
             return x32
 
-        o, sv = self.forward(p, None, actions, dom, d, training, skip_normalization, front=front, drop=drop)
-        Tcfg_rows = d.T * d.S
-        add = p["diffusion_pos_embed_learned"].reshape(-1, 256)[:Tcfg_rows]
+        o, sv = self.forward(p, None, actions, dom, d, training, skip_normalization, front=front, drop=drop, t0=t0, kv=kv,
+                             mode=mode, frame_cond=frame_cond)
+        if o is None:  # prefill: only the temporal K/V of these frames were needed
+            return None, None, None, None
+        add = p["diffusion_pos_embed_learned"].reshape(-1, 256)[t0 * d.S: (t0 + d.T) * d.S]
         z32, z16, stz = ops.mar_ln_fwd(o, gamma=p["decoder_norm.weight"], beta=p["decoder_norm.bias"], eps=1e-6, add=add,
                                        want32=True, want16=True, want_stats=training)
         if training:
@@ -533,6 +539,7 @@ class STMAR(STMaskGIT):
         self.maskgit_steps = config.maskgit_steps
         self.diffusion_batch_mul = config.diffusion_batch_mul
         self._graphs: Dict[tuple, tuple] = {}
+        self._kv = None
         self._randn: Optional[Callable] = None  # test hook: replaces torch.randn for the sampling noise
         super().__init__(config)
         for m in self.modules():  # st_mar.py:107-110 -> st_mask_git.py:737-752 init_weights
@@ -736,7 +743,9 @@ class STMAR(STMaskGIT):
         """prompt_THW: latents [B, T, H, W, C] (not modified — the reference rebinds the patchified copy). Returns
         (frame [B, H, W, C], latents of step 0 [B, d, h, w], None). As in the reference, every MaskGIT step recomputes
         the whole window and, because `unmasked` is never updated there, re-predicts every token outside mask_next
-        (all tokens on the last step)."""
+        (all tokens on the last step). `decode_algorithm = "incremental"` (default) computes the context frames once per
+        call and only frame out_t per MaskGIT step (same latents up to bf16 summation order); "full" recomputes the whole
+        window per step as the reference does."""
         assert out_t, "maskgit_generate requires out_t > 0"
         if cfg != 1.0:
             raise NotImplementedError("classifier-free guidance (cfg != 1.0) is not implemented")
@@ -756,15 +765,45 @@ class STMAR(STMaskGIT):
         d = eng.mar_dims(B, T, h * ps, w * ps, action_ids is not None)
         p = self._inference_params()
         eng.prepare_diffloss(p, False)
-        xp = x.view(B * T * S, D)
+        skip_norm = kwargs.get("skip_normalization", False)
         lens = self.mask_schedule(self.seq_len, maskgit_steps)
-        base = (torch.arange(B) * T + out_t) * S
+        incremental = self.decode_algorithm == "incremental"
         z0 = None
+        if incremental:
+            # Frames before out_t never change during the MaskGIT steps and reach frame out_t only through their per-layer
+            # temporal K/V (temporal attention is causal, spatial attention per frame): run them once, then only frame
+            # out_t per step. Frames after out_t cannot influence it at all.
+            n_tok = d.n
+            key = (B, T, n_tok, str(dev))
+            if self._kv is None or self._kv[0] != key:
+                self._kv = (key, torch.zeros(self.config.num_layers, T, B * n_tok, 512, device=dev, dtype=torch.bfloat16))
+            kv = self._kv[1]
+            d_ctx = eng.mar_dims(B, out_t, h * ps, w * ps, action_ids is not None)
+            d1 = eng.mar_dims(B, 1, h * ps, w * ps, action_ids is not None)
+            ctx = x[:, :out_t].reshape(B * out_t * S, D).contiguous()
+            eng.latents(p, None, None, ctx, None if action_ids is None else action_ids[:, :out_t].contiguous(), dom, d_ctx,
+                        h * ps, w * ps, False, skip_norm, kv=kv, mode="prefill")
+            cond = None
+            if action_ids is not None:
+                eng.prepare_weights(p, d1, dom, False)
+                act, c_bf = eng.action_stem(p, action_ids[:, out_t].reshape(B, -1).to(torch.float32).contiguous(), dom, skip_norm)
+                mods = eng.modulation_all_layers(p, c_bf, dom, d1.num_layers, False)[2] if d1.modulate else None
+                cond = (act, mods)
+            xf = x[:, out_t].reshape(B * S, D).contiguous()
+            base = torch.arange(B) * S
+        else:
+            xp = x.view(B * T * S, D)
+            base = (torch.arange(B) * T + out_t) * S
         for step in range(maskgit_steps):
-            z32, _, _, _ = eng.latents(p, None, None, xp, action_ids, dom, d, h * ps, w * ps, False,
-                                       kwargs.get("skip_normalization", False))
-            if step == 0:
-                z0 = z32.view(B, T, S, -1)[:, out_t].clone()
+            if incremental:
+                z32, _, _, _ = eng.latents(p, None, None, xf, None, dom, d1, h * ps, w * ps, False, skip_norm, t0=out_t, kv=kv,
+                                           mode="step", frame_cond=cond)
+                if step == 0:
+                    z0 = z32.view(B, S, -1).clone()
+            else:
+                z32, _, _, _ = eng.latents(p, None, None, xp, action_ids, dom, d, h * ps, w * ps, False, skip_norm)
+                if step == 0:
+                    z0 = z32.view(B, T, S, -1)[:, out_t].clone()
             to_pred = torch.ones(B, S, dtype=torch.bool)
             if step < maskgit_steps - 1:
                 to_pred.scatter_(1, orders[:, : lens[step]], False)  # mask ^ mask_next with mask all-True
@@ -772,7 +811,9 @@ class STMAR(STMaskGIT):
             idx = (base[bi] + si).to(torch.int32).to(dev)
             _, zc16 = ops.mar_gather_rows(z32, idx, False, True)
             smp = self._sample_rows(p, zc16, temperature, True)
-            ops.mar_scatter_rows(smp, idx, xp)
+            ops.mar_scatter_rows(smp, idx, xf if incremental else xp)
+        if incremental:
+            x[:, out_t] = xf.view(B, h, w, D)
         frame = self.unpatchify(x[:, out_t:out_t + 1])[:, 0]
         return frame, z0.view(B, h, w, -1).permute(0, 3, 1, 2), None
 
