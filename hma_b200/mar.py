@@ -681,8 +681,9 @@ class STMAR(STMaskGIT):
             return self._randn(shape).to(dev, torch.float32)
         return torch.randn(shape, device=dev)
 
-    def _sample_rows(self, p, z16: Tensor, temperature: float, clip: bool) -> Tensor:
-        """DiffLoss.sample (diffloss.py:37-59, cfg == 1.0) for the given conditioning rows."""
+    def _sample_rows(self, p, z16: Tensor, temperature: float, clip: bool, te_tab: Optional[Tensor] = None) -> Tensor:
+        """DiffLoss.sample (diffloss.py:37-59, cfg == 1.0) for the given conditioning rows. te_tab: the time embeddings of
+        the spaced steps if the caller already has them (they depend on the weights only)."""
         eng: MarEngine = self._engine
         dev = z16.device
         resp = self.num_sampling_steps
@@ -695,7 +696,8 @@ class STMAR(STMaskGIT):
                 noise[i] = self._draw((n, D), dev)
         else:
             noise = torch.randn(steps, n, D, device=dev)
-        te_tab = eng.time_table(p, resp, dev)
+        if te_tab is None:
+            te_tab = eng.time_table(p, resp, dev)
         if not (self.sample_cuda_graphs and self._randn is None):
             return eng.sample(p, z16, x0, noise, te_tab, resp, temperature, clip)
         key = (n, float(temperature), bool(clip), resp, self._weights_signature(p))
@@ -768,6 +770,7 @@ class STMAR(STMaskGIT):
         skip_norm = kwargs.get("skip_normalization", False)
         lens = self.mask_schedule(self.seq_len, maskgit_steps)
         incremental = self.decode_algorithm == "incremental"
+        te_tab = eng.time_table(p, self.num_sampling_steps, dev)
         z0 = None
         if incremental:
             # Frames before out_t never change during the MaskGIT steps and reach frame out_t only through their per-layer
@@ -810,7 +813,7 @@ class STMAR(STMaskGIT):
             bi, si = to_pred.nonzero(as_tuple=True)
             idx = (base[bi] + si).to(torch.int32).to(dev)
             _, zc16 = ops.mar_gather_rows(z32, idx, False, True)
-            smp = self._sample_rows(p, zc16, temperature, True)
+            smp = self._sample_rows(p, zc16, temperature, True, te_tab)
             ops.mar_scatter_rows(smp, idx, xf if incremental else xp)
         if incremental:
             x[:, out_t] = xf.view(B, h, w, D)
