@@ -190,12 +190,18 @@ __device__ __forceinline__ void epilogue_chunk(const GemmNtParams& p, const uint
     });
   } else if constexpr (EPI == HMA_EPI_RESID_F32) {
     float* out = static_cast<float*>(p.out);
+    __nv_bfloat16* out2 = static_cast<__nv_bfloat16*>(p.out2);  // optional bf16 copy: the next stage's GEMM operand
     transpose_f32(stage, lane, v, [&](int rr, int cc, float4 a) {
       const int row = row0 + rr;
       if (row < p.M) {
         const float4 x = pf[rr >> 2];
         a.x += x.x; a.y += x.y; a.z += x.z; a.w += x.w;
         *reinterpret_cast<float4*>(out + (size_t)row * p.ldo + n0 + cc) = a;
+        if (out2 != nullptr) {
+          const uint2 b = make_uint2(pack_bf16(a.x, a.y), pack_bf16(a.z, a.w));
+          *reinterpret_cast<uint2*>(out2 + (size_t)row * p.ldo2 + n0 + cc) = b;
+          csum.x += bf16_lo(b.x); csum.y += bf16_hi(b.x); csum.z += bf16_lo(b.y); csum.w += bf16_hi(b.y);
+        }
       }
     });
   }
@@ -353,7 +359,7 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       tc_fence_before();
       mbar_arrive(smem_u32(&bar_tempty[as]));
     }
-    if constexpr (EPI == HMA_EPI_DGELU_BF16 || EPI == HMA_EPI_DSILU_BF16) {
+    if constexpr (EPI == HMA_EPI_DGELU_BF16 || EPI == HMA_EPI_DSILU_BF16 || EPI == HMA_EPI_RESID_F32) {
       if (p.colsum != nullptr) {
 #pragma unroll
         for (int j = 0; j < kChunks; ++j) {
@@ -452,8 +458,9 @@ extern "C" int hma_gemm_nt(const void* A, long long lda, const void* B, long lon
   p.aux = static_cast<const __nv_bfloat16*>(aux); p.ldaux = ldaux;
   p.alpha = alpha;
   p.colsum = colsum;
-  HMA_REQUIRE(colsum == nullptr || epi == HMA_EPI_DGELU_BF16 || epi == HMA_EPI_DSILU_BF16,
-              "gemm_nt: colsum is only produced by the d-activation epilogues");
+  HMA_REQUIRE(colsum == nullptr || epi == HMA_EPI_DGELU_BF16 || epi == HMA_EPI_DSILU_BF16 ||
+                  (epi == HMA_EPI_RESID_F32 && out2 != nullptr),
+              "gemm_nt: colsum is produced by the d-activation epilogues and by the residual epilogue with a bf16 copy");
   switch (epi) {
     case HMA_EPI_BF16: return dispatch_nt<HMA_EPI_BF16>(tmA, tmB, p, bn, stream);
     case HMA_EPI_GELU_BF16: return dispatch_nt<HMA_EPI_GELU_BF16>(tmA, tmB, p, bn, stream);

@@ -300,8 +300,10 @@ class Engine:
                 qkv_s_raw = qkv_s
                 qkv_s = ops.qk_norm_fwd(qkv_s_raw, p[lp + "spatial_attn.norm.weight"], p[lp + "spatial_attn.norm.bias"])
             att_s, lse = ops.attn_spatial_fwd(qkv_s, M, n, d.heads, d.scale, want_lse=training)
+            plain = not d.modulate and not d.additive  # x2 is x1: the temporal stage's bf16 operand comes out of this GEMM
+            at = torch.empty(N, C, device=x.device, dtype=torch.bfloat16)
             x1 = ops.gemm_nt(att_s, Wp[lp + "spatial_attn.proj.weight"], EPI_RESID, bias=p.get(lp + "spatial_attn.proj.bias"),
-                             resid=x, out=None if training else x)
+                             resid=x, out=None if training else x, out2=at if plain else None)
             # ---- per-layer action conditioning (st_transformer.py:102-104; st_mask_git.py:66-76)
             if d.modulate:
                 ap = lp + f"action_projectors.{dom}."
@@ -312,15 +314,17 @@ class Engine:
                 zmod = zmods[i] if training else None
                 am, stm = ops.ln_fwd(x1, 2, mod=mod, rows_per_group=n, eps=1e-6, want_stats=True)
                 x2 = ops.gemm_nt(am, Wp[ap + "linear_out.weight"], EPI_RESID, bias=p[ap + "linear_out.bias"], resid=x1,
-                                 out=None if training else x1)
+                                 out=None if training else x1, out2=at)
                 if training:
                     L.update(zmod=zmod, hmod=hmod, mod=mod, am=am, stm=stm)
             elif d.additive:  # st_transformer.py:93-97: x += action embedding of the frame, broadcast over its tokens
                 x2 = ops.group_add(x1, act, n, out=None if training else x1)
             else:
                 x2 = x1
-            # ---- causal temporal attention, no pre-norm (st_transformer.py:111)
-            at = ops.ln_fwd(x2, 0)
+            # ---- causal temporal attention, no pre-norm (st_transformer.py:111): `at` = bf16(x2), written by the GEMM
+            # that produced x2 (or cast here after the additive conditioning)
+            if d.additive and not d.modulate:
+                ops.ln_fwd(x2, 0, out=at)
             qkv_t = ops.gemm_nt(at, Wp[lp + "temporal_attn.qkv.weight"], EPI_BF16, bias=p.get(lp + "temporal_attn.qkv.bias"))
             if qk:
                 qkv_t_raw = qkv_t
@@ -489,11 +493,14 @@ class Engine:
             ops.gemm_wgrad(dqkv, L["at"], g2(lp + "temporal_attn.qkv.weight"))
             if lp + "temporal_attn.qkv.bias" in g:
                 ops.colsum_bf16(dqkv, g2(lp + "temporal_attn.qkv.bias"))
-            ops.gemm_nt(dqkv, Wt[lp + "temporal_attn.qkv.weight"], EPI_RESID, resid=dx, out=dx)
+            # dx += dqkv . W; its bf16 copy and column sums (operand and bias gradient of the stage below) come out of
+            # the same epilogue
+            dy = torch.empty(N, C, device=dev, dtype=torch.bfloat16)
+            nb = g2(lp + f"action_projectors.{dom}.linear_out.bias") if d.modulate else g.get(lp + "spatial_attn.proj.bias")
+            ops.gemm_nt(dqkv, Wt[lp + "temporal_attn.qkv.weight"], EPI_RESID, resid=dx, out=dx, out2=dy, colsum=nb)
             # ---- modulate
             if d.modulate:
                 ap = lp + f"action_projectors.{dom}."
-                dy = ops.cast_colsum(dx, g2(ap + "linear_out.bias"))
                 ops.gemm_wgrad(dy, L["am"], g2(ap + "linear_out.weight"))
                 dam = ops.gemm_nt(dy, Wt[ap + "linear_out.weight"], EPI_BF16)
                 dmod = torch.zeros(M, 2 * C, device=dev, dtype=torch.float32)
@@ -512,10 +519,8 @@ class Engine:
                     ops.gemm_wgrad(dzm, sv["c_bf"], g2(ap + "adaLN_modulation.0.weight"))
                     ops.gemm_nt(dzm, Wt[ap + "adaLN_modulation.0.weight"], EPI_RESID, resid=dact, out=dact)
                     side_keep.append((dmod, dmod_bf, dzm))  # alive until the side stream has been joined
-            else:
-                if d.additive:
-                    ops.group_colsum(dx, dact, n)
-                dy = ops.cast_colsum(dx, g.get(lp + "spatial_attn.proj.bias"))
+            elif d.additive:
+                ops.group_colsum(dx, dact, n)
             # ---- spatial attention
             ops.gemm_wgrad(dy, L["att_s"], g2(lp + "spatial_attn.proj.weight"))
             datt = ops.gemm_nt(dy, Wt[lp + "spatial_attn.proj.weight"], EPI_BF16)

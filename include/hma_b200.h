@@ -40,11 +40,13 @@ int hma_device_check(void);
 #define HMA_EPI_BF16 0       /* out(bf16)  = alpha*acc + bias                                  */
 #define HMA_EPI_GELU_BF16 1  /* z = alpha*acc + bias; out2(bf16) = z (optional); out = gelu(z) */
 #define HMA_EPI_DGELU_BF16 2 /* out(bf16)  = (alpha*acc) * gelu'(aux)                          */
-#define HMA_EPI_RESID_F32 3  /* out(fp32)  = resid(fp32, optional) + alpha*acc + bias          */
+#define HMA_EPI_RESID_F32 3  /* out(fp32)  = resid(fp32, optional) + alpha*acc + bias; out2(bf16, optional) = bf16(out) */
 #define HMA_EPI_SILU_BF16 4  /* as GELU_BF16 with SiLU (adaLN_modulation, st_mask_git.py:61-63) */
 #define HMA_EPI_DSILU_BF16 5 /* out(bf16)  = (alpha*acc) * silu'(aux)                          */
-/* DGELU / DSILU only: if colsum != NULL, colsum[N] (fp32) += column sums of out — the bias gradient of the Linear whose
- * pre-activation gradient this is (accumulated in registers across the CTA's row tiles; a few atomics per CTA). */
+/* DGELU / DSILU: if colsum != NULL, colsum[N] (fp32) += column sums of out — the bias gradient of the Linear whose
+ * pre-activation gradient this is (accumulated in registers across the CTA's row tiles; a few atomics per CTA).
+ * RESID_F32 with out2: colsum[N] += column sums of out2 (the bf16 copy is the next backward stage's operand and its column
+ * sums that stage's bias gradient), which replaces a separate cast + column-sum pass over the residual stream. */
 
 /* out[M,N] = epi(A[M,K] . B[N,K]^T). A, B bf16 row-major. Replaces nn.Linear forward
  * (attention.py:141,154; st_transformer.py:24-27; st_mask_git.py:70-75,681-683) and, with B a
