@@ -117,10 +117,12 @@ class RawTokenDataset(torch.utils.data.Dataset):
             raise RuntimeError("RawTokenDataset.to_device needs a CUDA device (the host path is __getitem__)")
         if self.data.dtype.itemsize not in (2, 4):
             raise NotImplementedError(f"token dtype {self.data.dtype} (uint16 / uint32 tables are supported on the device)")
-        view = np.ascontiguousarray(self.data).view(np.int16 if self.data.dtype.itemsize == 2 else np.int32)
+        # one host copy of the read-only memmap (torch cannot wrap non-writable arrays), reinterpreted as a signed type of
+        # the same width for torch; the kernel reads the bits as unsigned
+        view = np.array(self.data).view(np.int16 if self.data.dtype.itemsize == 2 else np.int32)
         d = {"video": torch.from_numpy(view).to(dev), "starts": torch.tensor(self.valid_start_inds, dtype=torch.int64, device=dev)}
         if hasattr(self, "actions"):
-            d["actions"] = torch.from_numpy(np.ascontiguousarray(self.actions, dtype=np.float32)).to(dev)
+            d["actions"] = torch.from_numpy(np.array(self.actions, dtype=np.float32)).to(dev)
         self._dev = d
         return self
 
