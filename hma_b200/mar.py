@@ -530,6 +530,10 @@ class STMAR(STMaskGIT):
     """Spatial-time MAR (st_mar.py:38). See the module docstring."""
 
     sample_cuda_graphs = True
+    # Replaying the one-frame decode pass from a CUDA graph measured SLOWER at batch 8 (528 vs 490 ms per 2-frame generate
+    # call): the GPU is busy with the previous step's sampler graph while the host enqueues the pass, so there is no host
+    # time to save. Off by default; useful when the sampler is short (few rows, few steps) and the host is the limit.
+    decode_cuda_graphs = False
 
     def __init__(self, config: DiffusionGenieConfig):
         MarEngine.check(config)

@@ -534,6 +534,7 @@ def test_mar_incremental_decode_matches_full_window():
     dom = rec["domains"][0]
     r = rec[dom]
     outs = {}
+    model.decode_cuda_graphs = True  # exercise the graph replay of the one-frame pass as well (second MaskGIT step on)
     for algo in ("incremental", "full"):
         model.decode_algorithm = algo
         for out_t in (cfg.T - 1, 2):
