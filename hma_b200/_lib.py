@@ -82,7 +82,7 @@ _SIGNATURES = {
     "hma_mar_embed_bwd": [c_fp, c_fp, c_void_p, c_fp, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_fp, c_fp, c_fp,
                           c_fp, c_void_p],
     "hma_mar_ln_fwd": [c_fp, c_int, c_int, c_fp, c_fp, c_float, c_void_p, c_ll, c_int, c_int, c_fp, c_int, c_fp, c_void_p, c_fp,
-                       c_void_p],
+                       c_void_p, c_ll, c_int, c_void_p, c_fp, c_void_p],
     "hma_mar_ln_bwd": [c_void_p, c_fp, c_fp, c_fp, c_int, c_int, c_fp, c_fp, c_void_p, c_ll, c_int, c_int, c_fp, c_int, c_void_p,
                        c_fp, c_fp, c_void_p, c_ll, c_fp, c_int, c_void_p],
     "hma_mar_gate_fwd": [c_fp, c_void_p, c_ll, c_int, c_void_p, c_int, c_int, c_fp, c_void_p],

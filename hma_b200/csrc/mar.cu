@@ -182,6 +182,13 @@ struct LnArgs {
   float* y32;
   __nv_bfloat16* y16;
   float* stats;
+  // optional fused residual gate of the PREVIOUS block (diffloss.py:140): the row normalised is x + gmod[gate_off..] * h2,
+  // which is also written to xsum (the new residual stream)
+  const __nv_bfloat16* gmod;
+  long long ldg;
+  int gate_off;
+  const __nv_bfloat16* h2;
+  float* xsum;
 };
 
 template <int V>
@@ -191,12 +198,32 @@ __global__ void __launch_bounds__(256) mar_ln_fwd_kernel(const LnArgs a) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (long long r = (long long)blockIdx.x * 8 + warp; r < a.rows; r += (long long)gridDim.x * 8) {
     float4 v[V];
+    uint2 sh[V], sc[V];  // modulation of this row, requested before the statistics so that its latency overlaps them
     float s = 0.f;
 #pragma unroll
     for (int k = 0; k < V; ++k) {
       v[k] = reinterpret_cast<const float4*>(a.x + r * C)[k * 32 + lane];
-      s += v[k].x + v[k].y + v[k].z + v[k].w;
+      if (a.mod != nullptr) {
+        const int col = (k * 32 + lane) * 4;
+        sh[k] = *reinterpret_cast<const uint2*>(a.mod + r * a.ldmod + a.shift_off + col);
+        sc[k] = *reinterpret_cast<const uint2*>(a.mod + r * a.ldmod + a.scale_off + col);
+      }
     }
+    if (a.h2 != nullptr) {
+#pragma unroll
+      for (int k = 0; k < V; ++k) {
+        const int col = (k * 32 + lane) * 4;
+        const uint2 g = *reinterpret_cast<const uint2*>(a.gmod + r * a.ldg + a.gate_off + col);
+        const uint2 h = *reinterpret_cast<const uint2*>(a.h2 + r * C + col);
+        v[k].x = fmaf(bf16_lo(g.x), bf16_lo(h.x), v[k].x);
+        v[k].y = fmaf(bf16_hi(g.x), bf16_hi(h.x), v[k].y);
+        v[k].z = fmaf(bf16_lo(g.y), bf16_lo(h.y), v[k].z);
+        v[k].w = fmaf(bf16_hi(g.y), bf16_hi(h.y), v[k].w);
+        if (a.xsum != nullptr) *reinterpret_cast<float4*>(a.xsum + r * C + col) = v[k];
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < V; ++k) s += v[k].x + v[k].y + v[k].z + v[k].w;
     const float mean = warp_sum(s) * (1.f / C);
     float q = 0.f;
 #pragma unroll
@@ -219,12 +246,10 @@ __global__ void __launch_bounds__(256) mar_ln_fwd_kernel(const LnArgs a) {
         o[0] = o[0] * gm.x + bt.x; o[1] = o[1] * gm.y + bt.y; o[2] = o[2] * gm.z + bt.z; o[3] = o[3] * gm.w + bt.w;
       }
       if (a.mod != nullptr) {
-        const uint2 sh = *reinterpret_cast<const uint2*>(a.mod + r * a.ldmod + a.shift_off + col);
-        const uint2 sc = *reinterpret_cast<const uint2*>(a.mod + r * a.ldmod + a.scale_off + col);
-        o[0] = o[0] * (1.f + bf16_lo(sc.x)) + bf16_lo(sh.x);
-        o[1] = o[1] * (1.f + bf16_hi(sc.x)) + bf16_hi(sh.x);
-        o[2] = o[2] * (1.f + bf16_lo(sc.y)) + bf16_lo(sh.y);
-        o[3] = o[3] * (1.f + bf16_hi(sc.y)) + bf16_hi(sh.y);
+        o[0] = o[0] * (1.f + bf16_lo(sc[k].x)) + bf16_lo(sh[k].x);
+        o[1] = o[1] * (1.f + bf16_hi(sc[k].x)) + bf16_hi(sh[k].x);
+        o[2] = o[2] * (1.f + bf16_lo(sc[k].y)) + bf16_lo(sh[k].y);
+        o[3] = o[3] * (1.f + bf16_hi(sc[k].y)) + bf16_hi(sh[k].y);
       }
       if (a.add != nullptr) {
         const float4 ad = *reinterpret_cast<const float4*>(a.add + (r % a.add_rows) * C + col);
@@ -753,14 +778,17 @@ extern "C" int hma_mar_embed_bwd(const float* du, const float* xp, const unsigne
 
 extern "C" int hma_mar_ln_fwd(const float* x, int rows, int C, const float* gamma, const float* beta, float eps,
                               const void* mod, long long ldmod, int shift_off, int scale_off, const float* add, int add_rows,
-                              float* y32, void* y16, float* stats, void* stream_) {
+                              float* y32, void* y16, float* stats, const void* gmod, long long ldg, int gate_off,
+                              const void* h2, float* xsum, void* stream_) {
   if (rows == 0) return 0;
+  HMA_REQUIRE(h2 == nullptr || (gmod != nullptr && ldg % 4 == 0 && gate_off % 4 == 0), "mar_ln_fwd: fused gate needs gmod");
   HMA_REQUIRE(C == 256 || C == 1024, "mar_ln_fwd: width %d is not supported (256 or 1024)", C);
   HMA_REQUIRE((gamma == nullptr) == (beta == nullptr), "mar_ln_fwd: gamma and beta go together");
   HMA_REQUIRE(mod == nullptr || (ldmod % 4 == 0 && shift_off % 4 == 0 && scale_off % 4 == 0), "mar_ln_fwd: unaligned mod");
   HMA_REQUIRE(add == nullptr || add_rows > 0, "mar_ln_fwd: add_rows");
   LnArgs a{x, rows, gamma, beta, eps, static_cast<const __nv_bfloat16*>(mod), ldmod, shift_off, scale_off, add, add_rows,
-           y32, static_cast<__nv_bfloat16*>(y16), stats};
+           y32, static_cast<__nv_bfloat16*>(y16), stats, static_cast<const __nv_bfloat16*>(gmod), ldg, gate_off,
+           static_cast<const __nv_bfloat16*>(h2), xsum};
   const int grid = grid_for(rows, 8, 8);
   if (C == 256)
     HMA_CHECK_CUDA(hma_host::launch_pdl(mar_ln_fwd_kernel<2>, dim3(grid), dim3(256), 0, STREAM, a));

@@ -320,6 +320,8 @@ class MarEngine(Engine):
         n, Wp, cfg = self.NET, self.weights.plain, self.cfg
         w = cfg.diffloss_w
         x = ops.gemm_nt(x16, self._pad["in"], EPI_RESID, bias=p[n + "input_proj.bias"])
+        fuse = keep is None  # inference: the gate of block i (x + gate * h2) is applied inside the LayerNorm of block i + 1
+        pend = None          # (mod, gate offset, h2, destination) of the gate not yet applied
         for i in range(cfg.diffloss_d):
             q = n + f"res_blocks.{i}."
             if mods is not None:
@@ -327,10 +329,15 @@ class MarEngine(Engine):
             else:
                 mod = ops.gemm_nt(sy, Wp[q + "adaLN_modulation.1.weight"], EPI_BF16, bias=p[q + "adaLN_modulation.1.bias"])
             _, u16, st = ops.mar_ln_fwd(x, gamma=p[q + "in_ln.weight"], beta=p[q + "in_ln.bias"], eps=1e-6, mod=mod, shift_off=0,
-                                        scale_off=w, want_stats=keep is not None)
+                                        scale_off=w, want_stats=keep is not None, gate=pend)
+            if pend is not None:
+                x, pend = pend[3], None
             za = torch.empty(x.shape[0], w, device=x.device, dtype=torch.bfloat16) if keep is not None else None
             a = ops.gemm_nt(u16, Wp[q + "mlp.0.weight"], EPI_SILU, bias=p[q + "mlp.0.bias"], out2=za)
             h2 = ops.gemm_nt(a, Wp[q + "mlp.2.weight"], EPI_BF16, bias=p[q + "mlp.2.bias"])
+            if fuse:
+                pend = (mod, 2 * w, h2, torch.empty_like(x))
+                continue
             xn = ops.mar_gate_fwd(x, mod, 2 * w, h2)
             if keep is not None:
                 keep.append(dict(x=x, mod=mod, u16=u16, st=st, za=za, a=a, h2=h2))
@@ -340,7 +347,7 @@ class MarEngine(Engine):
             modf = mods[:, 3 * w * cfg.diffloss_d:]
         else:
             modf = ops.gemm_nt(sy, Wp[q + "adaLN_modulation.1.weight"], EPI_BF16, bias=p[q + "adaLN_modulation.1.bias"])
-        _, uf16, stf = ops.mar_ln_fwd(x, eps=1e-6, mod=modf, shift_off=0, scale_off=w, want_stats=keep is not None)
+        _, uf16, stf = ops.mar_ln_fwd(x, eps=1e-6, mod=modf, shift_off=0, scale_off=w, want_stats=keep is not None, gate=pend)
         out = ops.gemm_nt(uf16, self._pad["fl"], EPI_RESID, bias=self._pad["fl_bias"])
         if keep is not None:
             keep.append(dict(x=x, mod=modf, u16=uf16, st=stf))

@@ -353,8 +353,9 @@ def mar_embed_bwd(du, xp, mask_u8, We, pos_n: int, B: int, T: int, H: int, W: in
 
 
 def mar_ln_fwd(x: torch.Tensor, *, gamma=None, beta=None, eps: float = 1e-6, mod=None, shift_off: int = 0, scale_off: int = 0,
-               add=None, want32: bool = False, want16: bool = True, want_stats: bool = False):
-    """LayerNorm over the last dim (256 or 1024) of fp32 x, optional affine / bf16 modulation / additive row table."""
+               add=None, want32: bool = False, want16: bool = True, want_stats: bool = False, gate=None):
+    """LayerNorm over the last dim (256 or 1024) of fp32 x, optional affine / bf16 modulation / additive row table.
+    gate = (gmod, gate_off, h2, xsum): normalise x + gmod[:, gate_off:] * h2 instead and write that sum to xsum."""
     assert x.dtype == F32 and x.is_contiguous() and x.dim() == 2
     rows, C = x.shape
     y32 = torch.empty(rows, C, device=x.device, dtype=F32) if want32 else None
@@ -364,7 +365,9 @@ def mar_ln_fwd(x: torch.Tensor, *, gamma=None, beta=None, eps: float = 1e-6, mod
         assert add.dtype == F32 and add.is_contiguous() and add.shape[-1] == C
     _call(f"mar_ln_fwd[{C}]", rows * C * 6.0, "hma_mar_ln_fwd", x.data_ptr(), rows, C, _p(gamma), _p(beta), float(eps), _p(mod),
           mod.stride(0) if mod is not None else 0, shift_off, scale_off, _p(add),
-          add.numel() // C if add is not None else 0, _p(y32), _p(y16), _p(stats), _s())
+          add.numel() // C if add is not None else 0, _p(y32), _p(y16), _p(stats),
+          gate[0].data_ptr() if gate else None, gate[0].stride(0) if gate else 0, gate[1] if gate else 0,
+          gate[2].data_ptr() if gate else None, gate[3].data_ptr() if gate else None, _s())
     return y32, y16, stats
 
 

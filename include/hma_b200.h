@@ -229,10 +229,12 @@ int hma_mar_embed_bwd(const float* du, const float* xp, const unsigned char* mas
                       void* stream);
 /* y = LN_C(x)[*gamma + beta][*(1 + mod[scale_off..]) + mod[shift_off..]][+ add[row % add_rows]]; C in {256, 1024}.
  * z_proj_ln / decoder_norm + diffusion_pos_embed_learned (st_mar.py:174,190-191); ResBlock.in_ln + modulate and
- * FinalLayer (diffloss.py:116-159). Outputs y32 and/or y16 (bf16); stats fp32 [rows,2] = mean, rstd (optional). */
+ * FinalLayer (diffloss.py:116-159). Outputs y32 and/or y16 (bf16); stats fp32 [rows,2] = mean, rstd (optional).
+ * Optional fused residual gate of the previous ResBlock (diffloss.py:140): with h2 != NULL the row normalised is
+ * x + gmod[gate_off..] * h2 (bf16 gate and h2), also written to xsum (fp32, may alias nothing else). */
 int hma_mar_ln_fwd(const float* x, int rows, int C, const float* gamma, const float* beta, float eps, const void* mod,
                    long long ldmod, int shift_off, int scale_off, const float* add, int add_rows, float* y32, void* y16,
-                   float* stats, void* stream);
+                   float* stats, const void* gmod, long long ldg, int gate_off, const void* h2, float* xsum, void* stream);
 /* Backward of the above from dy16 (bf16) or dy32: dx32 (optionally accumulated) and/or dx16; dgamma/dbeta accumulated;
  * dmod (bf16 [rows, lddmod]) receives dshift and dscale at the same offsets; dadd[row % add_rows] accumulated. */
 int hma_mar_ln_bwd(const void* dy16, const float* dy32, const float* x, const float* stats, int rows, int C,

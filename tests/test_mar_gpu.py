@@ -559,3 +559,21 @@ def test_mar_incremental_decode_matches_full_window():
     model.decode_algorithm = "full"
     b = model.maskgit_generate(r["gen_prompt"].to(DEV), cfg.T - 1, maskgit_steps=1, temperature=1.0, _orders=r["gen_orders"])
     assert rel(a[1], b[1]) <= 1e-2
+
+
+def test_mar_ln_fused_gate_equals_separate_kernels():
+    """LayerNorm with the previous block's residual gate fused in (inference path of the diffusion MLP) == gate kernel
+    followed by the plain LayerNorm, bit for bit."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(13)
+    N, C = 200, 1024
+    x = torch.randn(N, C, generator=g).to(DEV)
+    prev = (torch.randn(N, 3 * C, generator=g) * 0.5).bfloat16().to(DEV)
+    mod = (torch.randn(N, 3 * C, generator=g) * 0.5).bfloat16().to(DEV)
+    h2 = torch.randn(N, C, generator=g).bfloat16().to(DEV)
+    gamma, beta = (1 + 0.1 * torch.randn(C, generator=g)).to(DEV), (0.1 * torch.randn(C, generator=g)).to(DEV)
+    xs = ops.mar_gate_fwd(x, prev, 2 * C, h2)
+    _, want, _ = ops.mar_ln_fwd(xs, gamma=gamma, beta=beta, eps=1e-6, mod=mod, shift_off=0, scale_off=C)
+    xsum = torch.empty_like(x)
+    _, got, _ = ops.mar_ln_fwd(x, gamma=gamma, beta=beta, eps=1e-6, mod=mod, shift_off=0, scale_off=C, gate=(prev, 2 * C, h2, xsum))
+    assert torch.equal(xsum, xs) and torch.equal(got, want)
