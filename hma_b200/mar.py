@@ -22,8 +22,9 @@ import torch.nn as nn
 from . import ops
 from .config import GenieConfig
 from .engine import Dims, Engine
-from .model import ModelOutput, STMaskGIT, _LazyParams, _xavier
+from .model import ModelOutput, STMaskGIT, _xavier
 from .ops import EPI_BF16, EPI_DSILU, EPI_RESID, EPI_SILU
+from .train import TrainStep
 
 Tensor = torch.Tensor
 KPAD = 128  # the token vector (D <= 64) and the 2D-wide output are zero-padded to one 128-column GEMM tile
@@ -903,9 +904,6 @@ class STMAR(STMaskGIT):
 # ------------------------------------------------------------------------------------------------
 # training step without autograd in the loop (the STMAR counterpart of train.TrainStep)
 # ------------------------------------------------------------------------------------------------
-from .train import TrainStep  # noqa: E402
-
-
 class MarTrainStep(TrainStep):
     """One optimisation step of STMAR (train_multi.py:556-598 with the continuous model): forward + diffusion loss +
     backward into the flat gradient buffer, then the shared gradient exchange / clip / AdamW tail of TrainStep.
