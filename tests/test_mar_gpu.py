@@ -577,3 +577,39 @@ def test_mar_ln_fused_gate_equals_separate_kernels():
     xsum = torch.empty_like(x)
     _, got, _ = ops.mar_ln_fwd(x, gamma=gamma, beta=beta, eps=1e-6, mod=mod, shift_off=0, scale_off=C, gate=(prev, 2 * C, h2, xsum))
     assert torch.equal(xsum, xs) and torch.equal(got, want)
+
+
+def test_mar_edge_cases_against_oracle():
+    """No actions (64 tokens per frame, no modulation), a window shorter than config.T, an all-false and an all-true mask."""
+    rec, cfg, sd = mar_golden()
+    model = build_model(rec, sd).eval()
+    dom = rec["domains"][0]
+    r = rec[dom]
+    B = 2
+    lat = r["latents"]
+    # (1) no actions
+    with torch.no_grad():
+        out = model(lat.to(DEV).clone(), lat.to(DEV), masked_tokens_indicator=r["mask"].to(DEV), h=[H], w=[W], _t=r["t"].to(DEV),
+                    _noise=r["noise"].to(DEV))
+    loss, z = M.forward(lat, lat, r["mask"], None, None, sd, cfg, r["t"], r["noise"], H, W)
+    assert math.isclose(out.loss.item(), loss.item(), rel_tol=1e-2), (out.loss.item(), loss.item())
+    assert rel(out.logits.permute(0, 2, 3, 4, 1).reshape(z.shape), z) <= 2e-2
+    # (2) three frames of a T = 4 model through compute_latents
+    x3 = M.patchify(lat.reshape(B, cfg.T, H, W, -1)[:, :3], 2)
+    z3 = M.compute_latents(x3, r["actions"][:, :3], [dom, dom], sd, cfg)
+    got, _ = model.compute_latents(x3.to(DEV), action_ids=r["actions"][:, :3].to(DEV), domain=[dom, dom])
+    assert rel(got.permute(0, 2, 3, 4, 1).reshape(z3.shape), z3) <= 2e-2
+    # (3) masks: nothing masked -> loss 0 (0 / (0 + 1e-8), diffloss.py:34) and zero gradients; everything masked
+    model.train()
+    for full in (False, True):
+        mask = torch.full_like(r["mask"], full)
+        model.zero_grad()
+        o = model(lat.to(DEV).clone(), lat.to(DEV), action_ids=r["actions"].to(DEV), domain=[dom, dom],
+                  masked_tokens_indicator=mask.to(DEV), h=[H], w=[W], _t=r["t"].to(DEV), _noise=r["noise"].to(DEV))
+        o.loss.backward()
+        want, _ = M.forward(lat, lat, mask, r["actions"], [dom, dom], sd, cfg, r["t"], r["noise"], H, W)
+        gmax = max(p.grad.abs().max().item() for p in model.parameters() if p.grad is not None)
+        if full:
+            assert math.isclose(o.loss.item(), want.item(), rel_tol=1e-2) and gmax > 0
+        else:
+            assert o.loss.item() == 0.0 == want.item() and gmax == 0.0
