@@ -296,23 +296,38 @@ __global__ void __launch_bounds__(256) mar_ln_bwd_kernel(const LnBwdArgs a) {
 #pragma unroll
     for (int e = 0; e < 4; ++e) dg[k][e] = db[k][e] = 0.f;
   for (long long r = (long long)blockIdx.x * 8 + warp; r < a.rows; r += (long long)gridDim.x * 8) {
-    const float mean = a.stats[r * 2], rstd = a.stats[r * 2 + 1];
+    // Phase 1: every load of the row is issued up front through the read-only path. (With plain loads interleaved with
+    // the dmod / dx stores below the compiler had to keep program order — possible aliasing — which serialised eight
+    // DRAM round trips per row: 115 us for 6144 rows of 1024.)
+    const float mean = __ldg(a.stats + r * 2), rstd = __ldg(a.stats + r * 2 + 1);
+    float4 xv[V], gv[V];
+    uint2 sc[V];
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+      const int col = (k * 32 + lane) * 4;
+      xv[k] = __ldg(reinterpret_cast<const float4*>(a.x + r * C + col));
+      if (a.dy16 != nullptr) {
+        const uint2 w = __ldg(reinterpret_cast<const uint2*>(a.dy16 + r * C + col));
+        gv[k] = make_float4(bf16_lo(w.x), bf16_hi(w.x), bf16_lo(w.y), bf16_hi(w.y));
+      } else {
+        gv[k] = __ldg(reinterpret_cast<const float4*>(a.dy32 + r * C + col));
+      }
+      if (a.mod != nullptr) sc[k] = __ldg(reinterpret_cast<const uint2*>(a.mod + r * a.ldmod + a.scale_off + col));
+    }
+    float4 old[V];
+    if (a.dx32 != nullptr && a.accumulate) {
+#pragma unroll
+      for (int k = 0; k < V; ++k) old[k] = *reinterpret_cast<const float4*>(a.dx32 + r * C + (k * 32 + lane) * 4);
+    }
+    // Phase 2: arithmetic + the modulation-gradient stores
     float dxn[V][4], xn[V][4];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int k = 0; k < V; ++k) {
       const int col = (k * 32 + lane) * 4;
-      float g[4];
-      if (a.dy16 != nullptr) {
-        const uint2 w = *reinterpret_cast<const uint2*>(a.dy16 + r * C + col);
-        g[0] = bf16_lo(w.x); g[1] = bf16_hi(w.x); g[2] = bf16_lo(w.y); g[3] = bf16_hi(w.y);
-      } else {
-        const float4 w = *reinterpret_cast<const float4*>(a.dy32 + r * C + col);
-        g[0] = w.x; g[1] = w.y; g[2] = w.z; g[3] = w.w;
-      }
-      const float4 xv = *reinterpret_cast<const float4*>(a.x + r * C + col);
-      xn[k][0] = (xv.x - mean) * rstd; xn[k][1] = (xv.y - mean) * rstd;
-      xn[k][2] = (xv.z - mean) * rstd; xn[k][3] = (xv.w - mean) * rstd;
+      const float g[4] = {gv[k].x, gv[k].y, gv[k].z, gv[k].w};
+      xn[k][0] = (xv[k].x - mean) * rstd; xn[k][1] = (xv[k].y - mean) * rstd;
+      xn[k][2] = (xv[k].z - mean) * rstd; xn[k][3] = (xv[k].w - mean) * rstd;
       if (a.dadd != nullptr) {
         float* dst = a.dadd + (r % a.add_rows) * C + col;
 #pragma unroll
@@ -320,15 +335,14 @@ __global__ void __launch_bounds__(256) mar_ln_bwd_kernel(const LnBwdArgs a) {
       }
       float gm[4] = {1.f, 1.f, 1.f, 1.f}, bt[4] = {0.f, 0.f, 0.f, 0.f};
       if (a.gamma != nullptr) {
-        const float4 g4 = *reinterpret_cast<const float4*>(a.gamma + col);
-        const float4 b4 = *reinterpret_cast<const float4*>(a.beta + col);
+        const float4 g4 = __ldg(reinterpret_cast<const float4*>(a.gamma + col));
+        const float4 b4 = __ldg(reinterpret_cast<const float4*>(a.beta + col));
         gm[0] = g4.x; gm[1] = g4.y; gm[2] = g4.z; gm[3] = g4.w;
         bt[0] = b4.x; bt[1] = b4.y; bt[2] = b4.z; bt[3] = b4.w;
       }
       float da[4] = {g[0], g[1], g[2], g[3]};
       if (a.mod != nullptr) {
-        const uint2 sc = *reinterpret_cast<const uint2*>(a.mod + r * a.ldmod + a.scale_off + col);
-        const float scl[4] = {bf16_lo(sc.x), bf16_hi(sc.x), bf16_lo(sc.y), bf16_hi(sc.y)};
+        const float scl[4] = {bf16_lo(sc[k].x), bf16_hi(sc[k].x), bf16_lo(sc[k].y), bf16_hi(sc[k].y)};
         float dsc[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
@@ -360,12 +374,10 @@ __global__ void __launch_bounds__(256) mar_ln_bwd_kernel(const LnBwdArgs a) {
 #pragma unroll
       for (int e = 0; e < 4; ++e) o[e] = rstd * (dxn[k][e] - s1 - xn[k][e] * s2);
       if (a.dx32 != nullptr) {
-        float4* dst = reinterpret_cast<float4*>(a.dx32 + r * C + col);
         if (a.accumulate) {
-          const float4 old = *dst;
-          o[0] += old.x; o[1] += old.y; o[2] += old.z; o[3] += old.w;
+          o[0] += old[k].x; o[1] += old[k].y; o[2] += old[k].z; o[3] += old[k].w;
         }
-        *dst = make_float4(o[0], o[1], o[2], o[3]);
+        *reinterpret_cast<float4*>(a.dx32 + r * C + col) = make_float4(o[0], o[1], o[2], o[3]);
       }
       if (a.dx16 != nullptr)
         *reinterpret_cast<uint2*>(a.dx16 + r * C + col) = make_uint2(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]));
@@ -813,7 +825,7 @@ extern "C" int hma_mar_ln_bwd(const void* dy16, const float* dy32, const float* 
   LnBwdArgs a{static_cast<const __nv_bfloat16*>(dy16), dy32, x, stats, rows, gamma, beta,
               static_cast<const __nv_bfloat16*>(mod), ldmod, shift_off, scale_off, dx32, accumulate,
               static_cast<__nv_bfloat16*>(dx16), dgamma, dbeta, static_cast<__nv_bfloat16*>(dmod), lddmod, dadd, add_rows};
-  const int grid = grid_for(rows, 32, 2);
+  const int grid = grid_for(rows, 8, 2);  // one resident CTA per SM at C = 1024 (registers): two full waves at most
   if (C == 256)
     HMA_CHECK_CUDA(hma_host::launch_pdl(mar_ln_bwd_kernel<2>, dim3(grid), dim3(256), 0, STREAM, a));
   else
