@@ -11,7 +11,8 @@ from .config import GenieConfig  # noqa: F401
 
 
 _LAZY = {"STMaskGIT": "model", "STMAR": "mar", "DiffusionGenieConfig": "mar", "MarTrainStep": "mar", "TrainStep": "train",
-         "RawTokenDataset": "dataset", "get_maskgit_collator": "data"}
+         "RawTokenDataset": "dataset", "get_maskgit_collator": "data", "MultiTaskBatchSampler": "sampler",
+         "DeviceBatchPipeline": "sampler"}
 
 
 def __getattr__(name):
