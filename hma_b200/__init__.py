@@ -11,7 +11,7 @@ from .config import GenieConfig  # noqa: F401
 
 
 _LAZY = {"STMaskGIT": "model", "STMAR": "mar", "DiffusionGenieConfig": "mar", "MarTrainStep": "mar", "TrainStep": "train",
-         "RawTokenDataset": "dataset", "get_maskgit_collator": "data", "MultiTaskBatchSampler": "sampler",
+         "RawTokenDataset": "dataset", "RawFeatureDataset": "dataset", "get_maskgit_collator_feature": "data", "get_maskgit_collator": "data", "MultiTaskBatchSampler": "sampler",
          "DeviceBatchPipeline": "sampler"}
 
 

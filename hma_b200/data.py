@@ -91,3 +91,50 @@ def get_maskgit_collator(config, device="cuda"):
         return out
 
     return collate_fn
+
+
+def cosine_schedule(u: torch.Tensor) -> torch.Tensor:
+    """hma/data.py cosine_schedule (st_mask_git.py:116-125 on tensors): cos(pi/2 * u)."""
+    return torch.cos(u * math.pi / 2)  # same association as the reference: (u * pi) / 2
+
+
+def get_maskgit_collator_feature(config, device=None):
+    """Drop-in for the reference's continuous-latent collator (hma/data.py:100-157), which STMAR training uses: the latents
+    pass through unchanged (input_ids, labels = a copy) and `masked_tokens_indicator` [B, T, h, w] marks, for the frames
+    from `first_masked_frame` on, the positions drawn with a per-(sample, frame) cosine-schedule rate — STMAR.forward puts
+    its mask token there (st_mar.py:240). Same consumption of Python's `random` and of torch's default generator as the
+    reference (so the same seeds give the same masks); with `device` set the batch is moved there first and the tensor
+    draws happen on that device."""
+    def collate_fn(features: List[dict]) -> Dict[str, object]:
+        h, w = features[0]["h"], features[0]["w"]
+        B, T = len(features), config.T
+        input_ids = torch.stack([ex["input_ids"] for ex in features])
+        if device is not None:
+            input_ids = input_ids.to(device, non_blocking=True)
+        dev = input_ids.device
+        x = input_ids.reshape(B, T, h, w, -1)
+        first_masked_frame = T
+        mask = torch.zeros(1).long()
+        indicator = torch.zeros((B, T, h, w)).long()
+        if config.dataloader_apply_mask:
+            if random.random() < config.non_mlm_ratio:
+                first_masked_frame = random.randint(config.num_prompt_frames, T - 1)
+            else:
+                first_masked_frame = 1
+            while mask.max() == 0:  # "we could get unlucky and mask no tokens"
+                rand = torch.rand(B, T - first_masked_frame, 1, 1, device=dev if device is not None else None)
+                rate = cosine_schedule(rand * (1 - config.dataloader_mask_ratio_min) + config.dataloader_mask_ratio_min)
+                r = torch.rand_like(x[:, first_masked_frame:, ..., 0], dtype=torch.float)
+                mask = r < rate.to(r.device)
+            indicator = torch.cat([torch.zeros((B, first_masked_frame, h, w), dtype=mask.dtype, device=mask.device), mask], dim=1)
+        out: Dict[str, object] = {"input_ids": x.reshape(B, T * h * w, -1), "labels": x.clone().reshape(B, T * h * w, -1),
+                                  "masked_tokens_indicator": indicator}
+        if "action_ids" in features[0]:
+            a = torch.stack([ex["action_ids"] for ex in features])
+            out["action_ids"] = a.to(device, non_blocking=True) if device is not None else a
+        out["domain"] = [ex["domain"] for ex in features]
+        out["h"] = [ex["h"] for ex in features]
+        out["w"] = [ex["w"] for ex in features]
+        return out
+
+    return collate_fn

@@ -27,6 +27,9 @@ import torch
 from . import _lib, ops
 
 
+SVD_SCALE = 0.18215  # hma/data.py:16: latent scaling of the continuous (SVD-VAE) features
+
+
 def normalize_actions(actions: np.ndarray):
     """data.py:18-24: statistics only; the normalisation itself happens inside the network (ActionStat)."""
     return actions, [np.mean(actions, axis=0).tolist(), np.std(actions, axis=0).tolist()]
@@ -152,4 +155,69 @@ class RawTokenDataset(torch.utils.data.Dataset):
         out["domain"] = [self.name] * B
         out["h"] = [h] * B
         out["w"] = [w] * B
+        return out
+
+
+class RawFeatureDataset(torch.utils.data.Dataset):
+    """The continuous-latent sibling (hma/data.py:297-435), read by STMAR training: `video.bin` holds
+    token_dtype (float16 by default) [num_images, latent_channels, h, w]; an item is the window scaled by SVD_SCALE and laid
+    out "(t h w) c". Host path only (CPU tensors, for a torch DataLoader); same constructor arguments and quirks as the
+    reference: `max_traj_num` caps the NUMBER of valid windows here (data.py:383-384), not the segment id, and "_noquant" is
+    stripped from the domain name."""
+
+    def __init__(self, data_dir, window_size, stride=1, filter_interrupts=True, filter_overlaps=False, use_actions=False,
+                 max_traj_num=1000000, compute_stride_from_freq_table=True, natural_hz=2, datio_noise_ratio=0.0,
+                 use_raw_image_as_latent=False, domain=None, freq_table: Optional[Dict[str, int]] = None):
+        data_dir = Path(data_dir)
+        with open(data_dir / "metadata.json") as f:
+            self.metadata = json.load(f)
+        n_img = self.metadata["num_images"]
+        shape = (n_img, self.metadata.get("latent_channels", 4), self.metadata["h"], self.metadata["w"])
+        self.data = np.memmap(data_dir / "video.bin", mode="r", shape=shape, dtype=np.dtype(self.metadata.get("token_dtype", "float16")))
+        self.window_size, self.stride = window_size, stride
+        self.datio_noise_ratio = datio_noise_ratio
+        self.name = (domain if domain is not None else self.metadata["name"]).replace("_noquant", "")
+        if compute_stride_from_freq_table:
+            if freq_table is not None:
+                hz = freq_table.get(self.name, 1)
+            else:
+                own = str(self.metadata.get("name", self.name)).replace("_noquant", "")
+                hz = self.metadata.get("hz", 1) if self.name == own else 1
+            self.stride = max(hz // natural_hz, 1)
+        self.n_action = self.metadata.get("action_dim", 1) * self.stride
+        if use_actions:
+            parts = [np.memmap(fn, dtype=np.float32, mode="r").reshape(len(self.data), -1)
+                     for fn in sorted((data_dir / "actions").iterdir())]
+            self.actions, self.action_stat = normalize_actions(np.concatenate(parts, axis=-1))
+        seg_path = data_dir / "segment_ids.bin"
+        if os.path.isfile(seg_path):
+            self.segment_ids = np.memmap(seg_path, dtype=np.int32, mode="r", shape=(n_img,))
+        else:
+            self.segment_ids = None
+            if filter_interrupts:
+                raise NotImplementedError("Cannot filter interrupted sequences without segment ids.")
+        self.video_len = (self.window_size - 1) * self.stride
+        n = max(len(self.data) - self.video_len - self.stride, 0)
+        starts = np.arange(n)
+        if filter_interrupts and n:
+            seg = np.asarray(self.segment_ids)
+            starts = starts[seg[:n] == seg[self.video_len: self.video_len + n]]
+        # the reference appends, then stops once it holds max_traj_num windows (max_traj_num <= 0 still keeps the first)
+        self.valid_start_inds = starts[: max(int(max_traj_num), 1)].tolist() if len(starts) else []
+        if filter_overlaps:
+            self.valid_start_inds = RawTokenDataset._drop_overlaps(self, self.valid_start_inds)
+
+    def __len__(self):
+        return len(self.valid_start_inds)
+
+    def __getitem__(self, idx):
+        start = self.valid_start_inds[idx]
+        x = torch.from_numpy(self.data[start: start + self.video_len + 1: self.stride].astype(np.float32)) * SVD_SCALE
+        x = x.permute(0, 2, 3, 1).reshape(-1, x.shape[1])  # "t c h w -> (t h w) c"
+        out = {"input_ids": x, "labels": x, "attention_mask": torch.ones_like(x), "h": self.metadata["h"], "w": self.metadata["w"],
+               "c": self.metadata["latent_channels"]}
+        if hasattr(self, "actions"):
+            a = self.actions[start: start + self.video_len + self.stride].reshape(self.window_size, -1)
+            out["action_ids"] = torch.from_numpy(a.astype(np.float32))
+        out["domain"] = self.name.replace("_noquant", "")
         return out

@@ -31,12 +31,12 @@ def reference_dataset_class(freq):
     sys.modules["datasets"] = pkg
     sys.modules["datasets.encode_openx_dataset"] = stub
     sys.modules.pop("hma.data", None)
-    from hma.data import RawTokenDataset
-    return RawTokenDataset
+    import hma.data as D
+    return D.RawTokenDataset, D
 
 
 def main():
-    Ref = reference_dataset_class({"synthetic_robot": 6})
+    Ref, D = reference_dataset_class({"synthetic_robot": 6})
     out = {}
     with tempfile.TemporaryDirectory() as tmp:
         root = _rawdata.write(Path(tmp) / "ds", seed=0)
@@ -52,6 +52,31 @@ def main():
                          "action_ids": torch.stack([it["action_ids"] for it in items]) if "action_ids" in items[0] else None,
                          "action_stat": getattr(ds, "action_stat", None), "domain": items[0]["domain"]}
             print(name, len(ds), ds.stride, ds.n_action)
+    # continuous-latent dataset + its collator (hma/data.py:297-435, 100-157)
+    import random
+
+    from hma.config import DiffusionGenieConfig
+    with tempfile.TemporaryDirectory() as tmp:
+        root = _rawdata.write(Path(tmp) / "feat", seed=3, token_dtype="float16", latent_channels=4, h=8, w=8)
+        for name, kw in _rawdata.FEATURE_CASES.items():
+            with contextlib.redirect_stdout(io.StringIO()):
+                ds = D.RawFeatureDataset(root, **kw)
+            idx = sorted(set([0, 1, len(ds) // 2, len(ds) - 1]))
+            items = [ds[i] for i in idx]
+            rec = {"valid_start_inds": list(map(int, ds.valid_start_inds)), "len": len(ds), "stride": ds.stride, "n_action": ds.n_action,
+                   "idx": idx, "input_ids": torch.stack([it["input_ids"] for it in items]),
+                   "action_ids": torch.stack([it["action_ids"] for it in items]) if "action_ids" in items[0] else None,
+                   "domain": items[0]["domain"], "c": items[0]["c"]}
+            for tag, cfg_kw, seed in (("mlm", dict(non_mlm_ratio=0.0), 5), ("non_mlm", dict(non_mlm_ratio=1.0, num_prompt_frames=1), 9)):
+                cfg = DiffusionGenieConfig(num_layers=1, num_heads=8, d_model=256, T=kw["window_size"], **cfg_kw)
+                torch.manual_seed(seed); random.seed(seed)
+                with contextlib.redirect_stdout(io.StringIO()):
+                    b = D.get_maskgit_collator_feature(cfg)(items)
+                rec[f"collate_{tag}"] = {"cfg": dict(T=kw["window_size"], **cfg_kw), "seed": seed,
+                                         "masked_tokens_indicator": b["masked_tokens_indicator"].clone(),
+                                         "input_ids_shape": tuple(b["input_ids"].shape)}
+            out["feature_" + name] = rec
+            print("feature", name, len(ds), ds.stride, ds.n_action, rec["collate_mlm"]["masked_tokens_indicator"].float().mean().item())
     path = ROOT / "tests" / "golden" / "rawtoken.pt"
     torch.save(out, path)
     print("wrote", path, path.stat().st_size)

@@ -72,3 +72,40 @@ def test_device_gather_equals_host_items(tmp_path, dtype):
     if dtype == "uint32":
         ids, labels = collate_from_draws(out["input_ids"], draw_on_device(cfg, 33, 16, 16, torch.device("cuda")), cfg, 16, 16)
         assert torch.equal(labels, out["input_ids"]) and (ids == cfg.image_vocab_size).any()
+
+
+@pytest.fixture(scope="module")
+def feature_root(tmp_path_factory):
+    return _rawdata.write(tmp_path_factory.mktemp("rawfeat") / "feat", seed=3, token_dtype="float16", latent_channels=4, h=8, w=8)
+
+
+@pytest.mark.parametrize("case", list(_rawdata.FEATURE_CASES))
+def test_feature_dataset_and_collator_match_reference_fixture(feature_root, case):
+    """RawFeatureDataset (hma/data.py:297-435) and get_maskgit_collator_feature (:100-157), the STMAR data path: same windows,
+    same items, and — seeding torch and `random` as the fixture did — the same masked_tokens_indicator."""
+    import random
+
+    from hma_b200.data import get_maskgit_collator_feature
+    from hma_b200.dataset import RawFeatureDataset
+    from hma_b200.mar import DiffusionGenieConfig
+
+    ref = torch.load(GOLDEN, weights_only=False)["feature_" + case]
+    ds = RawFeatureDataset(feature_root, **_rawdata.FEATURE_CASES[case])
+    assert ds.stride == ref["stride"] and ds.n_action == ref["n_action"]
+    assert len(ds) == ref["len"] and list(ds.valid_start_inds) == ref["valid_start_inds"]
+    items = [ds[i] for i in ref["idx"]]
+    assert torch.equal(torch.stack([it["input_ids"] for it in items]), ref["input_ids"])
+    assert items[0]["domain"] == ref["domain"] and items[0]["c"] == ref["c"] and "_noquant" not in items[0]["domain"]
+    if ref["action_ids"] is not None:
+        assert torch.equal(torch.stack([it["action_ids"] for it in items]), ref["action_ids"])
+    for tag in ("mlm", "non_mlm"):
+        c = ref[f"collate_{tag}"]
+        cfg = DiffusionGenieConfig(num_layers=1, num_heads=8, d_model=256, **c["cfg"])
+        torch.manual_seed(c["seed"])
+        random.seed(c["seed"])
+        b = get_maskgit_collator_feature(cfg)(items)
+        assert torch.equal(b["masked_tokens_indicator"], c["masked_tokens_indicator"])
+        assert tuple(b["input_ids"].shape) == c["input_ids_shape"]
+        assert torch.equal(b["input_ids"], torch.stack([it["input_ids"] for it in items]))
+        assert torch.equal(b["labels"], b["input_ids"]) and b["labels"].data_ptr() != b["input_ids"].data_ptr()
+        assert b["domain"] == [ref["domain"]] * len(items) and b["h"] == [8] * len(items)
