@@ -92,3 +92,45 @@ def test_no_cpu_fallback():
         m.maskgit_generate(r["gen_prompt"], cfg.T - 1, action_ids=r["actions"], domain=["dom00", "dom00"], maskgit_steps=1)
     with pytest.raises(NotImplementedError):
         m.maskgit_generate(r["gen_prompt"], cfg.T - 1, cfg=2.0)
+
+
+def test_param_arena_layout_for_stmar():
+    """MarTrainStep's flat parameter arena (train.ParamArena) on CPU: every parameter becomes a view of the arena with its
+    values intact, the shared block holds trunk + front end + latent head + diffusion MLP, each action domain has its own
+    contiguous block, and the never-executed per-domain action heads sit behind them."""
+    from hma_b200.train import ParamArena
+
+    rec, cfg, sd = mar_golden()
+    m = _model(rec)
+    m.load_state_dict(sd, strict=False)
+    before = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    arena = ParamArena(m)
+    named = dict(m.named_parameters())
+    flat = arena.flat
+    for k, p in named.items():
+        off = arena.offsets[k]
+        assert p.data_ptr() == flat.data_ptr() + 4 * off and off % 4 == 0, k
+        assert torch.equal(p.detach(), before[k]), k
+    assert set(arena.dom_range) == set(rec["domains"])
+    shared = [k for k, o in arena.offsets.items() if o < arena.shared_size]
+    assert any(k.startswith("diffloss.net.res_blocks.1.") for k in shared) and "mask_token" in shared
+    assert "diffusion_pos_embed_learned" in shared and "decoder_norm.weight" in shared and "z_proj_ln.bias" in shared
+    assert not any("action_projectors" in k or k.startswith("action_mlp.") or k.startswith("action_diff_losses.") for k in shared)
+    end_of_domains = max(lo + n for lo, n in arena.dom_range.values())
+    for dom, (lo, n) in arena.dom_range.items():
+        mine = [k for k, o in arena.offsets.items() if lo <= o < lo + n]
+        assert mine and all(dom in k for k in mine), dom
+        assert any("adaLN_modulation" in k for k in mine) and any(k.startswith(f"action_mlp.{dom}.") for k in mine)
+    left = [k for k, o in arena.offsets.items() if o >= end_of_domains]
+    assert left and all(k.startswith("action_diff_losses.") or k == "action_mask_tokens" for k in left), left[:5]
+    # the engine's gradient buffer uses the same intra-block order as the arena (optimizer = streaming kernels over ranges)
+    eng = m._engine
+    d = eng.mar_dims(2, cfg.T, 16, 16, True)
+    names = eng.active_param_names(named, d, rec["domains"][1], True)
+    offs = [arena.offsets[k] for k in names]
+    lo1 = arena.dom_range[rec["domains"][1]][0]
+    rel = [o if o < arena.shared_size else o - lo1 + arena.shared_size for o in offs]
+    assert rel == sorted(rel) and rel[0] == 0
+    g = eng.alloc_grads(named, d, rec["domains"][1], True, torch.device("cpu"))
+    base = g[names[0]].data_ptr()
+    assert [(g[k].data_ptr() - base) // 4 for k in names] == rel
