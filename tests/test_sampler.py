@@ -75,3 +75,4 @@ def test_device_pipeline_routes_batches_to_their_dataset():
     again = list(pipe)
     assert [b["domain"][0] for b in again] != [b["domain"][0] for b in batches] or \
         not all(torch.equal(x["input_ids"], y["input_ids"]) for x, y in zip(again, batches))
+
