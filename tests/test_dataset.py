@@ -68,7 +68,8 @@ def test_device_gather_equals_host_items(tmp_path, dtype):
     from hma_b200 import GenieConfig
     from hma_b200.data import collate_from_draws, draw_on_device
 
-    cfg = GenieConfig(num_layers=1, num_heads=8, d_model=256, T=4, S=256, num_factored_vocabs=2)
+    # non_mlm_ratio=0: with T = 4 and the default num_prompt_frames = 4 the non-MLM branch would call random.randint(4, 3)
+    cfg = GenieConfig(num_layers=1, num_heads=8, d_model=256, T=4, S=256, num_factored_vocabs=2, non_mlm_ratio=0.0)
     if dtype == "uint32":
         ids, labels = collate_from_draws(out["input_ids"], draw_on_device(cfg, 33, 16, 16, torch.device("cuda")), cfg, 16, 16)
         assert torch.equal(labels, out["input_ids"]) and (ids == cfg.image_vocab_size).any()
