@@ -88,3 +88,28 @@ def test_forward_consumes_cpu_rng_like_the_reference(monkeypatch):
     torch.rand(2, 3, 1)
     assert torch.equal(after, torch.rand(1))
     assert m.relevant_action_mask.shape == (2, 3, 1, 1)
+
+
+def test_config_fields_and_defaults_equal_the_reference():
+    """GenieConfig / DiffusionGenieConfig carry exactly the reference's fields and defaults (hma/config.py:8-117); checked
+    against the live reference when it is present (authoring container), otherwise skipped."""
+    import dataclasses
+
+    from oracle import reference_loader
+
+    if not reference_loader.available():
+        pytest.skip("reference not present")
+    reference_loader.load()
+    from hma.config import DiffusionGenieConfig as RD
+    from hma.config import GenieConfig as R
+
+    from hma_b200 import DiffusionGenieConfig, GenieConfig
+
+    for ref, ours in ((R, GenieConfig), (RD, DiffusionGenieConfig)):
+        a = {f.name: f.default for f in dataclasses.fields(ref)}
+        b = {f.name: f.default for f in dataclasses.fields(ours)}
+        assert a == b
+        assert [f.name for f in dataclasses.fields(ref)][:5] == [f.name for f in dataclasses.fields(ours)][:5]
+    kw = dict(num_layers=2, num_heads=8, d_model=256, num_factored_vocabs=2)
+    assert vars(R(**kw)) == vars(GenieConfig(**kw))
+    assert vars(RD(patch_size=2, **kw)) == vars(DiffusionGenieConfig(patch_size=2, **kw))
