@@ -70,12 +70,11 @@ _SIGNATURES = {
                    c_void_p],
     "hma_ce_bwd": [c_fp, c_ll, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_ll, c_float, c_fp, c_fp, c_fp,
                    c_void_p, c_ll, c_void_p],
-    "hma_sample_tokens": [c_fp, c_ll, c_ll, c_int, c_int, c_int, c_int, c_fp, c_void_p, c_fp, c_void_p],
+    "hma_sample_tokens": [c_fp, c_ll, c_ll, c_int, c_int, c_int, c_int, c_fp, c_float, c_void_p, c_fp, c_void_p],
     "hma_rank_remask": [c_fp, c_void_p, c_void_p, c_void_p, c_ll, c_int, c_int, c_int, c_ll, c_void_p, c_void_p],
     "hma_sumsq": [c_fp, c_ll, c_fp, c_void_p],
-    "hma_adamw_step": [c_fp, c_fp, c_fp, c_fp, c_ll, c_float, c_float, c_float, c_float, c_float, c_int, c_float, c_fp,
+    "hma_adamw_step": [c_fp, c_fp, c_fp, c_fp, c_ll, c_ll, c_float, c_float, c_float, c_float, c_float, c_int, c_float, c_fp,
                        c_float, c_void_p],
-    "hma_umma_probe": [c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_fp, c_void_p],
     "hma_gemm_wgrad": [c_void_p, c_ll, c_void_p, c_ll, c_int, c_int, c_int, c_fp, c_ll, c_void_p],
     "hma_mar_embed_fwd": [c_fp, c_void_p, c_fp, c_fp, c_fp, c_fp, c_fp, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                           c_int, c_fp, c_fp, c_fp, c_void_p],

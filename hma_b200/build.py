@@ -78,6 +78,25 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     return LIB
 
 
+PROBE_SRC = ROOT / "tests" / "csrc" / "umma_probe.cu"
+PROBE_LIB = ROOT / "tests" / "libhma_b200_probe.so"
+
+
+def build_probe(force: bool = False) -> Path:
+    """Test-only tcgen05 descriptor probe (tests/test_umma_probe_gpu.py): its own shared library, linked against the
+    product's host-side helpers (TMA descriptor encoding), so the probe is not an entry point of libhma_b200.so."""
+    build(force=False)
+    host_obj = OBJ / "host.o"
+    headers = sorted(CSRC.glob("*.cuh"))
+    if force or _stale(PROBE_LIB, [PROBE_SRC, host_obj] + headers):
+        cmd = [_nvcc(), *NVCC_FLAGS, "-shared", str(PROBE_SRC), str(host_obj), "-o", str(PROBE_LIB), "-cudart", "static"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"probe build failed:\n{r.stdout}\n{r.stderr}")
+    return PROBE_LIB
+
+
 if __name__ == "__main__":
     lib = build(force="--force" in sys.argv, verbose="--verbose" in sys.argv)
     print(lib)
+    print(build_probe(force="--force" in sys.argv))

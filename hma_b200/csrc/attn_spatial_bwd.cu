@@ -381,7 +381,8 @@ extern "C" int hma_attn_spatial_bwd(const void* qkv, long long ld_qkv, const voi
                                       (uint32_t)p.box_rows, 64);
   if (rc) return rc;
   constexpr size_t smem = 1024 + 4 * kBTile + 8 * kBPanel;
-  static bool attr_done = false;
+  static hma_host::PerDeviceFlag attr_flag;  // function attributes are per device (context)
+  bool& attr_done = attr_flag.get();
   if (!attr_done) {
     HMA_CHECK_CUDA(cudaFuncSetAttribute(attn_spatial_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_done = true;

@@ -313,7 +313,8 @@ extern "C" int hma_attn_spatial_fwd(const void* qkv, long long ld_qkv, int frame
                                           (uint32_t)p.box_rows, 64);
   if (rc) return rc;
   constexpr size_t smem = 1024 + 3 * kQKVBytes + kPBytes;
-  static bool attr_done = false;
+  static hma_host::PerDeviceFlag attr_flag;  // function attributes are per device (context)
+  bool& attr_done = attr_flag.get();
   if (!attr_done) {
     HMA_CHECK_CUDA(cudaFuncSetAttribute(attn_spatial_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_done = true;

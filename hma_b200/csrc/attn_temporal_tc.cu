@@ -619,7 +619,8 @@ extern "C" int hma_attn_temporal_fwd(const void* qkv, long long ld_qkv, int B, i
   CUtensorMap tm;
   if (int rc = make_unit_map(&tm, qkv, ld_qkv, B, T, n, p)) return rc;
   constexpr size_t smem = 1024 + kFwdStages * 3 * kTTile + kFwdGroups * 2 * kTPanel;
-  static bool attr_done = false;
+  static hma_host::PerDeviceFlag attr_flag;  // function attributes are per device (context)
+  bool& attr_done = attr_flag.get();
   if (!attr_done) {
     HMA_CHECK_CUDA(cudaFuncSetAttribute(attn_temporal_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_done = true;
@@ -649,7 +650,8 @@ extern "C" int hma_attn_temporal_bwd(const void* qkv, long long ld_qkv, const vo
   if (int rc = make_unit_map(&tmQ, qkv, ld_qkv, B, T, n, p)) return rc;
   if (int rc = make_unit_map(&tmD, dout, ld_dout, B, T, n, p)) return rc;
   constexpr size_t smem = 1024 + kBwdStages * 4 * kTTile + 8 * kTPanel;
-  static bool attr_done = false;
+  static hma_host::PerDeviceFlag attr_flag;  // function attributes are per device (context)
+  bool& attr_done = attr_flag.get();
   if (!attr_done) {
     HMA_CHECK_CUDA(cudaFuncSetAttribute(attn_temporal_tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_done = true;

@@ -60,11 +60,19 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
                : "memory");
 }
-// Bounded spin: a protocol bug traps (surfacing as a CUDA error on the host) instead of
-// hanging the GPU box.
+// Bounded wait: a protocol bug traps (surfacing as a CUDA error on the host) instead of hanging the GPU box. The bound
+// is WALL TIME (%globaltimer, checked every 4096 failed polls), not a spin count: a kernel that is merely slow — under a
+// profiler's replay passes, a debugger, time-slicing or preemption — must not trap.
+__device__ __forceinline__ uint64_t global_timer_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+constexpr uint64_t kMbarTimeoutNs = 20ull * 1000 * 1000 * 1000;
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t done = 0;
   uint32_t spins = 0;
+  uint64_t t0 = 0;
   while (true) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
@@ -74,7 +82,11 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         : "r"(bar), "r"(parity)
         : "memory");
     if (done) break;
-    if (++spins > (1u << 24)) __trap();
+    if ((++spins & 0xfffu) == 0) {
+      const uint64_t now = global_timer_ns();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > kMbarTimeoutNs) __trap();
+    }
   }
 }
 // generic-proxy smem writes -> visible to the async proxy (TMA / UMMA operand reads)
@@ -315,6 +327,13 @@ int make_tmap_bf16_3d_sw64(CUtensorMap* map, const void* base, uint64_t d0, uint
                            uint64_t stride1_bytes, uint64_t stride2_bytes, uint32_t b1, uint32_t b2);
 
 int sm_count();
+int current_device();
+// One flag per CUDA device: cudaFuncSetAttribute and friends are per-device state, and a process may drive several
+// devices (idempotent values; racing threads set the same flag).
+struct PerDeviceFlag {
+  bool done[64] = {};
+  bool& get() { return done[current_device() & 63]; }
+};
 bool pdl_enabled();  // HMA_B200_NO_PDL=1 turns programmatic dependent launch off (A/B measurements)
 
 // Launch `kern` with programmatic stream serialization; the kernel MUST call hma::pdl_wait() before it

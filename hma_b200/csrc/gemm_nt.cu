@@ -400,7 +400,8 @@ template <int BN, int EPI, bool STAT>
 static int launch_nt(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmNtParams& p, cudaStream_t stream) {
   const size_t smem = smem_need<BN, EPI>(p.K / kBK, STAT);
   auto kern = gemm_nt_kernel<BN, EPI, STAT>;
-  static bool attr_done = false;  // idempotent; racing threads set the same value
+  static hma_host::PerDeviceFlag attr_flag;  // function attributes are per device (context)
+  bool& attr_done = attr_flag.get();  // idempotent; racing threads set the same value
   if (!attr_done) {
     HMA_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
     attr_done = true;

@@ -151,7 +151,8 @@ static int launch_wgrad(const void* G, long long ldg, const void* X, long long l
   if (rc) return rc;
   constexpr size_t smem = 1024 + (size_t)WStages<BNW>::value * (2 * kBox + (BNW / 64) * kBox);
   auto kern = gemm_wgrad_kernel<BNW>;
-  static bool attr_done = false;
+  static hma_host::PerDeviceFlag attr_flag;  // function attributes are per device (context)
+  bool& attr_done = attr_flag.get();
   if (!attr_done) {
     HMA_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_done = true;

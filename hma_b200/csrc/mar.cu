@@ -757,7 +757,8 @@ extern "C" int hma_mar_embed_fwd(float* lat, const unsigned char* mask, const fl
   HMA_REQUIRE(A == 0 || act != nullptr, "mar_embed_fwd: action tokens requested without an action embedding");
   HMA_REQUIRE(mask == nullptr || mask_token != nullptr, "mar_embed_fwd: mask given without mask_token");
   const size_t smem = (size_t)d.D * 256 * sizeof(float);
-  static bool attr_done = false;
+  static hma_host::PerDeviceFlag attr_flag;  // function attributes are per device (context)
+  bool& attr_done = attr_flag.get();
   if (!attr_done) {
     HMA_CHECK_CUDA(cudaFuncSetAttribute(mar_embed_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 256 * 4));
     attr_done = true;
@@ -775,7 +776,8 @@ extern "C" int hma_mar_embed_bwd(const float* du, const float* xp, const unsigne
   if (int rc = fill_embed_dims(&d, B, T, H, W, Cv, p, A, pos_n)) return rc;
   HMA_REQUIRE(du != nullptr && xp != nullptr && dWe != nullptr && dpos != nullptr, "mar_embed_bwd: null argument");
   const size_t smem = ((size_t)2 * d.D * 256 + 8) * sizeof(float);
-  static bool attr_done = false;
+  static hma_host::PerDeviceFlag attr_flag;  // function attributes are per device (context)
+  bool& attr_done = attr_flag.get();
   if (!attr_done) {
     HMA_CHECK_CUDA(cudaFuncSetAttribute(mar_embed_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (2 * 64 * 256 + 8) * 4));

@@ -33,7 +33,7 @@ struct AdamParams {
   const float* g;
   float* m;
   float* v;
-  long long n4;
+  long long n4, n4_decay;
   float lr, beta1, beta2, eps, wd, bc1, bc2;  // bc = 1 - beta^t
   float grad_scale;                            // e.g. 1/world_size
   const float* sumsq;                          // device scalar (may be null: no clipping)
@@ -53,6 +53,7 @@ __global__ void __launch_bounds__(256) adamw_kernel(const AdamParams a) {
   const float4 g4 = reinterpret_cast<const float4*>(a.g)[i];
   float4 m = reinterpret_cast<float4*>(a.m)[i];
   float4 v = reinterpret_cast<float4*>(a.v)[i];
+  const float decay = i < a.n4_decay ? 1.f - a.lr * a.wd : 1.f;
   float* pp = reinterpret_cast<float*>(&p);
   const float* gg = reinterpret_cast<const float*>(&g4);
   float* mm = reinterpret_cast<float*>(&m);
@@ -60,7 +61,7 @@ __global__ void __launch_bounds__(256) adamw_kernel(const AdamParams a) {
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     const float g = gg[j] * gs;
-    pp[j] *= 1.f - a.lr * a.wd;  // decoupled weight decay
+    pp[j] *= decay;  // decoupled weight decay (1 for the no-decay group)
     mm[j] = a.beta1 * mm[j] + (1.f - a.beta1) * g;
     vv[j] = a.beta2 * vv[j] + (1.f - a.beta2) * g * g;
     const float denom = sqrtf(vv[j] / a.bc2) + a.eps;
@@ -85,15 +86,16 @@ extern "C" int hma_sumsq(const float* g, long long n, float* out, void* stream_)
   return 0;
 }
 
-extern "C" int hma_adamw_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1,
-                              float beta2, float eps, float wd, int step, float grad_scale, const float* sumsq,
-                              float max_norm, void* stream_) {
+extern "C" int hma_adamw_step(float* p, const float* g, float* m, float* v, long long n, long long n_decay, float lr,
+                              float beta1, float beta2, float eps, float wd, int step, float grad_scale,
+                              const float* sumsq, float max_norm, void* stream_) {
   using namespace hma;
   if (n == 0) return 0;
   HMA_REQUIRE(n % 4 == 0, "adamw: range length must be a multiple of 4");
   HMA_REQUIRE(step >= 1, "adamw: step counts from 1");
+  HMA_REQUIRE(n_decay >= 0 && n_decay <= n && n_decay % 4 == 0, "adamw: n_decay must be a multiple of 4 in [0, n]");
   AdamParams a;
-  a.p = p; a.g = g; a.m = m; a.v = v; a.n4 = n / 4;
+  a.p = p; a.g = g; a.m = m; a.v = v; a.n4 = n / 4; a.n4_decay = n_decay / 4;
   a.lr = lr; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.wd = wd;
   a.bc1 = 1.f - powf(beta1, (float)step);
   a.bc2 = 1.f - powf(beta2, (float)step);

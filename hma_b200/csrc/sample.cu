@@ -18,6 +18,7 @@ struct SampleParams {
   long long stride_b, ld;
   int B, S, nv, vs;
   const float* exp_noise;    // [nv][B*S, vs], index 0 = HIGH half (reference order) or null = greedy
+  float temperature;         // divides the probabilities before the renormalisation (cancels in exact arithmetic)
   long long* samples;        // [B*S]
   float* conf;               // [B*S]
 };
@@ -40,9 +41,28 @@ __global__ void __launch_bounds__(256) sample_tokens_kernel(const SampleParams p
       m = fmaxf(m, fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)));
     }
     m = warp_max(m);
-    float sum = 0.f, best = -INFINITY, best_e = 0.f;
-    int arg = 0;
+    // torch.softmax: p = exp(z - m) / sum. The reference then ranks Categorical(probs = p / temperature), i.e.
+    // ((p / temperature) / sum(p / temperature)) / Exp(1) (st_mask_git.py:409-416; torch.multinomial = argmax(probs / q)).
+    // The keys below are built with the same sequence of fp32 operations, so near-ties round the way the reference's do.
+    float sum = 0.f;
+    for (int c = lane * 4; c < p.vs; c += 128) {
+      const float4 v = *reinterpret_cast<const float4*>(zk + c);
+      sum += expf(v.x - m) + expf(v.y - m) + expf(v.z - m) + expf(v.w - m);
+    }
+    sum = warp_sum(sum);
     const float* q = p.exp_noise != nullptr ? p.exp_noise + ((size_t)j * p.B * p.S + tok) * p.vs : nullptr;
+    float sum2 = 1.f;
+    if (q != nullptr) {
+      sum2 = 0.f;
+      for (int c = lane * 4; c < p.vs; c += 128) {
+        const float4 v = *reinterpret_cast<const float4*>(zk + c);
+        sum2 += (expf(v.x - m) / sum) / p.temperature + (expf(v.y - m) / sum) / p.temperature +
+                (expf(v.z - m) / sum) / p.temperature + (expf(v.w - m) / sum) / p.temperature;
+      }
+      sum2 = warp_sum(sum2);
+    }
+    float best = -INFINITY, best_p = 0.f;
+    int arg = 0;
     for (int c = lane * 4; c < p.vs; c += 128) {
       const float4 v = *reinterpret_cast<const float4*>(zk + c);
       const float vv[4] = {v.x, v.y, v.z, v.w};
@@ -53,22 +73,20 @@ __global__ void __launch_bounds__(256) sample_tokens_kernel(const SampleParams p
       }
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        const float e = expf(vv[i] - m);
-        sum += e;
-        const float key = e / qq[i];  // argmax(p / Exp(1)) == multinomial draw; greedy when q == 1
-        if (key > best) { best = key; best_e = e; arg = c + i; }
+        const float pr = expf(vv[i] - m) / sum;
+        const float key = q != nullptr ? ((pr / p.temperature) / sum2) / qq[i] : pr;  // greedy: argmax of the probabilities
+        if (key > best) { best = key; best_p = pr; arg = c + i; }
       }
     }
-    sum = warp_sum(sum);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
       const float ob = __shfl_xor_sync(0xffffffffu, best, o);
-      const float oe = __shfl_xor_sync(0xffffffffu, best_e, o);
+      const float oe = __shfl_xor_sync(0xffffffffu, best_p, o);
       const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
-      if (ob > best || (ob == best && oa < arg)) { best = ob; best_e = oe; arg = oa; }
+      if (ob > best || (ob == best && oa < arg)) { best = ob; best_p = oe; arg = oa; }
     }
     id = id * p.vs + arg;
-    conf *= best_e / sum;
+    conf *= best_p;
   }
   if (lane == 0) {
     p.samples[tok] = id;
@@ -123,12 +141,14 @@ __global__ void __launch_bounds__(1024) rank_remask_kernel(const RemaskParams p)
 }  // namespace hma
 
 extern "C" int hma_sample_tokens(const float* logits, long long stride_b, long long ld, int B, int S, int nv, int vs,
-                                 const float* exp_noise, long long* samples, float* conf, void* stream_) {
+                                 const float* exp_noise, float temperature, long long* samples, float* conf,
+                                 void* stream_) {
   using namespace hma;
   HMA_REQUIRE(vs % 128 == 0 && nv >= 1 && nv <= 3, "sample_tokens: unsupported vocabulary %d x %d", nv, vs);
   HMA_REQUIRE(ld % 4 == 0 && stride_b % 4 == 0, "sample_tokens: logits must be 16-byte aligned");
   if (B * S == 0) return 0;
-  SampleParams p{logits, stride_b, ld, B, S, nv, vs, exp_noise, samples, conf};
+  HMA_REQUIRE(exp_noise == nullptr || temperature > 0.f, "sample_tokens: sampling needs temperature > 0");
+  SampleParams p{logits, stride_b, ld, B, S, nv, vs, exp_noise, temperature, samples, conf};
   sample_tokens_kernel<<<(B * S + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream_)>>>(p);
   HMA_CHECK_CUDA(cudaGetLastError());
   return 0;

@@ -52,6 +52,11 @@ def collate_from_draws(tokens: torch.Tensor, d: Dict[str, object], cfg, h: int, 
     if not tokens.is_cuda:
         raise RuntimeError("hma_b200.data collates on a CUDA device only (no CPU path exists)")
     dev = tokens.device
+    if not cfg.dataloader_apply_mask:
+        # data.py:69-83: the corrupted factors are only folded back into token ids (unfactorize_token_ids) inside
+        # `if config.dataloader_apply_mask`; without it the reference returns the ORIGINAL tokens as input_ids — the
+        # corruption draws are consumed and then discarded. Mirrored.
+        return tokens.clone(), tokens.clone()
 
     def f32(x):
         return None if x is None else x.to(device=dev, dtype=torch.float32).contiguous()

@@ -11,8 +11,9 @@ on the device (csrc/dataset.cu) that feeds the on-device collator (hma_b200/data
 dataloader workers.
 
 Stride: the reference looks the dataset name up in DATA_FREQ_TABLE (datasets/encode_openx_dataset.py:51-108) and uses
-max(hz // natural_hz, 1). The writer stores that same table entry in metadata.json as "hz" (:374), so it is read from
-there; pass `freq_table` to override (e.g. when `name` differs from the directory's own name).
+max(hz // natural_hz, 1); the same table ships here as data (data_freq_table.json) and is looked up the same way —
+by `name`, default 1 — so a `name` that differs from the directory's own name resolves exactly as in the reference.
+Pass `freq_table` to override it.
 """
 from __future__ import annotations
 
@@ -28,6 +29,16 @@ from . import _lib, ops
 
 
 SVD_SCALE = 0.18215  # hma/data.py:16: latent scaling of the continuous (SVD-VAE) features
+
+
+def _load_freq_table() -> Dict[str, int]:
+    """DATA_FREQ_TABLE of the reference (datasets/encode_openx_dataset.py:51-108; read at hma/data.py:207): control
+    frequency per dataset name. Shipped as data (hma_b200/data_freq_table.json, extracted by oracle/make_freq_table.py)."""
+    with open(Path(__file__).with_name("data_freq_table.json")) as f:
+        return {k: int(v) for k, v in json.load(f).items()}
+
+
+DATA_FREQ_TABLE: Dict[str, int] = _load_freq_table()
 
 
 def normalize_actions(actions: np.ndarray):
@@ -49,11 +60,9 @@ class RawTokenDataset(torch.utils.data.Dataset):
         self.window_size, self.stride = window_size, stride
         self.name = name if len(name) else self.metadata["name"]
         if compute_stride_from_freq_table:
-            if freq_table is not None:
-                hz = freq_table.get(self.name, 1)
-            else:
-                hz = self.metadata.get("hz", 1) if self.name == self.metadata.get("name", self.name) else 1
-            self.stride = max(hz // natural_hz, 1)
+            # data.py:207: DATA_FREQ_TABLE.get(self.name, 1) — the table, not the metadata's "hz" field
+            table = DATA_FREQ_TABLE if freq_table is None else freq_table
+            self.stride = max(table.get(self.name, 1) // natural_hz, 1)
         self.n_action = self.metadata.get("action_dim", 1) * self.stride
         self.drop_action_ratio = drop_action_ratio
         if use_actions:
@@ -178,12 +187,8 @@ class RawFeatureDataset(torch.utils.data.Dataset):
         self.datio_noise_ratio = datio_noise_ratio
         self.name = (domain if domain is not None else self.metadata["name"]).replace("_noquant", "")
         if compute_stride_from_freq_table:
-            if freq_table is not None:
-                hz = freq_table.get(self.name, 1)
-            else:
-                own = str(self.metadata.get("name", self.name)).replace("_noquant", "")
-                hz = self.metadata.get("hz", 1) if self.name == own else 1
-            self.stride = max(hz // natural_hz, 1)
+            table = DATA_FREQ_TABLE if freq_table is None else freq_table  # data.py:350
+            self.stride = max(table.get(self.name, 1) // natural_hz, 1)
         self.n_action = self.metadata.get("action_dim", 1) * self.stride
         if use_actions:
             parts = [np.memmap(fn, dtype=np.float32, mode="r").reshape(len(self.data), -1)

@@ -128,6 +128,22 @@ def layer_matrix_names(i: int, dom: Optional[str], modulate: bool) -> List[str]:
     return names
 
 
+NO_DECAY = ("bias", "layer_norm.weight")  # train_multi.py:906: substrings of parameter names that get weight_decay 0
+
+
+def is_no_decay(name: str) -> bool:
+    """The reference's optimizer grouping rule (train_multi.py:906-917), verbatim: a parameter whose NAME contains "bias"
+    or "layer_norm.weight" is not decayed. (No HMA module is called `layer_norm`, so norm1/norm2/LayerNorm gains ARE
+    decayed by the reference; kept.)"""
+    return any(nd in name for nd in NO_DECAY)
+
+
+def decay_partition(names: List[str]) -> List[str]:
+    """Stable partition [decayed | not decayed]: inside every flat range (parameter arena, moments, gradient buffer) the
+    decayed tensors come first, so the optimizer needs one boundary per range instead of a per-tensor table."""
+    return [k for k in names if not is_no_decay(k)] + [k for k in names if is_no_decay(k)]
+
+
 def stem_pad(da: int) -> int:
     return (da + 127) // 128 * 128
 
@@ -267,8 +283,6 @@ class Engine:
             x = ops.embed_fwd(ids, p["token_embed.factored_embeds.0.weight"], E1, p["token_embed.mask_token_embed"],
                               act if d.A else None, pos, pos_n, B, T, S, d.A, d.vs, d.mask_id)
         drop_p = drop[0] if (drop is not None and training) else 0.0
-        if drop_p > 0.0:
-            assert not self.cfg.mlp_bias, "mlp_drop > 0 together with mlp_bias=True is not implemented"
         # adaLN_modulation (Linear -> SiLU -> Linear on the [B*T, 256] action embedding) depends only on the
         # stem output: all layers' shift/scale are produced up-front on a side stream, where these
         # one-tile GEMMs fill the tails of the main stream's kernels instead of serialising with them.
@@ -349,8 +363,8 @@ class Engine:
             h = ops.gemm_nt(a2, Wp[lp + "mlp.fc1.weight"], EPI_GELU, bias=p.get(lp + "mlp.fc1.bias"), out2=z)
             if drop_p > 0.0:
                 ops.dropout_bf16_(h, drop_p, drop[1] + 2 * i, drop[2])
-                x4 = ops.dropout_add_f32(ops.gemm_nt(h, Wp[lp + "mlp.fc2.weight"], EPI_RESID), x3, drop_p, drop[1] + 2 * i + 1,
-                                         seed_dev=drop[2])
+                x4 = ops.dropout_add_f32(ops.gemm_nt(h, Wp[lp + "mlp.fc2.weight"], EPI_RESID, bias=p.get(lp + "mlp.fc2.bias")),
+                                         x3, drop_p, drop[1] + 2 * i + 1, seed_dev=drop[2])
             else:
                 x4 = ops.gemm_nt(h, Wp[lp + "mlp.fc2.weight"], EPI_RESID, bias=p.get(lp + "mlp.fc2.bias"), resid=x3,
                                  out=None if training else x3)
@@ -382,7 +396,7 @@ class Engine:
                 if lp + k in p:
                     names.append(lp + k)
         names += ["out_x_proj.weight", "out_x_proj.bias"]
-        return names + self.head_param_names(p, d)
+        return decay_partition(names + self.head_param_names(p, d))
 
     def front_param_names(self, p: Dict[str, Tensor], d: Dims) -> List[str]:
         names = ["pos_embed_TSC", "token_embed.mask_token_embed", "token_embed.factored_embeds.0.weight"]
@@ -405,7 +419,7 @@ class Engine:
                 ap = f"decoder.layers.{i}.action_projectors.{dom}."
                 names += [ap + "linear_out.weight", ap + "linear_out.bias", ap + "adaLN_modulation.0.weight",
                           ap + "adaLN_modulation.0.bias", ap + "adaLN_modulation.2.weight", ap + "adaLN_modulation.2.bias"]
-        return names
+        return decay_partition(names)
 
     def active_param_names(self, p: Dict[str, Tensor], d: Dims, dom: Optional[str], has_actions: bool) -> List[str]:
         return self.shared_param_names(p, d) + self.domain_param_names(p, d, dom, has_actions)
@@ -413,6 +427,10 @@ class Engine:
     @staticmethod
     def padded_numel(t: Tensor) -> int:
         return (t.numel() + 3) // 4 * 4  # keep every tensor 16-byte aligned inside flat buffers
+
+    def decayed_numel(self, p: Dict[str, Tensor], names: List[str]) -> int:
+        """Padded length of the decayed prefix of a range laid out by `names` (see decay_partition)."""
+        return sum(self.padded_numel(p[k]) for k in names if not is_no_decay(k))
 
     def alloc_grads(self, p: Dict[str, Tensor], d: Dims, dom: Optional[str], has_actions: bool, dev,
                     flat: Optional[Tensor] = None) -> Dict[str, Tensor]:
@@ -470,12 +488,17 @@ class Engine:
             # ---- MLP
             if drop is not None:  # x4 = x3 + drop(fc2(drop(gelu(z)))): the keep masks are regenerated from the seeds
                 dy = ops.dropout_cast_bf16(dx, drop[0], drop[1] + 2 * i + 1, drop[2])
+                if lp + "mlp.fc2.bias" in g:
+                    ops.colsum_bf16(dy, g[lp + "mlp.fc2.bias"])
             elif dy is None:
                 dy = ops.cast_colsum(dx, g.get(lp + "mlp.fc2.bias"))
             ops.gemm_wgrad(dy, L["h"], g2(lp + "mlp.fc2.weight"))
-            dz = ops.gemm_nt(dy, Wt[lp + "mlp.fc2.weight"], EPI_DGELU, aux=L["z"], colsum=g.get(lp + "mlp.fc1.bias"))
-            if drop is not None:
+            dz = ops.gemm_nt(dy, Wt[lp + "mlp.fc2.weight"], EPI_DGELU, aux=L["z"],
+                             colsum=g.get(lp + "mlp.fc1.bias") if drop is None else None)
+            if drop is not None:  # the GELU-output dropout mask applies to dz: fc1's bias gradient is taken after it
                 ops.dropout_bf16_(dz, drop[0], drop[1] + 2 * i, drop[2])
+                if lp + "mlp.fc1.bias" in g:
+                    ops.colsum_bf16(dz, g[lp + "mlp.fc1.bias"])
             ops.gemm_wgrad(dz, L["a2"], g2(lp + "mlp.fc1.weight"))
             da2 = ops.gemm_nt(dz, Wt[lp + "mlp.fc1.weight"], EPI_BF16)
             if qk:

@@ -9,8 +9,6 @@ the diffusion-MLP loss (DiffLoss / SimpleMLPAdaLN / GaussianDiffusion.training_l
 DDPM sampler behind maskgit_generate. All arithmetic runs in libhma_b200.so (csrc/mar.cu + the tcgen05 GEMMs); torch
 allocates buffers, draws the random numbers the reference draws, and permutes layouts. There is no CPU path.
 """
-from __future__ import annotations
-
 import math
 from dataclasses import dataclass
 from typing import Callable, Dict, List, Optional
@@ -912,7 +910,6 @@ class MarTrainStep(TrainStep):
 
     def __init__(self, model: STMAR, **kw):
         super().__init__(model, **kw)
-        self._seed_dev = torch.zeros(1, device=self.arena.flat.device, dtype=torch.int64)
 
     def _eager(self, p, lat, mask_u8, tgt, actions, dom, d, H, W, t, noise):
         cfg = self.model.config

@@ -6,8 +6,6 @@ update). The sub-modules below are parameter containers only: no torch op comput
 hot path, which is scheduled by hma_b200.engine and executed by libhma_b200.so. There is no CPU
 path: calling the model without a CUDA device raises.
 """
-from __future__ import annotations
-
 import math
 from typing import Optional
 
@@ -145,11 +143,11 @@ class _LazyParams:
 # ------------------------------------------------------------------------------------------------
 class _ForwardLoss(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, model, names, ids, labels, actions, dom, dims, *params):
+    def forward(ctx, model, names, ids, labels, actions, dom, dims, drop, *params):
         p = dict(model._buffers_dict())
         p.update({k: t.detach() for k, t in zip(names, params)})
         eng: Engine = model._engine
-        logits, sv = eng.forward(p, ids, actions, dom, dims, training=True)
+        logits, sv = eng.forward(p, ids, actions, dom, dims, training=True, drop=drop)
         loss_acc, lse, sums = ops.ce_fwd(logits, labels, ids, dims.B, dims.T, dims.S, dims.nv, dims.vs, dims.mask_id,
                                          SMOOTHING)
         ctx.model, ctx.names, ctx.p, ctx.sv = model, names, p, sv
@@ -167,7 +165,49 @@ class _ForwardLoss(torch.autograd.Function):
         dlogits = ops.ce_bwd(logits, labels, ids, d.B, d.T, d.S, d.nv, d.vs, d.mask_id, SMOOTHING, lse, sums, dl)
         grads = model._engine.backward(p, sv, dlogits)
         ctx.sv = ctx.ce = None
-        return (None,) * 7 + tuple(grads.get(k) for k in names)
+        return (None,) * 8 + tuple(grads.get(k) for k in names)
+
+
+class _Logits(torch.autograd.Function):
+    """compute_logits as a differentiable call (st_mask_git.py:632-686 is an ordinary autograd forward in the reference):
+    the trunk's saved activations ride on the Function; backward takes d(logits) in whatever layout autograd hands back."""
+
+    @staticmethod
+    def forward(ctx, model, names, ids, actions, dom, dims, drop, skip_norm, *params):
+        p = dict(model._buffers_dict())
+        p.update({k: t.detach() for k, t in zip(names, params)})
+        logits, sv = model._engine.forward(p, ids, actions, dom, dims, training=True, skip_normalization=skip_norm, drop=drop)
+        ctx.model, ctx.names, ctx.p, ctx.sv = model, names, p, sv
+        return logits
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        model, names, p, sv = ctx.model, ctx.names, ctx.p, ctx.sv
+        grads = model._engine.backward(p, sv, dlogits.to(torch.bfloat16).contiguous())
+        ctx.sv = None
+        return (None,) * 8 + tuple(grads.get(k) for k in names)
+
+
+class _VideoLoss(torch.autograd.Function):
+    """compute_video_loss_and_acc (st_mask_git.py:603-630) on logits rows [B*T*S, nv*vs]: factorised cross entropy with
+    label smoothing over the masked positions of frames >= 1, and its gradient w.r.t. the logits."""
+
+    @staticmethod
+    def forward(ctx, rows, labels, ids, B, T, S, nv, vs, mask_id):
+        la, lse, sums = ops.ce_fwd(rows, labels, ids, B, T, S, nv, vs, mask_id, SMOOTHING)
+        ctx.save_for_backward(rows, labels, ids, lse, sums)
+        ctx.dims = (B, T, S, nv, vs, mask_id)
+        loss, acc = la[0], la[1]
+        ctx.mark_non_differentiable(acc)
+        return loss, acc
+
+    @staticmethod
+    def backward(ctx, dloss, _dacc):
+        rows, labels, ids, lse, sums = ctx.saved_tensors
+        B, T, S, nv, vs, mask_id = ctx.dims
+        dl = dloss.detach().to(torch.float32).reshape(1).contiguous()
+        d = ops.ce_bwd(rows, labels, ids, B, T, S, nv, vs, mask_id, SMOOTHING, lse, sums, dl)
+        return (d.to(rows.dtype),) + (None,) * 8
 
 
 class STMaskGIT(nn.Module, PyTorchModelHubMixin):
@@ -191,6 +231,7 @@ class STMaskGIT(nn.Module, PyTorchModelHubMixin):
         self._engine = self._make_engine(config)
         self._sessions = {}
         self._lazy = None
+        self._arena = None
         if (config.init_actions or config.use_actions) and config.action_domains is not None:
             self.init_action_projectors(config.action_domains, config.d_actions, config.action_stats, config.action_network)
 
@@ -231,6 +272,19 @@ class STMaskGIT(nn.Module, PyTorchModelHubMixin):
                     layer.action_projectors[dom] = nn.Identity()
         self.to(dev)
         self._lazy = None
+
+    def _save_pretrained(self, save_directory) -> None:
+        """save_pretrained (the reference's checkpoint call, train_multi.py:310-321). After a TrainStep has re-homed the
+        parameters into its flat arena they are views of one storage, which safetensors refuses to serialise: clone
+        them first (same keys, shapes and values; the file is identical to one written before re-homing)."""
+        if getattr(self, "_arena", None) is None:
+            return super()._save_pretrained(save_directory)
+        from pathlib import Path
+
+        from huggingface_hub import constants
+        from safetensors.torch import save_file
+        tensors = {k: v.detach().clone().contiguous() for k, v in self.state_dict().items()}
+        save_file(tensors, str(Path(save_directory) / constants.SAFETENSORS_SINGLE_FILE), metadata={"format": "pt"})
 
     def _inference_params(self) -> _LazyParams:
         if self._lazy is None:
@@ -284,24 +338,34 @@ class STMaskGIT(nn.Module, PyTorchModelHubMixin):
     def compute_logits(self, x_THW: torch.Tensor, action_ids: Optional[torch.Tensor] = None, domain=None, **kwargs):
         self._require_cuda(x_THW)
         B, T, H, W = x_THW.shape
-        # Inference entry point: the returned logits are not part of an autograd graph (forward() is the
-        # differentiable call; it fuses head, loss and their backward).
-        logits, _ = self._logits_nograd(x_THW, action_ids, domain, kwargs)
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            # differentiable, like the reference's (forward() is the faster training call: it fuses head, loss and backward)
+            dom = self._domain0(domain, action_ids)
+            if action_ids is not None:
+                assert action_ids.shape[1] == T, "action_ids must provide one action vector per frame"
+            d = self._engine.dims(B, T, H * W, action_ids is not None)
+            named = [(k, v) for k, v in self.named_parameters()]
+            drop = None
+            if self.training and self.config.mlp_drop > 0.0:
+                drop = (float(self.config.mlp_drop), int(torch.randint(0, 2 ** 62, ()).item()), None)
+            logits = _Logits.apply(self, [k for k, _ in named], x_THW.reshape(B, T, H * W).contiguous(), action_ids, dom, d, drop,
+                                   bool(kwargs.get("skip_normalization", False)), *[v for _, v in named])
+        else:
+            logits, _ = self._logits_nograd(x_THW, action_ids, domain, kwargs)
         return self._as_CTHW(logits, B, T, H, W), None
 
     # ---------------------------------------------------------------- st_mask_git.py:603-630
     def compute_video_loss_and_acc(self, logits_CTHW, targets_THW, relevant_mask_THW):
         """Same contract as the reference: logits [B, nv*vs, T, H, W], targets [B, T*H*W], mask [B, T-1, H, W].
-        (forward() does not call this; it fuses the loss with the head.) Not differentiable."""
+        (forward() does not call this; it fuses the loss with the head.) Differentiable w.r.t. the logits."""
         B, Cv, T, H, W = logits_CTHW.shape
         cfg = self.config
         rows = logits_CTHW.permute(0, 2, 3, 4, 1).reshape(B * T * H * W, Cv).float().contiguous()
         ids = torch.zeros(B, T, H * W, dtype=torch.long, device=rows.device)
         ids[:, 1:][relevant_mask_THW.reshape(B, T - 1, H * W).bool()] = self.mask_token_id
         labels = targets_THW.reshape(B, T * H * W).contiguous()
-        la, _, _ = ops.ce_fwd(rows, labels, ids, B, T, H * W, cfg.num_factored_vocabs, cfg.factored_vocab_size,
-                              self.mask_token_id, SMOOTHING)
-        return la[0], la[1]
+        return _VideoLoss.apply(rows, labels, ids, B, T, H * W, cfg.num_factored_vocabs, cfg.factored_vocab_size,
+                                self.mask_token_id)
 
     # ---------------------------------------------------------------- st_mask_git.py:688-735
     def forward(self, input_ids, labels, action_ids=None, domain="default", **kwargs):
@@ -324,7 +388,10 @@ class STMaskGIT(nn.Module, PyTorchModelHubMixin):
         if torch.is_grad_enabled():
             named = [(k, v) for k, v in self.named_parameters()]
             names = [k for k, _ in named]
-            loss, acc, logits = _ForwardLoss.apply(self, names, ids, labels, action_ids, dom, d, *[v for _, v in named])
+            drop = None
+            if self.training and self.config.mlp_drop > 0.0:  # nn.Dropout after GELU and after fc2 (st_transformer.py:24-27)
+                drop = (float(self.config.mlp_drop), int(torch.randint(0, 2 ** 62, ()).item()), None)
+            loss, acc, logits = _ForwardLoss.apply(self, names, ids, labels, action_ids, dom, d, drop, *[v for _, v in named])
         else:
             logits, _ = self._logits_nograd(ids.view(B, T, H, W), action_ids, domain, kwargs)
             la, _, _ = ops.ce_fwd(logits, labels, ids, B, T, H * W, d.nv, d.vs, d.mask_id, SMOOTHING)
@@ -391,7 +458,7 @@ class STMaskGIT(nn.Module, PyTorchModelHubMixin):
                 # Appendix C of SURVEY.md: one Exp(1) tensor [B*S, vs] per vocabulary half, high half first
                 noise = torch.stack([torch.empty(B * S, vs, device=logits.device, dtype=torch.float32).exponential_(1)
                                      for _ in range(nv)])
-            new, conf = ops.sample_tokens(lf, nv, vs, noise)
+            new, conf = ops.sample_tokens(lf, nv, vs, noise, temperature if noise is not None else 1.0)
             if step != maskgit_steps - 1:
                 n = math.ceil(cosine_schedule((step + 1) / maskgit_steps) * S)
                 if unmask_mode == "greedy":

@@ -311,13 +311,13 @@ def ce_bwd(logits, labels, input_ids, B, T, S, nv, vs, mask_id, smoothing, lse, 
     return dlogits
 
 
-def sample_tokens(logits_frame: torch.Tensor, nv: int, vs: int, exp_noise: Optional[torch.Tensor]):
+def sample_tokens(logits_frame: torch.Tensor, nv: int, vs: int, exp_noise: Optional[torch.Tensor], temperature: float = 1.0):
     """logits_frame: fp32 view [B, S, nv*vs] (arbitrary batch stride). Returns (samples i64 [B,S], conf f32 [B,S])."""
     B, S, _ = logits_frame.shape
     samples = torch.empty(B, S, device=logits_frame.device, dtype=torch.long)
     conf = torch.empty(B, S, device=logits_frame.device, dtype=F32)
     _call("sample_tokens", B * S * nv * vs * 4.0, "hma_sample_tokens", logits_frame.data_ptr(), logits_frame.stride(0), logits_frame.stride(1), B, S, nv,
-              vs, _p(exp_noise), samples.data_ptr(), conf.data_ptr(), _s())
+              vs, _p(exp_noise), float(temperature), samples.data_ptr(), conf.data_ptr(), _s())
     return samples, conf
 
 

@@ -38,11 +38,15 @@ class ParamArena:
         leftovers = [k for k in named if k not in claimed]
         order: List[str] = list(shared_used)
         self.shared_size = sum(eng.padded_numel(named[k]) for k in shared_used)
+        # every range is laid out [decayed | not decayed] (engine.decay_partition): decayed prefix lengths
+        self.shared_decay = eng.decayed_numel(named, shared_used)
         self.dom_range: Dict[str, tuple] = {}
+        self.dom_decay: Dict[int, int] = {}  # arena offset of a domain block -> length of its decayed prefix
         off = self.shared_size
         for dom in domains:
             size = sum(eng.padded_numel(named[k]) for k in dom_used[dom])
             self.dom_range[dom] = (off, size)
+            self.dom_decay[off] = eng.decayed_numel(named, dom_used[dom])
             off += size
             order += dom_used[dom]
         order += leftovers
@@ -94,13 +98,25 @@ def exchange_gradients(grad: torch.Tensor, shared_size: int, max_dom_size: int, 
 
 class TrainStep:
     def __init__(self, model, lr: float = 1e-4, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.05,
-                 max_grad_norm: Optional[float] = 1.0, process_group=None, cuda_graphs: bool = False):
-        """cuda_graphs=True: forward + loss + backward of each (domain, shape) is captured into a CUDA graph on its
+                 max_grad_norm: Optional[float] = 1.0, process_group=None, cuda_graphs: bool = False,
+                 mu_transfer: bool = False):
+        """The optimizer is the reference's (train_multi.py:899-922): AdamW over two parameter groups — names containing
+        "bias" or "layer_norm.weight" get weight_decay 0, everything else `weight_decay`. `mu_transfer=True` selects the
+        reference's `mup.MuAdamW`: it divides the learning rate of matrix-like parameters by their width multiplier
+        relative to the base shapes, which the reference hard-codes to d_model=256, num_heads=8
+        (st_mask_git.py:755-760) — the only width these kernels are built for, so every multiplier is 1 and MuAdamW's
+        update is AdamW's; wider models are rejected by engine.check_config before they get here.
+
+        cuda_graphs=True: forward + loss + backward of each (domain, shape) is captured into a CUDA graph on its
         second use (or by precapture()) and replayed from static input buffers afterwards; the gradient exchange,
         the clip and AdamW stay ordinary launches. The ~1400 launches of a step otherwise cost ~30 ms of host time."""
         self.model = model
         self.engine: Engine = model._engine
+        if mu_transfer:
+            assert model.config.d_model == 256 and model.config.num_heads == 8, "MuAdamW: only the base width is built"
+        self.mu_transfer = mu_transfer
         self.arena = ParamArena(model)
+        model._arena = self.arena  # save_pretrained() clones arena-backed parameters (model._save_pretrained)
         self.lr, self.betas, self.eps, self.wd, self.max_norm = lr, betas, eps, weight_decay, max_grad_norm
         dev = self.arena.flat.device
         self.m = torch.zeros_like(self.arena.flat)
@@ -116,6 +132,9 @@ class TrainStep:
         self.gathered = (torch.zeros(self.world, self.arena.max_dom_size, device=dev, dtype=torch.float32)
                          if self.world > 1 else None)
         self._p = None
+        # nn.Dropout(mlp_drop) (st_transformer.py:24-27): keep masks are keyed by (seed, element); the device-side part of
+        # the seed is redrawn every step, so a CUDA-graph replay gets new masks
+        self._seed_dev = torch.zeros(1, device=dev, dtype=torch.int64)
         self.cuda_graphs = cuda_graphs
         self._graphs: Dict[tuple, dict] = {}
         self._warm = set()
@@ -128,18 +147,45 @@ class TrainStep:
             self._p = p
         return self._p
 
-    def _adamw(self, lo: int, n: int, g: torch.Tensor, scale: float, step: int) -> None:
+    def _adamw(self, lo: int, n: int, n_decay: int, g: torch.Tensor, scale: float, step: int) -> None:
         a = self.arena.flat
         _lib.call("hma_adamw_step", a.data_ptr() + 4 * lo, g.data_ptr(), self.m.data_ptr() + 4 * lo,
-                  self.v.data_ptr() + 4 * lo, n, self.lr, self.betas[0], self.betas[1], self.eps, self.wd,
+                  self.v.data_ptr() + 4 * lo, n, n_decay, self.lr, self.betas[0], self.betas[1], self.eps, self.wd,
                   step, scale, self.sumsq.data_ptr() if self.max_norm is not None else None,
                   float(self.max_norm or 0.0), ops._s())
+
+    # ------------------------------------------------------------------------------------------
+    def state_dict(self) -> dict:
+        """Optimizer state for checkpoint / resume (what `accelerator.save_state` keeps of AdamW, train_multi.py:321):
+        both moments over the whole arena, the shared step count and the per-domain step counts (keyed by domain name)."""
+        off_to_dom = {lo: dom for dom, (lo, _) in self.arena.dom_range.items()}
+        return {"m": self.m.detach().clone(), "v": self.v.detach().clone(), "step_count": self.step_count,
+                "dom_steps": {off_to_dom[lo]: n for lo, n in self.dom_steps.items()},
+                "param_offsets": dict(self.arena.offsets),
+                "hyper": {"lr": self.lr, "betas": tuple(self.betas), "eps": self.eps, "weight_decay": self.wd,
+                          "max_grad_norm": self.max_norm, "mu_transfer": self.mu_transfer}}
+
+    def load_state_dict(self, state: dict) -> None:
+        """Resume from state_dict(): the model's parameters must already hold the checkpointed values (they live in the
+        arena; load them with model.load_state_dict / from_pretrained before building the TrainStep, or after — the
+        parameters are views, so load_state_dict copies in place)."""
+        if state["param_offsets"] != self.arena.offsets:
+            raise ValueError("optimizer state was saved for a different parameter layout (domains / config differ)")
+        self.m.copy_(state["m"])
+        self.v.copy_(state["v"])
+        self.step_count = int(state["step_count"])
+        self.dom_steps = {self.arena.dom_range[dom][0]: int(n) for dom, n in state["dom_steps"].items()}
+        hy = state.get("hyper", {})
+        self.lr, self.eps, self.wd = hy.get("lr", self.lr), hy.get("eps", self.eps), hy.get("weight_decay", self.wd)
+        self.betas, self.max_norm = tuple(hy.get("betas", self.betas)), hy.get("max_grad_norm", self.max_norm)
 
     # ------------------------------------------------------------------------------------------
     def _fwd_bwd_eager(self, p, ids, labels, action_ids, dom, d) -> torch.Tensor:
         eng = self.engine
         B, T, S = d.B, d.T, d.S
-        logits, sv = eng.forward(p, ids, action_ids, dom, d, training=True)
+        mlp_drop = float(getattr(self.model.config, "mlp_drop", 0.0))
+        drop = (mlp_drop, 0x5EED, self._seed_dev) if (mlp_drop > 0.0 and self.model.training) else None
+        logits, sv = eng.forward(p, ids, action_ids, dom, d, training=True, drop=drop)
         loss_acc, lse, sums = ops.ce_fwd(logits, labels, ids, B, T, S, d.nv, d.vs, d.mask_id, SMOOTHING)
         dlogits = ops.ce_bwd(logits, labels, ids, B, T, S, d.nv, d.vs, d.mask_id, SMOOTHING, lse, sums, self.ones)
         self.grad.zero_()
@@ -205,6 +251,7 @@ class TrainStep:
         dom = model._domain0(domain, action_ids)
         d = eng.dims(B, T, S, action_ids is not None)
         p = self._params()
+        self._seed_dev.random_()  # new dropout masks every step (no-op cost when mlp_drop == 0)
         loss_acc = self._fwd_bwd(p, ids, labels, action_ids, dom, d)
         self._apply(dom, rank_domains)
         return loss_acc
@@ -233,12 +280,12 @@ class TrainStep:
             _lib.call("hma_sumsq", g_shared.data_ptr(), shared, self.sumsq.data_ptr(), ops._s())
             for _, n_r, g in updates:
                 _lib.call("hma_sumsq", g.data_ptr(), n_r, self.sumsq.data_ptr(), ops._s())
-        self._adamw(0, shared, g_shared, scale, self.step_count)
+        self._adamw(0, shared, self.arena.shared_decay, g_shared, scale, self.step_count)
         for lo, n_r, g in updates:
             # torch.optim.AdamW counts steps per parameter and skips parameters without a gradient, so a domain's
             # bias correction follows the number of updates THAT domain has received (train_multi.py:593-598)
             self.dom_steps[lo] = self.dom_steps.get(lo, 0) + 1
-            self._adamw(lo, n_r, g, scale, self.dom_steps[lo])
+            self._adamw(lo, n_r, self.arena.dom_decay[lo], g, scale, self.dom_steps[lo])
         # parameters changed underneath torch's version counters: drop the cached bf16 inference copies
         eng.weights._versions.clear()
         eng._stem_w0.clear()

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define HMA_B200_ABI_VERSION 1
+#define HMA_B200_ABI_VERSION 2
 
 int hma_abi_version(void);
 const char* hma_last_error(void);
@@ -187,9 +187,10 @@ int hma_ce_bwd(const float* logits, long long ld, const long long* labels, const
 /* ---------------------------------------------------------------------------------------------
  * MaskGIT sampling (st_mask_git.py:397-453)
  * ------------------------------------------------------------------------------------------- */
-/* exp_noise: fp32 [nv][B*S, vs] Exp(1) draws, HIGH vocabulary half first (null = greedy). */
+/* exp_noise: fp32 [nv][B*S, vs] Exp(1) draws, HIGH vocabulary half first (null = greedy). temperature: the reference
+ * ranks ((softmax / temperature) / sum(softmax / temperature)) / Exp(1); the same fp32 operation sequence is used. */
 int hma_sample_tokens(const float* logits, long long stride_b, long long ld, int B, int S, int nv, int vs,
-                      const float* exp_noise, long long* samples, float* conf, void* stream);
+                      const float* exp_noise, float temperature, long long* samples, float* conf, void* stream);
 /* n_mask < 0: last step (no ranking). frame: prompt[:, out_t] (token (b,s) at frame + b*stride_b + s). */
 int hma_rank_remask(const float* keys, unsigned char* unmasked, const long long* samples, long long* frame,
                     long long stride_b, int B, int S, int n_mask, long long mask_id, long long* out_samples,
@@ -201,9 +202,13 @@ int hma_rank_remask(const float* keys, unsigned char* unmasked, const long long*
 /* *out += sum(g^2) */
 int hma_sumsq(const float* g, long long n, float* out, void* stream);
 /* AdamW with decoupled weight decay; gradient = g * grad_scale * clip where
- * clip = min(1, max_norm / (sqrt(*sumsq) * grad_scale + 1e-6)) if sumsq != NULL. step counts from 1. */
-int hma_adamw_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
-                   float eps, float wd, int step, float grad_scale, const float* sumsq, float max_norm, void* stream);
+ * clip = min(1, max_norm / (sqrt(*sumsq) * grad_scale + 1e-6)) if sumsq != NULL. step counts from 1.
+ * Elements [0, n_decay) are decayed with `wd`, elements [n_decay, n) are not: the two parameter groups of the reference
+ * trainer (train_multi.py:906-917 — names containing "bias" / "layer_norm.weight" get weight_decay 0); the arena lays
+ * every range out as [decayed | not decayed]. n_decay must be a multiple of 4. */
+int hma_adamw_step(float* p, const float* g, float* m, float* v, long long n, long long n_decay, float lr, float beta1,
+                   float beta2, float eps, float wd, int step, float grad_scale, const float* sumsq, float max_norm,
+                   void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * STMAR: continuous-token model with a diffusion-MLP head (hma/model/st_mar.py, hma/model/diffloss.py,
@@ -296,10 +301,6 @@ int hma_gather_token_windows(const void* video, int elem_bytes, long long num_im
                              int window, int stride, int frame_elems, long long* out, void* stream);
 int hma_gather_rows_f32(const float* table, long long num_rows, long long row_elems, const long long* starts, int B,
                         long long rows_per_sample, float* out, void* stream);
-
-/* Test-only: single-CTA tcgen05 descriptor probe (see csrc/probe.cu; params is a HOST int[18]). */
-int hma_umma_probe(const void* A, long long lda, const void* B, long long ldb, const int* params, float* out,
-                   void* stream);
 
 #ifdef __cplusplus
 }

@@ -76,5 +76,7 @@ def apply(tokens: torch.Tensor, d: dict, cfg, h: int, w: int):
         mask = d["mask_r"] < d["mask_prob"]
         out[:, fmf:][mask] = cfg.image_vocab_size
     else:
-        out = out if cfg.dataloader_apply_corruption or "frame_r" in d else x
+        # data.py:69-83: x_THWC is folded back into x_THW (unfactorize_token_ids) only inside `if dataloader_apply_mask`;
+        # otherwise input_ids are the original tokens and the corruption is discarded (checked against the live reference)
+        out = x
     return out.reshape(B, -1), labels.reshape(B, -1)

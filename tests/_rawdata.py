@@ -5,6 +5,10 @@ from pathlib import Path
 
 import numpy as np
 
+# the stub DATA_FREQ_TABLE the golden generators install into the reference (oracle/make_rawtoken_golden.py): the synthetic
+# dataset's name is not in the shipped table, so the tests pass the same stub through `freq_table`
+FREQ = {"synthetic_robot": 6}
+
 CASES = {
     "default": dict(window_size=4, use_actions=True),
     "overlaps": dict(window_size=3, use_actions=True, filter_overlaps=True),

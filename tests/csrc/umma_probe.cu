@@ -2,8 +2,11 @@
 // issues tcgen05.mma with descriptor fields chosen by the host, then dumps the fp32 accumulator.
 // Used by tests/test_umma_probe_gpu.py to pin down (on the real B200) every shared-memory
 // descriptor variant the attention kernels rely on before those kernels depend on it.
-#include "common.cuh"
-#include "../../include/hma_b200.h"
+// TEST INFRASTRUCTURE: built into tests/libhma_b200_probe.so (hma_b200.build.build_probe), not part of the product ABI.
+#include "../../hma_b200/csrc/common.cuh"
+
+extern "C" int hma_umma_probe(const void* A, long long lda, const void* B, long long ldb, const int* params, float* out,
+                              void* stream);
 
 namespace hma {
 
@@ -118,7 +121,8 @@ extern "C" int hma_umma_probe(const void* A, long long lda, const void* B, long 
   if (rc) return rc;
   const size_t smem = 3072 + (size_t)(p.a_rows * p.a_boxes + p.b_rows * p.b_boxes) * sw;
   HMA_REQUIRE(smem <= 200 * 1024, "probe: tiles too large");
-  static bool attr_done = false;
+  static hma_host::PerDeviceFlag attr_flag;  // function attributes are per device (context)
+  bool& attr_done = attr_flag.get();
   if (!attr_done) {
     HMA_CHECK_CUDA(cudaFuncSetAttribute(umma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr_done = true;

@@ -53,6 +53,36 @@ def test_collator_oracle_matches_live_reference_other_seed():
         assert torch.equal(ids, ref["input_ids"]) and torch.equal(labels, ref["labels"])
 
 
+@pytest.mark.skipif(not reference_loader.available(), reason="live reference not present")
+def test_collator_without_masking_returns_the_original_tokens_like_the_reference():
+    """dataloader_apply_mask=False: the reference folds the corrupted factors back only inside `if apply_mask` (data.py:69-83),
+    so input_ids stay the original tokens even with corruption on."""
+    from oracle.make_collator_golden import reference_collator
+    GenieConfig, get_maskgit_collator = reference_collator()
+    cfg = GenieConfig(num_layers=1, num_heads=8, d_model=256, T=6, S=256, num_factored_vocabs=2, non_mlm_ratio=0.5,
+                      dataloader_apply_mask=False, dataloader_apply_corruption=True)
+    for seed in (31, 32):
+        g = torch.Generator().manual_seed(seed)
+        tokens = torch.randint(0, 262144, (2, cfg.T * 256), generator=g)
+        feats = [dict(input_ids=tokens[b].clone(), h=16, w=16, domain="d") for b in range(2)]
+        torch.manual_seed(seed); random.seed(seed)
+        ref = get_maskgit_collator(cfg)(feats)
+        torch.manual_seed(seed); random.seed(seed)
+        ids, labels = C.apply(tokens, C.draw(cfg, 2, 16, 16), cfg, 16, 16)
+        assert torch.equal(ref["input_ids"], tokens) and torch.equal(ids, tokens) and torch.equal(labels, ref["labels"])
+
+
+@pytest.mark.gpu
+def test_device_collator_without_masking_returns_the_original_tokens():
+    from hma_b200 import data
+    cfg = _cfg(dict(num_layers=1, num_heads=8, d_model=256, T=6, S=256, num_factored_vocabs=2, non_mlm_ratio=0.5,
+                    dataloader_apply_mask=False, dataloader_apply_corruption=True))
+    tokens = torch.randint(0, 262144, (2, cfg.T * 256)).cuda()
+    random.seed(3)
+    ids, labels = data.collate_from_draws(tokens, data.draw_on_device(cfg, 2, 16, 16, tokens.device), cfg, 16, 16)
+    assert torch.equal(ids, tokens) and torch.equal(labels, tokens)
+
+
 @pytest.mark.gpu
 def test_device_collator_bit_exact_given_reference_draws():
     from hma_b200 import data

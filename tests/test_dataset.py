@@ -21,7 +21,7 @@ def test_matches_reference_fixture(root, case):
     from hma_b200.dataset import RawTokenDataset
 
     ref = torch.load(GOLDEN, weights_only=False)[case]
-    ds = RawTokenDataset(root, **_rawdata.CASES[case])
+    ds = RawTokenDataset(root, freq_table=_rawdata.FREQ, **_rawdata.CASES[case])
     assert ds.stride == ref["stride"] and ds.n_action == ref["n_action"] and ds.num_videos == ref["num_videos"]
     assert len(ds) == ref["len"] and list(ds.valid_start_inds) == ref["valid_start_inds"]
     np.random.seed(0)
@@ -45,7 +45,7 @@ def test_edge_cases(tmp_path):
     (r / "segment_ids.bin").unlink()
     with pytest.raises(NotImplementedError):
         RawTokenDataset(r, window_size=2)
-    assert len(RawTokenDataset(r, window_size=2, filter_interrupts=False)) == 10 - 3 - 3
+    assert len(RawTokenDataset(r, window_size=2, filter_interrupts=False, freq_table=_rawdata.FREQ)) == 10 - 3 - 3
     with pytest.raises(RuntimeError, match="to_device"):
         RawTokenDataset(r, window_size=2, filter_interrupts=False).gather([0])
 
@@ -56,7 +56,7 @@ def test_device_gather_equals_host_items(tmp_path, dtype):
     from hma_b200.dataset import RawTokenDataset
 
     r = _rawdata.write(tmp_path / dtype, seed=2, num_images=300, token_dtype=dtype)
-    ds = RawTokenDataset(r, window_size=4, use_actions=True).to_device("cuda")
+    ds = RawTokenDataset(r, window_size=4, use_actions=True, freq_table=_rawdata.FREQ).to_device("cuda")
     g = torch.Generator().manual_seed(0)
     idx = torch.randint(0, len(ds), (33,), generator=g)
     out = ds.gather(idx)
@@ -91,7 +91,7 @@ def test_feature_dataset_and_collator_match_reference_fixture(feature_root, case
     from hma_b200.mar import DiffusionGenieConfig
 
     ref = torch.load(GOLDEN, weights_only=False)["feature_" + case]
-    ds = RawFeatureDataset(feature_root, **_rawdata.FEATURE_CASES[case])
+    ds = RawFeatureDataset(feature_root, freq_table=_rawdata.FREQ, **_rawdata.FEATURE_CASES[case])
     assert ds.stride == ref["stride"] and ds.n_action == ref["n_action"]
     assert len(ds) == ref["len"] and list(ds.valid_start_inds) == ref["valid_start_inds"]
     items = [ds[i] for i in ref["idx"]]

@@ -217,7 +217,7 @@ def test_sample_and_remask():
     conf = torch.zeros(B * S, device="cuda")
     probs = lg.reshape(B * S, nv, vs).softmax(-1)
     # greedy
-    _lib.call("hma_sample_tokens", lg.data_ptr(), lg.stride(0), lg.stride(1), B, S, nv, vs, None, samples.data_ptr(),
+    _lib.call("hma_sample_tokens", lg.data_ptr(), lg.stride(0), lg.stride(1), B, S, nv, vs, None, 1.0, samples.data_ptr(),
               conf.data_ptr(), S_())
     torch.cuda.synchronize()
     hi, lo = probs[:, 1].argmax(-1), probs[:, 0].argmax(-1)
@@ -226,7 +226,7 @@ def test_sample_and_remask():
     assert torch.allclose(conf, ref_conf, rtol=1e-4)
     # sampling with injected Exp(1) noise (hi first)
     q = torch.empty(nv, B * S, vs, device="cuda").exponential_(1)
-    _lib.call("hma_sample_tokens", lg.data_ptr(), lg.stride(0), lg.stride(1), B, S, nv, vs, q.data_ptr(),
+    _lib.call("hma_sample_tokens", lg.data_ptr(), lg.stride(0), lg.stride(1), B, S, nv, vs, q.data_ptr(), 1.0,
               samples.data_ptr(), conf.data_ptr(), S_())
     torch.cuda.synchronize()
     hi, lo = (probs[:, 1] / q[0]).argmax(-1), (probs[:, 0] / q[1]).argmax(-1)

@@ -60,7 +60,7 @@ def test_c_abi_exports_every_declared_symbol():
     assert len(names) >= 20
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/hma_b200.h but not exported"
-    assert lib.hma_abi_version() == 1
+    assert lib.hma_abi_version() == 2
 
 
 def test_forward_consumes_cpu_rng_like_the_reference(monkeypatch):
@@ -113,3 +113,38 @@ def test_config_fields_and_defaults_equal_the_reference():
     kw = dict(num_layers=2, num_heads=8, d_model=256, num_factored_vocabs=2)
     assert vars(R(**kw)) == vars(GenieConfig(**kw))
     assert vars(RD(patch_size=2, **kw)) == vars(DiffusionGenieConfig(patch_size=2, **kw))
+
+
+def test_save_pretrained_from_pretrained_roundtrip(tmp_path):
+    """The reference's checkpoint path (evaluate.py:141, generate.py:110, train_multi.py:310-321): config + weights through
+    PyTorchModelHubMixin, for both model classes, and again after a TrainStep has re-homed the parameters into its arena."""
+    import torch
+    from hma_b200 import DiffusionGenieConfig, GenieConfig, STMaskGIT
+    from hma_b200.mar import STMAR
+    from hma_b200.train import TrainStep
+
+    stats = [[[0.0] * 7, [1.0] * 7], [[0.0] * 14, [1.0] * 14]]
+    for cls, cfg in ((STMaskGIT, GenieConfig(num_layers=2, num_heads=8, d_model=256, T=4, S=256, num_factored_vocabs=2,
+                                             action_network="concat+modulate")),
+                     (STMAR, DiffusionGenieConfig(num_layers=2, num_heads=8, d_model=256, T=4, S=256, num_factored_vocabs=2,
+                                                  patch_size=2, action_network="concat+modulate"))):
+        torch.manual_seed(0)
+        m = cls(cfg)
+        m.init_action_projectors(["a", "b"], [7, 14], stats, "concat+modulate")
+        with torch.no_grad():
+            for p in m.parameters():
+                p.normal_(0.0, 0.1)
+        m.save_pretrained(tmp_path / cls.__name__)
+        m2 = cls.from_pretrained(tmp_path / cls.__name__)
+        assert type(m2.config) is type(cfg) and m2.config.action_domains == ["a", "b"]
+        sd1, sd2 = m.state_dict(), m2.state_dict()
+        assert list(sd1) == list(sd2) and all(torch.equal(sd1[k], sd2[k]) for k in sd1)
+    # parameters re-homed into the TrainStep arena are views of one storage: save_pretrained must still work
+    m = STMaskGIT(GenieConfig(num_layers=2, num_heads=8, d_model=256, T=4, S=256, num_factored_vocabs=2,
+                              action_network="concat+modulate"))
+    m.init_action_projectors(["a", "b"], [7, 14], stats, "concat+modulate")
+    before = {k: v.clone() for k, v in m.state_dict().items()}
+    TrainStep(m)
+    m.save_pretrained(tmp_path / "arena")
+    m3 = STMaskGIT.from_pretrained(tmp_path / "arena")
+    assert all(torch.equal(before[k], v) for k, v in m3.state_dict().items())

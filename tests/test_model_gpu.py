@@ -128,7 +128,7 @@ def test_maskgit_decode_bit_exact_given_identical_logits_and_noise(setup):
         for step in range(steps):
             lg = logits_steps[step].permute(0, 2, 3, 4, 1).reshape(B, T, S, nv * vs)[:, T - 1].contiguous().cuda()
             nz = torch.stack(noise["exp"][step]).cuda() if temperature > 1e-8 else None
-            new, conf = ops.sample_tokens(lg, nv, vs, nz)
+            new, conf = ops.sample_tokens(lg, nv, vs, nz, temperature if nz is not None else 1.0)
             if step != steps - 1:
                 n = math.ceil(O.cosine_schedule((step + 1) / steps) * S)
                 keys = conf if mode == "greedy" else noise["rand"][step].reshape(B, S).cuda()

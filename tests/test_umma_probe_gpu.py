@@ -5,9 +5,23 @@ import ctypes
 import pytest
 import torch
 
-from hma_b200 import _lib
+from hma_b200 import _lib, build as _build
 
 pytestmark = pytest.mark.gpu
+
+_PROBE = None
+
+
+def _probe_lib():
+    """The probe is test infrastructure with its own shared library (tests/libhma_b200_probe.so, built by
+    hma_b200.build.build_probe); it is not an entry point of the product ABI."""
+    global _PROBE
+    if _PROBE is None:
+        _PROBE = ctypes.CDLL(str(_build.build_probe()))
+        _PROBE.hma_umma_probe.argtypes = [ctypes.c_void_p, ctypes.c_longlong, ctypes.c_void_p, ctypes.c_longlong, ctypes.c_void_p,
+                                          ctypes.c_void_p, ctypes.c_void_p]
+        _PROBE.hma_umma_probe.restype = ctypes.c_int
+    return _PROBE
 
 
 def probe(A, B, *, box_inner, layout_type, a_rows, a_boxes, b_rows, b_boxes, a_major, b_major, a_off=0, b_off=0,
@@ -15,8 +29,9 @@ def probe(A, B, *, box_inner, layout_type, a_rows, a_boxes, b_rows, b_boxes, a_m
     params = (ctypes.c_int * 18)(a_rows, a_boxes, b_rows, b_boxes, box_inner, layout_type, a_major, b_major, a_off,
                                  b_off, a_lbo, a_sbo, b_lbo, b_sbo, ksteps, a_kstep, b_kstep, N)
     out = torch.zeros(128, N, device="cuda")
-    _lib.call("hma_umma_probe", A.data_ptr(), A.stride(0), B.data_ptr(), B.stride(0),
-              ctypes.cast(params, ctypes.c_void_p), out.data_ptr(), _lib.current_stream())
+    rc = _probe_lib().hma_umma_probe(A.data_ptr(), A.stride(0), B.data_ptr(), B.stride(0),
+                                     ctypes.cast(params, ctypes.c_void_p), out.data_ptr(), _lib.current_stream())
+    assert rc == 0, rc
     torch.cuda.synchronize()
     return out
 
