@@ -59,7 +59,7 @@ def test_mar_entry_points_reject_unsupported_configurations():
 def test_row_and_attention_entry_points_reject_bad_arguments():
     rc, msg = _call("hma_colsum_bf16", P, 4096, 128, 4096, P, None)
     assert rc < 0 and "<= 2048" in msg
-    rc, msg = _call("hma_adamw_step", P, P, P, P, 1024, 1e-4, 0.9, 0.999, 1e-8, 0.0, 0, 1.0, None, 1.0, None)
+    rc, msg = _call("hma_adamw_step", P, P, P, P, 1024, 1024, 1e-4, 0.9, 0.999, 1e-8, 0.0, 0, 1.0, None, 1.0, None)
     assert rc < 0 and "step counts from 1" in msg
     rc, msg = _call("hma_sumsq", P + 4, 1024, P, None)
     assert rc < 0 and "aligned" in msg
