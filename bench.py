@@ -250,6 +250,172 @@ def run_reference_arm(args) -> None:
     print(json.dumps(line), flush=True)
 
 
+def decode_flops_per_sample(Tp: int, Tn: int, K: int) -> float:
+    """FLOPs the frame-incremental decode actually executes for one sample of generate(Tp prompt -> Tn new frames, K MaskGIT
+    steps): one prefill of the Tp context frames (no head), then per new frame K one-frame passes with the head and (except
+    for the last frame) one "commit" pass without it; a one-frame pass at window position t attends t+1 cached frames."""
+    n, d = N_TOK_FRAME, D_MODEL
+    per_tok = 34 * d * d + 4 * n * d
+    prefill = Tp * n * L * (per_tok + 4 * d * (Tp + 1) / 2) + 6 * d * d * Tp * L
+    head = S * 2 * d * 1024
+    total = prefill
+    for t in range(Tp, Tp + Tn):
+        one = n * L * (per_tok + 4 * d * (t + 1)) + 6 * d * d * L
+        total += K * (one + head) + (one if t != Tp + Tn - 1 else 0.0)
+    return total
+
+
+def interactive_leg(model, dev, domains, d_actions, horizon: int = 8, K: int = 2, iters: int = 20):
+    """SURVEY.md §8(f) rank 3, the loop of sim/simulator.py:233-372: B=1, a sliding window of `horizon` past frames, one
+    maskgit_generate() per simulator step with the new action, tokens read back to the host (the simulator decodes them to
+    pixels next). Wall-clock latency per step through the public API (host-synchronous by construction)."""
+    model.eval()
+    model._sessions.clear()
+    g = torch.Generator().manual_seed(1)
+    P = horizon
+    frames = torch.randint(0, 262144, (P, 16, 16), generator=g).to(dev)
+    actions = torch.randn(P, d_actions[1], generator=g).to(dev)
+    lat = []
+    for it in range(iters + 5):
+        a = torch.randn(1, d_actions[1], generator=g).to(dev)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        window = torch.cat([frames, torch.zeros_like(frames[:1])]).unsqueeze(0)[:, : P + 1].long().contiguous()
+        window[:, -1] = model.mask_token_id
+        acts = torch.cat([actions, a, a]).view(1, -1, a.shape[-1])[:, : P + 1].float().contiguous()
+        nxt = model.maskgit_generate(window, out_t=P, maskgit_steps=K, temperature=1.0, action_ids=acts,
+                                     domain=[domains[1]])[0].squeeze(0)
+        nxt.cpu()
+        t1 = time.perf_counter()
+        frames = torch.cat([frames[1:], nxt.unsqueeze(0)])
+        actions = torch.cat([actions[1:], a])
+        if it >= 5:
+            lat.append((t1 - t0) * 1e3)
+    lat.sort()
+    model._sessions.clear()
+    model.train()
+    return {"metric": "interactive_step_latency_ms", "median_ms": lat[len(lat) // 2], "p90_ms": lat[int(len(lat) * 0.9)],
+            "frames_per_s": 1e3 / lat[len(lat) // 2], "higher_is_better": False,
+            "config": {"batch": 1, "prompt_horizon": P, "maskgit_steps": K, "layers": model.config.num_layers,
+                       "loop": "sim/simulator.py:233-372 shape: slide the window, maskgit_generate(out_t=horizon), tokens to host",
+                       "algorithm": "per-session temporal K/V cache, CUDA-graph replay of prefill and one-frame passes"}}
+
+
+def pipeline_leg(dev, cfg_T: int = T, batch: int = B_PER_GPU, batches: int = 40):
+    """feed rate of the on-device data path (MultiTaskBatchSampler -> index gather from the HBM-resident
+    token / action tables -> on-device MaskGIT collator), in samples/s, next to the training step's consumption rate.
+    Synthetic datasets in the reference's on-disk format (tests/_rawdata.py layout) written to a temp directory."""
+    import tempfile
+
+    import numpy as np
+
+    from hma_b200 import GenieConfig
+    from hma_b200.dataset import RawTokenDataset
+    from hma_b200.sampler import DeviceBatchPipeline
+    with tempfile.TemporaryDirectory() as tmp:
+        dsets = []
+        for j, (n_img, adim) in enumerate(((20000, 7), (12000, 14))):
+            root = os.path.join(tmp, f"ds{j}")
+            os.makedirs(os.path.join(root, "actions"))
+            rng = np.random.default_rng(j)
+            arrs = {"video.bin": rng.integers(0, 2 ** 18, size=(n_img, 16, 16)).astype(np.uint32),
+                    "segment_ids.bin": (np.arange(n_img) // 200).astype(np.int32),
+                    "actions/actions.bin": rng.normal(size=(n_img, adim)).astype(np.float32)}
+            for name, arr in arrs.items():
+                arr.tofile(os.path.join(root, name))
+            with open(os.path.join(root, "metadata.json"), "w") as fh:
+                json.dump({"token_dtype": "uint32", "action_dim": adim, "s": 16, "h": 16, "w": 16, "vocab_size": 2 ** 18, "hz": 2,
+                           "num_images": n_img, "name": f"bench_robot_{j}"}, fh)
+            dsets.append(RawTokenDataset(root, window_size=cfg_T, use_actions=True, freq_table={}).to_device(dev))
+        cfg = GenieConfig(num_layers=1, num_heads=HEADS, d_model=D_MODEL, T=cfg_T, S=S, num_factored_vocabs=2,
+                          dataloader_apply_corruption=True, non_mlm_ratio=0.5)
+        pipe = DeviceBatchPipeline(dsets, cfg, batch_size=batch, seed=0)
+        it = iter(pipe)
+        for _ in range(5):
+            next(it)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        for _ in range(batches):
+            b = next(it)
+        e1.record()
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+        return {"metric": "device_pipeline_samples_per_s", "value": batches * batch / wall, "unit": "samples/s",
+                "ms_per_batch_wall": wall / batches * 1e3, "ms_per_batch_device": e0.elapsed_time(e1) / batches,
+                "config": {"batch": batch, "T": cfg_T, "datasets": 2, "corruption": True, "non_mlm_ratio": 0.5,
+                           "path": "sampler (host index draw) -> hma_gather_token_windows / hma_gather_rows_f32 -> "
+                                   "torch device RNG draws -> hma_collate_maskgit"}}
+
+
+def gpu_reference_leg(dev, steps: int = 3, warmup: int = 1):
+    """SURVEY.md §8(d) / BASELINE.md §5, "the bar to beat on the same box": the reference's algorithm in plain PyTorch on the
+    SAME B200 under torch.autocast(bf16) — cuBLAS GEMMs, ATen element-wise kernels and (i) the reference's own math attention
+    (BasicSelfAttention, attention.py:37-61), (ii) fused attention through scaled_dot_product_attention (what the reference
+    gets from xformers, attention.py:139-155). It is the oracle module (a restatement pinned on the real reference), never
+    part of the product path. Training: fwd + loss + bwd of the config-2 batch (no optimizer: flattering to the reference);
+    generation: the reference algorithm (full-window recompute per MaskGIT step) at batch 64."""
+    from oracle import stmaskgit_oracle as O
+    cfg = O.OracleConfig(num_layers=L, num_heads=HEADS, d_model=D_MODEL, T=T, S=S, num_factored_vocabs=2, qk_norm=False,
+                         action_network="concat+modulate")
+    sd = O.make_state_dict(cfg, ["dom00"], [D_ACTION_CYCLE[0]], seed=0, action_dims=[ACTION_DIM_CYCLE[0]])
+    params = {k: v.to(dev).requires_grad_(v.is_floating_point() and "action_preprocessor" not in k) for k, v in sd.items()}
+    gen = torch.Generator().manual_seed(1234)
+    ids, labels, actions = (t.to(dev) for t in synthetic_batch(gen, B_PER_GPU, D_ACTION_CYCLE[0]))
+    dom = ["dom00"] * B_PER_GPU
+    out = {}
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for impl in ("math", "sdpa"):
+        O.ATTENTION_IMPL = impl
+        try:
+            for i in range(warmup + steps):
+                if i == warmup:
+                    torch.cuda.synchronize()
+                    e0.record()
+                with torch.autocast("cuda", dtype=torch.bfloat16):
+                    loss, _, _ = O.forward(ids, labels, actions, dom, params, cfg)
+                loss.backward()
+                for v in params.values():
+                    v.grad = None
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / steps
+            out[f"train_{impl}"] = {"value": B_PER_GPU * T * S / (ms / 1e3), "unit": "tokens/s", "ms_per_step": ms,
+                                    "loss": float(loss)}
+        finally:
+            O.ATTENTION_IMPL = "math"
+        torch.cuda.empty_cache()
+    # generation, reference algorithm, batch 64 (fused attention: the faster of the two above)
+    Tp, Tn, K, Bg = 8, T - 8, 2, 64
+    prompt = torch.randint(0, 262144, (Bg, Tp * S), generator=gen).to(dev)
+    acts = torch.randn(Bg, T, D_ACTION_CYCLE[0], generator=gen).to(dev)
+    nograd = {k: v.detach() for k, v in params.items()}
+    O.ATTENTION_IMPL = "sdpa"
+    try:
+        for i in range(2):
+            if i == 1:
+                torch.cuda.synchronize()
+                e0.record()
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                toks, _ = O.generate(prompt, Tn * S, nograd, cfg, 16, 16, maskgit_steps=K, temperature=1.0, action_ids=acts,
+                                     domain=["dom00"] * Bg)
+            toks.cpu()
+        e1.record()
+        torch.cuda.synchronize()
+    finally:
+        O.ATTENTION_IMPL = "math"
+    ms = e0.elapsed_time(e1)
+    out["generate_sdpa"] = {"value": Bg * Tn / (ms / 1e3), "unit": "frames/s", "ms_per_generate_call": ms, "batch": Bg,
+                            "maskgit_steps": K}
+    out["what"] = ("the reference's algorithm as plain PyTorch (oracle module) on this GPU under torch.autocast(bf16): 32 layers, "
+                   "B=8, T=16 fwd+loss+bwd without optimizer step; math = BasicSelfAttention, sdpa = fused attention; generation = "
+                   "full-window recompute per MaskGIT step at batch 64")
+    del params, nograd
+    torch.cuda.empty_cache()
+    return out
+
+
 def generation_leg(model, dev, world, rank, domains, d_actions, sync_all, reps: int = 3, per_gpu: bool = True):
     """BASELINE configs[2]: 8 prompt frames -> 8 generated frames, 16x16 tokens, batch 64 split over the GPUs (replicas,
     no collective), maskgit_steps 2, temperature 1, through the public STMaskGIT.generate API. Host prompt in, host
@@ -299,6 +465,8 @@ def main() -> None:
     ap.add_argument("--no-graphs", action="store_true", help="launch every kernel from the host instead of replaying CUDA graphs")
     ap.add_argument("--no-generation", action="store_true", help="skip the MaskGIT generation leg (BASELINE configs[2])")
     ap.add_argument("--no-mar", action="store_true", help="skip the HMA-MAR leg (BASELINE configs[3])")
+    ap.add_argument("--no-gpu-reference", action="store_true", help="skip the plain-PyTorch-on-this-GPU reference leg")
+    ap.add_argument("--no-extras", action="store_true", help="skip the interactive-latency and data-pipeline legs")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)
@@ -430,6 +598,13 @@ def main() -> None:
         if world > 1:  # the same 64 samples split over the GPUs (strong scaling), for reference
             gen_strong = generation_leg(model, dev, world, rank, domains, d_actions, sync_all, per_gpu=False)
 
+    # ---------------- interactive single-frame loop (B=1) and the on-device data pipeline (rank 0 only: no collective)
+    interactive = pipeline = None
+    if not args.no_extras and rank == 0:
+        interactive = interactive_leg(model, dev, domains, d_actions)
+        pipeline = pipeline_leg(dev)
+    sync_all()
+
     # ---------------- optional per-stage breakdown (one extra, untimed step)
     if args.breakdown and rank == 0:
         ops.PROFILER = ops.Profiler()
@@ -448,6 +623,13 @@ def main() -> None:
         model = None
         torch.cuda.empty_cache()
         mar = mar_leg(dev, world, rank, sync_all, args.layers)
+
+    # ---------------- the reference algorithm as plain PyTorch on this same GPU (rank 0, N = 1 only)
+    gpu_ref = None
+    if not args.no_gpu_reference and world == 1:
+        step_fn = run_resident = model = None
+        torch.cuda.empty_cache()
+        gpu_ref = gpu_reference_leg(dev)
 
     if rank != 0:
         if world > 1:
@@ -518,9 +700,27 @@ def main() -> None:
                                     "one-frame pass (reference algorithm recomputes the 16-frame window per MaskGIT step)",
                        "io": "pinned host prompt/actions in, host tokens out, inside the timed region",
                        "scaling": "weak (batch 64 per GPU)"}}
+        gflops = decode_flops_per_sample(8, T - 8, 2) * (args.layers / L) * gen_b
+        ach = gflops / (gen_ms / 1e3) / 1e12
+        line["generation"]["roofline"] = {
+            "bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf if peak_tf else None,
+            "traffic": None, "flops_per_generate_call": gflops,
+            "what": "FLOPs the frame-incremental decode executes per generate() call (prefill of 8 frames + per new frame K one-frame "
+                    "passes with the head + one commit pass) / device time of the call, H2D prompt and D2H tokens included"}
         if gen_strong is not None:
             line["generation"]["strong_scaling_total_batch_64"] = {"value": gen_strong[0], "unit": "frames/s",
                                                                     "ms_per_generate_call": gen_strong[1], "batch_per_gpu": gen_strong[2]}
+    if interactive is not None:
+        line["interactive"] = interactive
+    if pipeline is not None:
+        pipeline["train_step_consumes_samples_per_s"] = B_PER_GPU * args.steps / (ms_resident / 1e3)
+        line["pipeline"] = pipeline
+    if gpu_ref is not None:
+        gpu_ref["speedup_train_vs_sdpa"] = value / gpu_ref["train_sdpa"]["value"]
+        gpu_ref["speedup_train_vs_math"] = value / gpu_ref["train_math"]["value"]
+        if gen_fps is not None:
+            gpu_ref["speedup_generate_vs_sdpa"] = gen_fps / gpu_ref["generate_sdpa"]["value"]
+        line["gpu_reference"] = gpu_ref
     if mar is not None:
         line["mar"] = mar
     if not args.no_cpu_baseline and world == 1:

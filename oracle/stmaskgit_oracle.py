@@ -101,6 +101,13 @@ def action_stem(a_BTD: Tensor, sd: SD, dom: str, skip_normalization: bool = Fals
 # --------------------------------------------------------------------------------------------
 # attention (attention.py:37-61, the in-repo restatement of the xformers call at :139-155)
 # --------------------------------------------------------------------------------------------
+# "math": BasicSelfAttention (attention.py:37-61), what the reference runs with XFORMERS_DISABLED — the parity pin.
+# "sdpa": the fused-attention variant (attention.py:139-155 calls xformers' memory_efficient_attention, i.e. FlashAttention;
+#         torch's scaled_dot_product_attention is the same algorithm) — only used by bench.py's GPU reference leg.
+ATTENTION_IMPL = "math"
+CHECKPOINT_LAYERS = False  # torch.utils.checkpoint around every ST block (full-size GPU parity tests: caps activation memory)
+
+
 def self_attention(x_BNC: Tensor, sd: SD, prefix: str, cfg: OracleConfig, causal: bool) -> Tensor:
     B, N, C = x_BNC.shape
     H = cfg.num_heads
@@ -110,6 +117,9 @@ def self_attention(x_BNC: Tensor, sd: SD, prefix: str, cfg: OracleConfig, causal
         w, b = sd[prefix + "norm.weight"], sd[prefix + "norm.bias"]
         q = F.layer_norm(q, (C // H,), w, b, 1e-5)
         k = F.layer_norm(k, (C // H,), w, b, 1e-5)
+    if ATTENTION_IMPL == "sdpa":
+        o = F.scaled_dot_product_attention(q.to(v.dtype), k.to(v.dtype), v, is_causal=causal, scale=cfg.attn_scale)
+        return F.linear(o.transpose(1, 2).reshape(B, N, C), sd[prefix + "proj.weight"], sd.get(prefix + "proj.bias"))
     s = (q * cfg.attn_scale) @ k.transpose(-2, -1)
     if causal:  # attention.py:51-55
         keep = torch.ones(N, N, dtype=torch.bool, device=x_BNC.device).tril()
@@ -187,7 +197,11 @@ def hidden_states(x_THW: Tensor, action_ids: Optional[Tensor], domain: Optional[
             x = torch.cat([x, a[:, :T, None].expand(-1, -1, cfg.action_token_size, -1)], dim=2)
     x = x + sd["pos_embed_TSC"][:, :T, : x.shape[2]]  # :670-672
     for i in range(cfg.num_layers if layers is None else layers):
-        x = st_block(x, a, sd, i, dom, cfg)
+        if CHECKPOINT_LAYERS and torch.is_grad_enabled():
+            from torch.utils.checkpoint import checkpoint
+            x = checkpoint(lambda xx, aa, i=i: st_block(xx, aa, sd, i, dom, cfg), x, a, use_reentrant=False)
+        else:
+            x = st_block(x, a, sd, i, dom, cfg)
     return x
 
 
@@ -257,7 +271,8 @@ def maskgit_generate(prompt_THW: Tensor, out_t: int, sd: SD, cfg: OracleConfig, 
     B, T, H, W = prompt_THW.shape
     S = H * W
     nv, vs = cfg.num_factored_vocabs, cfg.factored_vocab_size
-    unmasked = torch.zeros(B, S, dtype=torch.bool)
+    dev = prompt_THW.device
+    unmasked = torch.zeros(B, S, dtype=torch.bool, device=dev)
     orig = None
     samples = None
     for step in range(maskgit_steps):
@@ -266,8 +281,8 @@ def maskgit_generate(prompt_THW: Tensor, out_t: int, sd: SD, cfg: OracleConfig, 
             orig = logits.clone()
         fl = logits.reshape(B, nv, vs, H, W).permute(0, 2, 1, 3, 4)  # b vs nv h w
         probs = fl.softmax(dim=1)
-        samples = torch.zeros(B, H, W, dtype=torch.long)
-        conf = torch.ones(B, H, W)
+        samples = torch.zeros(B, H, W, dtype=torch.long, device=dev)
+        conf = torch.ones(B, H, W, device=dev)
         for j, k in enumerate(reversed(range(nv))):  # .flip(2).unbind(2): high factor first (:408)
             p = probs[:, :, k]  # b vs h w
             if temperature <= 1e-8:
@@ -296,7 +311,7 @@ def maskgit_generate(prompt_THW: Tensor, out_t: int, sd: SD, cfg: OracleConfig, 
                 if noise is not None:
                     keys = noise["rand"][step].reshape(B, S).clone()
                 else:
-                    keys = torch.rand(B, H, W, generator=generator).reshape(B, S)
+                    keys = torch.rand(B, H, W, generator=generator, device=dev).reshape(B, S)
             else:
                 raise NotImplementedError(unmask_mode)
             keys[unmasked] = torch.inf
@@ -318,7 +333,7 @@ def generate(input_ids: Tensor, max_new_tokens: int, sd: SD, cfg: OracleConfig, 
     S = h * w
     n_new = max_new_tokens // S
     prompt = input_ids.clone().reshape(B, -1, h, w)
-    full = torch.cat([prompt, torch.full((B, n_new, h, w), cfg.mask_token_id, dtype=torch.long)], dim=1)
+    full = torch.cat([prompt, torch.full((B, n_new, h, w), cfg.mask_token_id, dtype=torch.long, device=prompt.device)], dim=1)
     all_logits = []
     for t in range(prompt.shape[1], prompt.shape[1] + n_new):
         s, fl = maskgit_generate(full, t, sd, cfg, maskgit_steps, temperature, unmask_mode, action_ids, domain,

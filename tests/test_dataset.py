@@ -110,3 +110,62 @@ def test_feature_dataset_and_collator_match_reference_fixture(feature_root, case
         assert torch.equal(b["input_ids"], torch.stack([it["input_ids"] for it in items]))
         assert torch.equal(b["labels"], b["input_ids"]) and b["labels"].data_ptr() != b["input_ids"].data_ptr()
         assert b["domain"] == [ref["domain"]] * len(items) and b["h"] == [8] * len(items)
+
+
+@pytest.mark.gpu
+def test_device_batch_pipeline_end_to_end(tmp_path):
+    """MultiTaskBatchSampler -> device gather -> on-device collator (DeviceBatchPipeline), two datasets of different action
+    widths: every batch comes from ONE dataset (= one action domain, external/data_sampler.py:177-303), its labels are
+    exactly the host-path windows of the sampled indices, frame 0 and the prompt frames of the non-MLM branch are never
+    masked, and a 2-layer model trains on the stream through TrainStep."""
+    import random
+
+    from hma_b200 import GenieConfig, STMaskGIT
+    from hma_b200.dataset import RawTokenDataset
+    from hma_b200.sampler import DeviceBatchPipeline
+    from hma_b200.train import TrainStep
+
+    T = 6
+    roots = [_rawdata.write(tmp_path / "a", seed=5, num_images=400, action_dim=7),
+             _rawdata.write(tmp_path / "b", seed=6, num_images=300, action_dim=3)]
+    names = ["robot_a", "robot_b"]
+    dsets = [RawTokenDataset(r, window_size=T, use_actions=True, name=n, freq_table={}).to_device("cuda") for r, n in zip(roots, names)]
+    # num_prompt_frames < T so that the non-MLM branch's random.randint(num_prompt_frames, T - 1) is valid (data.py:55)
+    cfg = GenieConfig(num_layers=2, num_heads=8, d_model=256, T=T, S=256, num_factored_vocabs=2, non_mlm_ratio=0.5,
+                      num_prompt_frames=2, dataloader_apply_corruption=True, action_network="concat+modulate")
+    pipe = DeviceBatchPipeline(dsets, cfg, batch_size=4, seed=3)
+    random.seed(0)
+    torch.manual_seed(0)
+    plan = list(pipe.sampler.iter_tasks())
+    seen = set()
+    batches = []
+    for (task, local), batch in zip(plan, pipe):
+        ds = dsets[task]
+        seen.add(task)
+        assert batch["domain"] == [names[task]] * 4 and batch["input_ids"].is_cuda and batch["input_ids"].shape == (4, T * 256)
+        want = torch.stack([ds[int(i)]["input_ids"] for i in local])
+        assert torch.equal(batch["labels"].cpu(), want)
+        assert batch["action_ids"].shape == (4, T, ds.n_action)
+        x = batch["input_ids"].view(4, T, 256)
+        assert (x[:, 0] != cfg.image_vocab_size).all() and (x == cfg.image_vocab_size).any()
+        batches.append(batch)
+        if len(batches) == 12:
+            break
+    assert seen == {0, 1}
+    torch.manual_seed(0)
+    with torch.device("cuda"):
+        model = STMaskGIT(cfg)
+        model.init_action_projectors(names, [d.n_action for d in dsets], [d.action_stat for d in dsets], "concat+modulate")
+    with torch.no_grad():
+        for p in model.parameters():
+            if p.dim() >= 2:
+                p.normal_(0.0, 0.05)
+    step = TrainStep(model, lr=3e-3, weight_decay=0.0)
+    first = last = None
+    for rep in range(3):
+        for b in batches:
+            loss = step(b["input_ids"], b["labels"], b["action_ids"], b["domain"])[0].item()
+            assert loss == loss
+            first = loss if first is None else first
+            last = loss
+    assert last < first, (first, last)

@@ -1,4 +1,5 @@
-"""Size-independent properties at BASELINE.json's FULL sizes (the oracle is too slow there):
+"""BASELINE.json's FULL sizes: parity against the fp32 oracle run on the GPU as the checker (second half of this file), and
+size-independent properties of the CUDA path:
 config 2 = HMA-MagVit 32 layers, B=8, T=16, 16x16 tokens + 64 action tokens; config 3 = generate 8 -> 8 frames, B=64.
 
   causality               logits of frames <= t do not move (bit-exact) when tokens / actions of frames > t change
@@ -176,4 +177,158 @@ def test_maskgit_invariants_full_size(model):
                           h=[16], w=[16])
     assert toks.shape == (B, T * S) and (toks != 262144).all()
     assert torch.equal(toks[:, : Tp * S], prompt_frames.reshape(B, -1))
+    model._sessions.clear()
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Parity against the ORACLE at BASELINE.json's full sizes. The oracle is plain torch, so it runs on the B200 itself in
+# fp32 (true fp32: TF32 is off for matmuls by default) as the CHECKER — activation checkpointing per ST block keeps its
+# autograd memory at one layer. 32 layers of bf16 operand rounding on the fp32 residual stream is exactly what the
+# 2-layer fixtures cannot show. Tolerances are north_star's: loss and logits within 1e-2 relative (logits: of the
+# largest |logit|), every parameter-gradient norm within 5 %.
+# ------------------------------------------------------------------------------------------------------------------
+def _oracle_cfg(cfg):
+    from oracle import stmaskgit_oracle as O
+    return O.OracleConfig(num_layers=cfg.num_layers, num_heads=cfg.num_heads, d_model=cfg.d_model, T=cfg.T, S=cfg.S,
+                          num_factored_vocabs=cfg.num_factored_vocabs, use_mup=cfg.use_mup, qkv_bias=cfg.qkv_bias,
+                          proj_bias=cfg.proj_bias, qk_norm=cfg.qk_norm, mlp_bias=cfg.mlp_bias, action_network=cfg.action_network)
+
+
+def _collated(B, Tn, d_action, seed):
+    """Collator distribution (data.py:42-83): per (sample, frame >= 1) mask rate cos(pi/2 U)."""
+    g = torch.Generator().manual_seed(seed)
+    labels = torch.randint(0, 262144, (B, Tn * S), generator=g)
+    rate = torch.cos(math.pi / 2 * torch.rand(B, Tn, 1, generator=g))
+    rate[:, 0] = 0.0
+    mask = torch.rand(B, Tn, S, generator=g) < rate
+    ids = torch.where(mask.view(B, -1), torch.full_like(labels, 262144), labels)
+    return ids.cuda(), labels.cuda(), torch.randn(B, Tn, d_action, generator=g).cuda()
+
+
+def _train_parity(m, B, Tn, dom_i, seed):
+    from oracle import stmaskgit_oracle as O
+    ids, labels, acts = _collated(B, Tn, D_ACTIONS[dom_i], seed)
+    dom = [DOMAINS[dom_i]] * B
+    m.zero_grad(set_to_none=True)
+    out = m(ids, labels, action_ids=acts, domain=dom)
+    out.loss.backward()
+    got_logits = out.logits.float()
+    params = {k: v.detach().clone().requires_grad_(v.is_floating_point() and "action_preprocessor" not in k)
+              for k, v in m.state_dict().items()}
+    O.CHECKPOINT_LAYERS = True
+    try:
+        loss, acc, logits = O.forward(ids, labels, acts, dom, params, _oracle_cfg(m.config))
+        loss.backward()
+    finally:
+        O.CHECKPOINT_LAYERS = False
+    rel = abs(out.loss.item() - loss.item()) / abs(loss.item())
+    dl = (got_logits - logits.detach()).abs()
+    lmax = logits.detach().abs().max().item()
+    rms = (dl.pow(2).mean().sqrt() / logits.detach().pow(2).mean().sqrt()).item()
+    assert rel <= 1e-2, (out.loss.item(), loss.item())
+    assert abs(out.acc.item() - acc.item()) <= 2e-3
+    assert dl.max().item() <= 1e-2 * lmax, (dl.max().item(), lmax)
+    assert rms <= 1e-2, rms
+    worst, worst_k, checked = 0.0, None, 0
+    named = dict(m.named_parameters())
+    for k, ref in params.items():
+        if not ref.requires_grad or ref.grad is None:
+            continue
+        g = named[k].grad
+        if g is None:  # other domains' blocks: the oracle's autograd leaves them None as well or exactly zero
+            assert ref.grad.abs().max().item() == 0.0, k
+            continue
+        rn = ref.grad.norm().item()
+        if rn < 1e-7:
+            continue
+        dev = abs(g.float().norm().item() - rn) / rn
+        cos = torch.nn.functional.cosine_similarity(g.float().flatten(), ref.grad.flatten(), dim=0).item()
+        if dev > worst:
+            worst, worst_k = dev, k
+        assert dev <= 5e-2, (k, g.float().norm().item(), rn)
+        assert cos >= 0.98, (k, cos)
+        checked += 1
+    print(f"[fullsize B={B} T={Tn} dom={DOMAINS[dom_i]}] loss rel {rel:.2e}, logits max {dl.max().item() / lmax:.2e} of max, rms {rms:.2e}, "
+          f"{checked} gradient tensors, worst norm deviation {worst:.2e} ({worst_k})")
+    assert checked >= 32 * 20
+    m.zero_grad(set_to_none=True)
+
+
+def test_config2_training_step_matches_fp32_oracle_full_size(model):
+    """BASELINE.json configs[1]: 32 layers, B=8, T=16, 16x16 tokens + 64 action tokens, loss + logits + every gradient."""
+    _train_parity(model, 8, T, 1, seed=11)
+
+
+@pytest.fixture(scope="module")
+def model_t32():
+    from hma_b200 import GenieConfig, STMaskGIT
+    cfg = GenieConfig(num_layers=32, num_heads=8, d_model=256, T=32, S=S, num_factored_vocabs=2, qk_norm=False, qkv_bias=False,
+                      use_mup=False, action_network="concat+modulate")
+    torch.manual_seed(1)
+    with torch.device("cuda"):
+        m = STMaskGIT(cfg)
+        m.init_action_projectors(DOMAINS, D_ACTIONS, [[[0.0] * a, [1.0] * a] for a in ADIMS], "concat+modulate")
+    with torch.no_grad():
+        for p in m.parameters():
+            if p.dim() >= 2:
+                p.normal_(0.0, 0.03)
+    return m
+
+
+def test_config5_long_context_heterogeneous_actions_matches_fp32_oracle_full_size(model_t32):
+    """BASELINE.json configs[4]: 32 frames x 16x16 tokens, batches from action domains of different widths (7 / 70)."""
+    _train_parity(model_t32, 8, 32, 0, seed=12)
+    _train_parity(model_t32, 8, 32, 2, seed=13)
+
+
+def test_config3_decode_matches_fp32_oracle_full_size(model):
+    """BASELINE.json configs[2] at batch 64: logits of the frame being generated (frame-incremental decode: K/V cache of 8
+    prompt frames) against the oracle's full-window fp32 pass; the sampling kernels on the oracle's own logits and noise
+    are bit-exact; greedy tokens decoded from our logits agree with the oracle's except at near-ties."""
+    from hma_b200 import ops
+    from oracle import stmaskgit_oracle as O
+    B, Tp = 64, 8
+    x, a, dom = _batch(B, 21, masked_from=Tp)
+    sd = {k: v.detach() for k, v in model.state_dict().items()}
+    ocfg = _oracle_cfg(model.config)
+    with torch.no_grad():
+        ref = O.compute_logits(x, a, dom, sd, ocfg)[:, :, Tp]                       # [B, 1024, 16, 16]
+        ref_rows = ref.permute(0, 2, 3, 1).reshape(B, S, -1).contiguous()
+        model._sessions.clear()
+        sess = model._decode_session(x.clone(), Tp, a, dom, {})
+        got = sess.step(x[:, Tp], Tp).float().view(B, S, -1)
+        d = (got - ref_rows).abs().max().item()
+        assert d <= 1e-2 * ref_rows.abs().max().item(), (d, ref_rows.abs().max().item())
+        # sampling kernels on IDENTICAL logits and noise: bit-exact against the oracle's sampling arithmetic
+        g = torch.Generator(device="cuda").manual_seed(3)
+        noise = torch.stack([torch.empty(B * S, 512, device="cuda").exponential_(1, generator=g) for _ in range(2)])
+        for temperature in (0.0, 1.0, 0.7):
+            nz = noise if temperature > 1e-8 else None
+            new, conf = ops.sample_tokens(ref_rows, 2, 512, nz, temperature if nz is not None else 1.0)
+            probs = ref.reshape(B, 2, 512, 16, 16).permute(0, 2, 1, 3, 4).softmax(dim=1)   # b vs nv h w
+            want = torch.zeros(B, 16, 16, dtype=torch.long, device="cuda")
+            wconf = torch.ones(B, 16, 16, device="cuda")
+            for j, k in enumerate((1, 0)):
+                p = probs[:, :, k]
+                if nz is None:
+                    s = p.argmax(dim=1)
+                else:
+                    p2 = p.permute(0, 2, 3, 1).reshape(-1, 512) / temperature
+                    p2 = p2 / p2.sum(-1, keepdim=True)
+                    s = (p2 / noise[j]).argmax(dim=-1).reshape(B, 16, 16)
+                want = want * 512 + s
+                wconf = wconf * torch.gather(p, 1, s.unsqueeze(1)).squeeze(1)
+            mism = (new.view(B, 16, 16) != want).float().mean().item()
+            # torch's softmax sums its 512 terms in a different order than the warp reduction: a key can differ in the
+            # last ulp, so exact equality holds except where two keys tie to within that ulp
+            assert mism <= 1e-4, (temperature, mism)
+            assert torch.allclose(conf.view(B, 16, 16), wconf, rtol=1e-4, atol=1e-12)
+        # greedy tokens from OUR logits vs the oracle's: equal except near-ties under the bf16 logit noise
+        ours, _ = ops.sample_tokens(got.contiguous(), 2, 512, None)
+        theirs, _ = ops.sample_tokens(ref_rows, 2, 512, None)
+        agree = (ours == theirs).float().mean().item()
+        print(f"[fullsize decode B=64] logits max err {d / ref_rows.abs().max().item():.2e} of max, greedy token agreement {agree:.4f}")
+        # (a disagreement needs the oracle's top-2 gap below twice the logit error: with random weights the 512-way logits are
+        # nearly flat, so this is a reported figure with a loose floor, not a tolerance)
+        assert agree >= 0.5, agree
     model._sessions.clear()
