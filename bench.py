@@ -359,7 +359,7 @@ def gpu_reference_leg(dev, steps: int = 3, warmup: int = 1):
     from oracle import stmaskgit_oracle as O
     cfg = O.OracleConfig(num_layers=L, num_heads=HEADS, d_model=D_MODEL, T=T, S=S, num_factored_vocabs=2, qk_norm=False,
                          action_network="concat+modulate")
-    sd = O.make_state_dict(cfg, ["dom00"], [D_ACTION_CYCLE[0]], seed=0, action_dims=[ACTION_DIM_CYCLE[0]])
+    sd = O.make_state_dict(cfg, ["dom00"], [D_ACTION_CYCLE[0]], seed=0, std=0.02, action_dims=[ACTION_DIM_CYCLE[0]])
     params = {k: v.to(dev).requires_grad_(v.is_floating_point() and "action_preprocessor" not in k) for k, v in sd.items()}
     gen = torch.Generator().manual_seed(1234)
     ids, labels, actions = (t.to(dev) for t in synthetic_batch(gen, B_PER_GPU, D_ACTION_CYCLE[0]))
@@ -382,7 +382,7 @@ def gpu_reference_leg(dev, steps: int = 3, warmup: int = 1):
             torch.cuda.synchronize()
             ms = e0.elapsed_time(e1) / steps
             out[f"train_{impl}"] = {"value": B_PER_GPU * T * S / (ms / 1e3), "unit": "tokens/s", "ms_per_step": ms,
-                                    "loss": float(loss)}
+                                    "loss": float(loss.detach())}
         finally:
             O.ATTENTION_IMPL = "math"
         torch.cuda.empty_cache()
