@@ -349,6 +349,72 @@ def pipeline_leg(dev, cfg_T: int = T, batch: int = B_PER_GPU, batches: int = 40)
                                    "torch device RNG draws -> hma_collate_maskgit"}}
 
 
+def config5_leg(dev, world: int, rank: int, sync_all, layers: int, steps: int = 4, warmup: int = 3):
+    """BASELINE.json configs[4]: long context — 32 frames x 16x16 tokens (+64 action tokens per frame), batch 8 per GPU, batches
+    drawn from a 40-domain mix with heterogeneous action widths (each rank trains one domain per step, as the reference's
+    MultiTaskBatchSampler guarantees). Same TrainStep as the headline leg; device-timed, max over ranks."""
+    import torch.distributed as dist
+    from hma_b200 import GenieConfig, STMaskGIT
+    from hma_b200.train import TrainStep
+    T5 = 32
+    domains = [f"dom{i:02d}" for i in range(NUM_DOMAINS)]
+    d_actions = [D_ACTION_CYCLE[i % 10] for i in range(NUM_DOMAINS)]
+    stats = [[[0.0] * a, [1.0] * a] for a in (ACTION_DIM_CYCLE[i % 10] for i in range(NUM_DOMAINS))]
+    cfg = GenieConfig(num_layers=layers, num_heads=HEADS, d_model=D_MODEL, T=T5, S=S, num_factored_vocabs=2, qk_norm=False,
+                      qkv_bias=False, use_mup=False, action_network="concat+modulate")
+    torch.manual_seed(0)
+    with torch.device(dev):
+        model = STMaskGIT(cfg)
+        model.init_action_projectors(domains, d_actions, stats, "concat+modulate")
+    with torch.no_grad():
+        for k, p in model.named_parameters():
+            if p.dim() >= 2:
+                p.normal_(0.0, 0.02)
+    step_fn = TrainStep(model, lr=1e-4, weight_decay=0.05, max_grad_norm=1.0, cuda_graphs=True)
+    gen = torch.Generator().manual_seed(99 + rank)
+    total = warmup + steps
+    batches, sched = [], []
+    for i in range(total):
+        di = (rank + 3 * i) % NUM_DOMAINS
+        labels = torch.randint(0, 262144, (B_PER_GPU, T5 * S), generator=gen)
+        rate = torch.cos(math.pi / 2 * torch.rand(B_PER_GPU, T5, 1, generator=gen))
+        rate[:, 0] = 0.0
+        mask = torch.rand(B_PER_GPU, T5, S, generator=gen) < rate
+        ids = torch.where(mask.view(B_PER_GPU, -1), torch.full_like(labels, 262144), labels)
+        batches.append((ids.to(dev), labels.to(dev), torch.randn(B_PER_GPU, T5, d_actions[di], generator=gen).to(dev), domains[di]))
+        sched.append([domains[(r + 3 * i) % NUM_DOMAINS] for r in range(world)])
+    seen = set()
+    for b in batches:
+        if b[3] not in seen:
+            seen.add(b[3])
+            step_fn.precapture(b[0], b[1], b[2], [b[3]] * B_PER_GPU)
+    sync_all()
+    for i in range(warmup):
+        b = batches[i]
+        step_fn(b[0], b[1], b[2], [b[3]] * B_PER_GPU, rank_domains=sched[i])
+    sync_all()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(warmup, total):
+        b = batches[i]
+        out = step_fn(b[0], b[1], b[2], [b[3]] * B_PER_GPU, rank_domains=sched[i])
+    e1.record()
+    sync_all()
+    ms = torch.tensor([e0.elapsed_time(e1) / steps], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms.item())
+    loss = float(out[0].item())
+    n, d = N_TOK_FRAME, D_MODEL
+    fwd = T5 * n * layers * (34 * d * d + 4 * n * d + 4 * d * (T5 + 1) / 2) + 6 * d * d * T5 * layers + T5 * S * 2 * d * 1024
+    del step_fn, model
+    torch.cuda.empty_cache()
+    return {"workload": "HMA-MagVit 32 frames x 16x16 tokens + 64 action tokens/frame, batch 8/GPU, 40 action domains of widths "
+                        "2..70 (a different domain every step), training step", "metric": "train_video_tokens_per_s",
+            "value": world * B_PER_GPU * T5 * S / (ms / 1e3), "unit": "tokens/s", "ms_per_step": ms, "steps": steps, "warmup": warmup,
+            "domains_visited": len(seen), "loss": loss, "model_tflops_per_gpu": 3.0 * fwd * B_PER_GPU / (ms / 1e3) / 1e12}
+
+
 def gpu_reference_leg(dev, steps: int = 3, warmup: int = 1):
     """SURVEY.md §8(d) / BASELINE.md §5, "the bar to beat on the same box": the reference's algorithm in plain PyTorch on the
     SAME B200 under torch.autocast(bf16) — cuBLAS GEMMs, ATen element-wise kernels and (i) the reference's own math attention
@@ -467,6 +533,7 @@ def main() -> None:
     ap.add_argument("--no-mar", action="store_true", help="skip the HMA-MAR leg (BASELINE configs[3])")
     ap.add_argument("--no-gpu-reference", action="store_true", help="skip the plain-PyTorch-on-this-GPU reference leg")
     ap.add_argument("--no-extras", action="store_true", help="skip the interactive-latency and data-pipeline legs")
+    ap.add_argument("--no-config5", action="store_true", help="skip the long-context (T=32) training leg (BASELINE configs[4])")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)
@@ -624,6 +691,13 @@ def main() -> None:
         torch.cuda.empty_cache()
         mar = mar_leg(dev, world, rank, sync_all, args.layers)
 
+    # ---------------- long context, heterogeneous action stems (BASELINE configs[4])
+    cfg5 = None
+    if not args.no_config5:
+        step_fn = run_resident = model = None
+        torch.cuda.empty_cache()
+        cfg5 = config5_leg(dev, world, rank, sync_all, args.layers)
+
     # ---------------- the reference algorithm as plain PyTorch on this same GPU (rank 0, N = 1 only)
     gpu_ref = None
     if not args.no_gpu_reference and world == 1:
@@ -721,6 +795,8 @@ def main() -> None:
         if gen_fps is not None:
             gpu_ref["speedup_generate_vs_sdpa"] = gen_fps / gpu_ref["generate_sdpa"]["value"]
         line["gpu_reference"] = gpu_ref
+    if cfg5 is not None:
+        line["config5_long_context"] = cfg5
     if mar is not None:
         line["mar"] = mar
     if not args.no_cpu_baseline and world == 1:

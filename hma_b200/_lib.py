@@ -30,11 +30,11 @@ _SIGNATURES = {
     "hma_abi_version": [],
     "hma_device_check": [],
     "hma_gemm_nt": [c_void_p, c_ll, c_void_p, c_ll, c_int, c_int, c_int, c_int, c_void_p, c_ll, c_void_p, c_ll,
-                    c_fp, c_fp, c_ll, c_void_p, c_ll, c_float, c_fp, c_void_p],
+                    c_fp, c_fp, c_ll, c_void_p, c_ll, c_float, c_fp, c_fp, c_void_p],
     "hma_attn_spatial_fwd": [c_void_p, c_ll, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p, c_ll, c_fp,
                              c_void_p],
     "hma_attn_spatial_bwd": [c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_ll, c_fp, c_int, c_int, c_int, c_int, c_int,
-                             c_int, c_float, c_void_p, c_ll, c_void_p],
+                             c_int, c_float, c_void_p, c_ll, c_fp, c_void_p],
     "hma_attn_temporal_fwd": [c_void_p, c_ll, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p,
                               c_ll, c_fp, c_void_p],
     "hma_attn_temporal_bwd": [c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_ll, c_fp, c_int, c_int, c_int, c_int, c_int,

@@ -35,6 +35,7 @@ struct GemmNtParams {
   long long ldaux;
   float alpha;
   float* colsum;  // d-activation epilogues: colsum[N] += column sums of the output (the bias gradient of the Linear below)
+  float* rowdot;  // EPI_BF16: rowdot[row, N/32] = sum over each 32-column chunk of bf16(out) * aux (attention backward's delta)
 };
 
 constexpr int kBM = 128;
@@ -169,6 +170,26 @@ __device__ __forceinline__ void epilogue_chunk(const GemmNtParams& p, const uint
     }
   }
   if constexpr (EPI == HMA_EPI_BF16) {
+    if (p.rowdot != nullptr) {
+      // delta[row, head] = sum_c dO[row, c] O[row, c] over the 32 channels of a head (= this chunk), taken on the bf16
+      // values the attention backward will read. A lane owns the row here; O's 64 bytes of the row are two full sectors.
+      const int row = row0 + lane;
+      if (row < p.M) {
+        const uint4* o4 = reinterpret_cast<const uint4*>(p.aux + (size_t)row * p.ldaux + n0);
+        float acc = 0.f;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const uint4 o = __ldg(o4 + q);
+          const uint32_t ow[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint32_t g = pack_bf16(v[8 * q + 2 * j], v[8 * q + 2 * j + 1]);
+            acc += bf16_lo(g) * bf16_lo(ow[j]) + bf16_hi(g) * bf16_hi(ow[j]);
+          }
+        }
+        p.rowdot[(size_t)row * (p.N >> 5) + (n0 >> 5)] = acc;
+      }
+    }
     store_chunk_bf16(stage, lane, v, static_cast<__nv_bfloat16*>(p.out), p.ldo, row0, n0, p.M);
   } else if constexpr (EPI == HMA_EPI_GELU_BF16 || EPI == HMA_EPI_SILU_BF16) {
     if (p.out2 != nullptr) store_chunk_bf16(stage, lane, v, static_cast<__nv_bfloat16*>(p.out2), p.ldo2, row0, n0, p.M);
@@ -434,7 +455,7 @@ static int dispatch_nt(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
 extern "C" int hma_gemm_nt(const void* A, long long lda, const void* B, long long ldb, int M, int N, int K,
                            int epi, void* out, long long ldo, void* out2, long long ldo2, const float* bias,
                            const float* resid, long long ldr, const void* aux, long long ldaux, float alpha,
-                           float* colsum, void* stream_) {
+                           float* colsum, float* rowdot, void* stream_) {
   using namespace hma;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (M == 0) return 0;
@@ -459,6 +480,9 @@ extern "C" int hma_gemm_nt(const void* A, long long lda, const void* B, long lon
   p.aux = static_cast<const __nv_bfloat16*>(aux); p.ldaux = ldaux;
   p.alpha = alpha;
   p.colsum = colsum;
+  p.rowdot = rowdot;
+  HMA_REQUIRE(rowdot == nullptr || (epi == HMA_EPI_BF16 && aux != nullptr && ldaux % 8 == 0),
+              "gemm_nt: rowdot needs the plain bf16 epilogue and a bf16 aux matrix with 16-byte aligned rows");
   HMA_REQUIRE(colsum == nullptr || epi == HMA_EPI_DGELU_BF16 || epi == HMA_EPI_DSILU_BF16 ||
                   (epi == HMA_EPI_RESID_F32 && out2 != nullptr),
               "gemm_nt: colsum is produced by the d-activation epilogues and by the residual epilogue with a bf16 copy");

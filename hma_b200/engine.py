@@ -546,8 +546,11 @@ class Engine:
                 ops.group_colsum(dx, dact, n)
             # ---- spatial attention
             ops.gemm_wgrad(dy, L["att_s"], g2(lp + "spatial_attn.proj.weight"))
-            datt = ops.gemm_nt(dy, Wt[lp + "spatial_attn.proj.weight"], EPI_BF16)
-            dqkv = ops.attn_spatial_bwd(L["qkv_s"], L["att_s"], datt, L["lse"], M, n, d.heads, d.scale)
+            # delta = rowsum(dO * O) per (token, head) comes out of the epilogue of the GEMM that produces dO (a head's 32
+            # channels are one epilogue chunk), so the attention kernel's prologue reads 8 bytes per row instead of 128
+            delta = torch.empty(N, d.heads, device=dev, dtype=torch.float32)
+            datt = ops.gemm_nt(dy, Wt[lp + "spatial_attn.proj.weight"], EPI_BF16, aux=L["att_s"], rowdot=delta)
+            dqkv = ops.attn_spatial_bwd(L["qkv_s"], None, datt, L["lse"], M, n, d.heads, d.scale, delta=delta)
             if qk:
                 ops.qk_norm_bwd(L["qkv_s_raw"], p[lp + "spatial_attn.norm.weight"], dqkv, g2(lp + "spatial_attn.norm.weight"),
                                 g2(lp + "spatial_attn.norm.bias"))

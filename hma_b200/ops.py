@@ -65,7 +65,7 @@ def _p(t: Optional[torch.Tensor]):
 def gemm_nt(A: torch.Tensor, B: torch.Tensor, epi: int, *, out: Optional[torch.Tensor] = None,
             bias: Optional[torch.Tensor] = None, resid: Optional[torch.Tensor] = None,
             aux: Optional[torch.Tensor] = None, out2: Optional[torch.Tensor] = None, alpha: float = 1.0,
-            colsum: Optional[torch.Tensor] = None) -> torch.Tensor:
+            colsum: Optional[torch.Tensor] = None, rowdot: Optional[torch.Tensor] = None) -> torch.Tensor:
     """out[M,N] = epi(A[M,K] @ B[N,K]^T); A, B bf16 (row stride arbitrary, unit column stride)."""
     M, K = A.shape
     N = B.shape[0]
@@ -75,7 +75,7 @@ def gemm_nt(A: torch.Tensor, B: torch.Tensor, epi: int, *, out: Optional[torch.T
     _call(f"gemm_nt[N={N},K={K},epi={epi}]", 2.0 * M * N * K, "hma_gemm_nt", A.data_ptr(), A.stride(0), B.data_ptr(), B.stride(0), M, N, K, epi, out.data_ptr(),
               out.stride(0), _p(out2), out2.stride(0) if out2 is not None else 0, _p(bias), _p(resid),
               resid.stride(0) if resid is not None else 0, _p(aux), aux.stride(0) if aux is not None else 0,
-              float(alpha), _p(colsum), _s())
+              float(alpha), _p(colsum), _p(rowdot), _s())
     return out
 
 
@@ -222,12 +222,15 @@ def attn_spatial_fwd(qkv: torch.Tensor, frames: int, n: int, heads: int, scale: 
     return out, lse
 
 
-def attn_spatial_bwd(qkv, out, dout, lse, frames: int, n: int, heads: int, scale: float) -> torch.Tensor:
+def attn_spatial_bwd(qkv, out, dout, lse, frames: int, n: int, heads: int, scale: float, delta: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """delta: fp32 [frames*n, heads] = rowsum(dout * out) per (token, head) (gemm_nt's rowdot), or None to let the kernel
+    compute it from `out`."""
     C = heads * 32
     dqkv = torch.empty_like(qkv)
-    _call("attn_spatial_bwd", 10.0 * frames * heads * n * n * 32, "hma_attn_spatial_bwd", qkv.data_ptr(), qkv.stride(0), out.data_ptr(), out.stride(0), dout.data_ptr(),
-              dout.stride(0), lse.data_ptr(), frames, n, heads, 0, C, 2 * C, float(scale), dqkv.data_ptr(),
-              dqkv.stride(0), _s())
+    _call("attn_spatial_bwd", 10.0 * frames * heads * n * n * 32, "hma_attn_spatial_bwd", qkv.data_ptr(), qkv.stride(0),
+          _p(out) if delta is None else None, out.stride(0) if (out is not None and delta is None) else 0, dout.data_ptr(),
+          dout.stride(0), lse.data_ptr(), frames, n, heads, 0, C, 2 * C, float(scale), dqkv.data_ptr(), dqkv.stride(0),
+          _p(delta), _s())
     return dqkv
 
 

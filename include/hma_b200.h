@@ -46,14 +46,17 @@ int hma_device_check(void);
 /* DGELU / DSILU: if colsum != NULL, colsum[N] (fp32) += column sums of out — the bias gradient of the Linear whose
  * pre-activation gradient this is (accumulated in registers across the CTA's row tiles; a few atomics per CTA).
  * RESID_F32 with out2: colsum[N] += column sums of out2 (the bf16 copy is the next backward stage's operand and its column
- * sums that stage's bias gradient), which replaces a separate cast + column-sum pass over the residual stream. */
+ * sums that stage's bias gradient), which replaces a separate cast + column-sum pass over the residual stream.
+ * BF16 with rowdot != NULL (needs aux, bf16 [M, N]): rowdot[row * N/32 + c] (fp32) = sum over the 32 columns of chunk c of
+ * bf16(out[row, .]) * aux[row, .] — with out = dO and aux = O of an attention with head_dim 32 this is the softmax-backward
+ * row term delta = rowsum(dO * O) per (token, head), produced while dO is still in registers. */
 
 /* out[M,N] = epi(A[M,K] . B[N,K]^T). A, B bf16 row-major. Replaces nn.Linear forward
  * (attention.py:141,154; st_transformer.py:24-27; st_mask_git.py:70-75,681-683) and, with B a
  * pre-transposed weight, its input-gradient. K % 64 == 0, N % 128 == 0. */
 int hma_gemm_nt(const void* A, long long lda, const void* B, long long ldb, int M, int N, int K, int epi,
                 void* out, long long ldo, void* out2, long long ldo2, const float* bias, const float* resid,
-                long long ldr, const void* aux, long long ldaux, float alpha, float* colsum, void* stream);
+                long long ldr, const void* aux, long long ldaux, float alpha, float* colsum, float* rowdot, void* stream);
 
 /* dW[Mw,Nw] (fp32) += G[tokens,Mw]^T . X[tokens,Nw]; G, X bf16 row-major. The weight gradient of
  * the same Linears. Mw % 128 == 0, Nw % 128 == 0. Accumulates (caller zeroes dW). */
@@ -72,10 +75,12 @@ int hma_gemm_wgrad(const void* G, long long ldg, const void* X, long long ldx, i
 int hma_attn_spatial_fwd(const void* qkv, long long ld_qkv, int frames, int n, int heads, int q_col, int k_col,
                          int v_col, float scale, void* out, long long ldo, float* lse, void* stream);
 
-/* dqkv (bf16, same layout as qkv) from dout (bf16 [frames*n, ld_dout]), out and lse of the forward. */
+/* dqkv (bf16, same layout as qkv) from dout (bf16 [frames*n, ld_dout]), out and lse of the forward.
+ * delta: fp32 [frames*n, heads] = rowsum(dout * out) per (token, head) — hma_gemm_nt's rowdot of the GEMM that produced
+ * dout — or NULL to have the kernel compute it from out and dout (out may be NULL when delta is given). */
 int hma_attn_spatial_bwd(const void* qkv, long long ld_qkv, const void* out, long long ldo, const void* dout,
                          long long ld_dout, const float* lse, int frames, int n, int heads, int q_col, int k_col,
-                         int v_col, float scale, void* dqkv, long long ld_dqkv, void* stream);
+                         int v_col, float scale, void* dqkv, long long ld_dqkv, const float* delta, void* stream);
 
 /* Causal attention over the T frames of each of the n slots of each sample (attention.py:37-61 with
  * causal=True, st_transformer.py:111), reading the (B,T,n,.) layout in place. T <= 128.

@@ -19,13 +19,13 @@ P = 0x1000  # a non-null dummy address: validation must fail before it is ever d
 
 
 def test_gemm_rejects_bad_shapes():
-    rc, msg = _call("hma_gemm_nt", P, 256, P, 256, 128, 256, 100, 0, P, 256, None, 0, None, None, 0, None, 0, 1.0, None, None)
+    rc, msg = _call("hma_gemm_nt", P, 256, P, 256, 128, 256, 100, 0, P, 256, None, 0, None, None, 0, None, 0, 1.0, None, None, None)
     assert rc < 0 and "multiple of 64" in msg
-    rc, msg = _call("hma_gemm_nt", P, 256, P, 256, 128, 200, 256, 0, P, 200, None, 0, None, None, 0, None, 0, 1.0, None, None)
+    rc, msg = _call("hma_gemm_nt", P, 256, P, 256, 128, 200, 256, 0, P, 200, None, 0, None, None, 0, None, 0, 1.0, None, None, None)
     assert rc < 0 and "multiple of 128" in msg
-    rc, msg = _call("hma_gemm_nt", P, 256, P, 256, 128, 256, 256, 0, None, 256, None, 0, None, None, 0, None, 0, 1.0, None, None)
+    rc, msg = _call("hma_gemm_nt", P, 256, P, 256, 128, 256, 256, 0, None, 256, None, 0, None, None, 0, None, 0, 1.0, None, None, None)
     assert rc < 0 and "out is null" in msg
-    rc, msg = _call("hma_gemm_nt", P, 256, P, 256, 0, 256, 256, 0, P, 256, None, 0, None, None, 0, None, 0, 1.0, None, None)
+    rc, msg = _call("hma_gemm_nt", P, 256, P, 256, 0, 256, 256, 0, P, 256, None, 0, None, None, 0, None, 0, 1.0, None, None, None)
     assert rc == 0  # an empty problem is a no-op
     rc, msg = _call("hma_gemm_wgrad", P, 256, P, 256, 1000, 100, 256, P, 256, None)
     assert rc < 0 and "multiple of 128" in msg
@@ -69,5 +69,5 @@ def test_row_and_attention_entry_points_reject_bad_arguments():
 
 def test_python_binding_raises_with_the_library_message():
     with pytest.raises(_lib.HmaError, match="multiple of 64"):
-        _lib.call("hma_gemm_nt", P, 256, P, 256, 128, 256, 100, 0, P, 256, None, 0, None, None, 0, None, 0, 1.0, None, None)
+        _lib.call("hma_gemm_nt", P, 256, P, 256, 128, 256, 100, 0, P, 256, None, 0, None, None, 0, None, 0, 1.0, None, None, None)
     assert isinstance(_lib.lib(), ctypes.CDLL)

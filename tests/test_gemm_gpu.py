@@ -22,7 +22,7 @@ def _report(name, got, ref):
     return rel
 
 
-def gemm_nt(A, B, epi, bias=None, resid=None, aux=None, alpha=1.0, want_z=False, colsum=None):
+def gemm_nt(A, B, epi, bias=None, resid=None, aux=None, alpha=1.0, want_z=False, colsum=None, rowdot=None):
     M, K = A.shape
     N = B.shape[0]
     out_dtype = torch.float32 if epi == EPI_RESID else torch.bfloat16
@@ -31,9 +31,24 @@ def gemm_nt(A, B, epi, bias=None, resid=None, aux=None, alpha=1.0, want_z=False,
     _lib.call(
         "hma_gemm_nt", A.data_ptr(), A.stride(0), B.data_ptr(), B.stride(0), M, N, K, epi, out.data_ptr(),
         out.stride(0), _lib.ptr(out2), N, _lib.ptr(bias), _lib.ptr(resid), N, _lib.ptr(aux), N, alpha,
-        _lib.ptr(colsum), _lib.current_stream(),
+        _lib.ptr(colsum), _lib.ptr(rowdot), _lib.current_stream(),
     )
     return out, out2
+
+
+def test_gemm_nt_rowdot_is_the_attention_delta():
+    """EPI_BF16 with rowdot: per (row, 32-column chunk) sum of bf16(out) * aux — delta = rowsum(dO * O) per (token, head)."""
+    torch.manual_seed(3)
+    M, N, K = 1300, 256, 256
+    A = torch.randn(M, K, device="cuda").bfloat16()
+    B = (torch.randn(N, K, device="cuda") * 0.1).bfloat16()
+    O = torch.randn(M, N, device="cuda").bfloat16()
+    rowdot = torch.full((M, N // 32), float("nan"), device="cuda")
+    out, _ = gemm_nt(A, B, EPI_BF16, aux=O, rowdot=rowdot)
+    plain, _ = gemm_nt(A, B, EPI_BF16)
+    assert torch.equal(out, plain)
+    want = (out.float() * O.float()).view(M, N // 32, 32).sum(-1)
+    assert torch.allclose(rowdot, want, rtol=1e-4, atol=1e-4), (rowdot - want).abs().max().item()
 
 
 @pytest.mark.parametrize("M,N,K", [(128, 128, 64), (256, 256, 256), (1000, 768, 256), (4096, 1024, 256),

@@ -279,8 +279,16 @@ def test_attn_spatial_bwd(frames, n):
     _lib.call("hma_attn_spatial_fwd", qkv.data_ptr(), 3 * C, frames, n, H, 0, C, 2 * C, scale, out.data_ptr(), C,
               lse.data_ptr(), S_())
     _lib.call("hma_attn_spatial_bwd", qkv.data_ptr(), 3 * C, out.data_ptr(), C, dout.data_ptr(), C, lse.data_ptr(),
-              frames, n, H, 0, C, 2 * C, scale, dqkv.data_ptr(), 3 * C, S_())
+              frames, n, H, 0, C, 2 * C, scale, dqkv.data_ptr(), 3 * C, None, S_())
     torch.cuda.synchronize()
+    # the same call with delta = rowsum(dO * O) per (token, head) handed in (what the engine does: the GEMM that produces
+    # dO emits it) instead of computed in the kernel's prologue: bit-identical
+    delta = (dout.float() * out.float()).view(rows, H, hd).sum(-1).contiguous()
+    dqkv2 = torch.zeros_like(dqkv)
+    _lib.call("hma_attn_spatial_bwd", qkv.data_ptr(), 3 * C, None, 0, dout.data_ptr(), C, lse.data_ptr(),
+              frames, n, H, 0, C, 2 * C, scale, dqkv2.data_ptr(), 3 * C, delta.data_ptr(), S_())
+    torch.cuda.synchronize()
+    assert relerr(dqkv2, dqkv.float()) < 1e-3
     x = qkv.float().reshape(frames, n, 3, H, hd).requires_grad_(True)
     q, k, v = x.permute(2, 0, 3, 1, 4)
     o = (((q @ k.transpose(-1, -2)) * scale).softmax(-1) @ v).permute(0, 2, 1, 3).reshape(rows, C)

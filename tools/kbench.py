@@ -33,11 +33,16 @@ def rnd(*shape, dtype=BF, s=1.0):
 def stages():
     """name -> (callable, algorithmic work, 'flop' | 'byte')"""
     st = {}
+    rnd_a, rnd_w = rnd(N, C), rnd(C, C, s=0.05)
     qkv = rnd(N, 3 * C)
     out_s, lse = ops.attn_spatial_fwd(qkv, M, n, H, SCALE, want_lse=True)
     dout = rnd(N, C)
     st["attn_spatial_fwd"] = (lambda: ops.attn_spatial_fwd(qkv, M, n, H, SCALE, want_lse=True), 4.0 * M * H * n * n * 32, "flop")
-    st["attn_spatial_bwd"] = (lambda: ops.attn_spatial_bwd(qkv, out_s, dout, lse, M, n, H, SCALE), 10.0 * M * H * n * n * 32, "flop")
+    delta = (dout.float() * out_s.float()).view(N, H, 32).sum(-1).contiguous()
+    st["attn_spatial_bwd"] = (lambda: ops.attn_spatial_bwd(qkv, None, dout, lse, M, n, H, SCALE, delta=delta), 10.0 * M * H * n * n * 32, "flop")
+    st["attn_spatial_bwd_nodelta"] = (lambda: ops.attn_spatial_bwd(qkv, out_s, dout, lse, M, n, H, SCALE), 10.0 * M * H * n * n * 32, "flop")
+    st["gemm_datt_rowdot"] = (lambda: ops.gemm_nt(rnd_a, rnd_w, EPI_BF16, aux=out_s, rowdot=delta), N * C * (2.0 + 2 + 2), "byte")
+    st["gemm_datt_plain"] = (lambda: ops.gemm_nt(rnd_a, rnd_w, EPI_BF16), N * C * (2.0 + 2), "byte")
     out_t, _ = ops.attn_temporal_fwd(qkv, B, T, n, H, SCALE)
     st["attn_temporal_fwd"] = (lambda: ops.attn_temporal_fwd(qkv, B, T, n, H, SCALE), N * C * 2.0 * 4, "byte")
     st["attn_temporal_bwd"] = (lambda: ops.attn_temporal_bwd(qkv, out_t, dout, None, B, T, n, H, SCALE), N * C * 2.0 * 7, "byte")

@@ -16,8 +16,9 @@ KERNELS = {
     "gemm_nt": dict(single=(0, 10), names={0: "start", 10: "end", 1: "mma:top", 2: "mma:tmem_free", 3: "mma:committed", 4: "epi:top",
                                            5: "epi:acc_ready", 6: "epi:done"}),
     "gemm_wgrad": dict(single=(0, 3, 4, 5), names={0: "start", 3: "mma_done", 4: "red_issued", 5: "end", 1: "tma_issued", 2: "full"}),
-    "attn_spatial_bwd": dict(names={0: "start", 11: "loaded", 1: "SdP_issued", 5: "c:top", 6: "c:sdp_ready", 7: "c:tmem_freed",
-                                    8: "c:pds_arrived", 2: "dVdK:go", 3: "dVdK:issued", 4: "dQ:issued", 9: "final", 10: "end"}),
+    "attn_spatial_bwd": dict(names={0: "start", 11: "loaded", 1: "SdP_issued", 5: "A:top", 6: "A:S_ready", 7: "A:S_freed",
+                                    8: "A:P_arrived", 12: "B:top", 13: "B:dP_ready", 14: "B:P_seen", 15: "B:dS_arrived",
+                                    2: "dV:go", 3: "dV:issued", 4: "dK:issued", 9: "final", 10: "end"}),
 }
 
 def run_attn_spatial_bwd():
@@ -25,8 +26,9 @@ def run_attn_spatial_bwd():
     qkvs = [torch.randn(frames * n, 768, device="cuda").bfloat16() for _ in range(4)]  # rotate: operands come from HBM
     outs = [ops.attn_spatial_fwd(q, frames, n, H, 0.17, True) for q in qkvs]
     douts = [torch.randn_like(o[0]) for o in outs]
+    deltas = [(d.float() * o[0].float()).view(frames * n, H, 32).sum(-1).contiguous() for d, o in zip(douts, outs)]
     for i in range(4):
-        ops.attn_spatial_bwd(qkvs[i], outs[i][0], douts[i], outs[i][1], frames, n, H, 0.17)
+        ops.attn_spatial_bwd(qkvs[i], None, douts[i], outs[i][1], frames, n, H, 0.17, delta=deltas[i])
 
 def run_gemm_wgrad():
     N = 40960
@@ -67,6 +69,7 @@ def main():
     t0 = a[0, 0]
     single = [e for e in names if e in KERNELS[name].get('single', (0, 9, 10, 11))]
     print(" ".join(f"{names[e]}={a[e, 0] - t0}" for e in single))
+    print("event-0 sub-stamps:", " ".join(f"[{i}]={a[0, i] - t0}" for i in range(1, 8) if a[0, i]))
     per_it = [e for e in sorted(names) if e not in single]
     for i in range(40):
         if all(a[e, i] == 0 for e in per_it):
