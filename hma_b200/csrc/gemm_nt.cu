@@ -155,9 +155,22 @@ __device__ __forceinline__ void prefetch_chunk(const GemmNtParams& p, int row0, 
   }
 }
 
+// rowdot operand: the 32 bf16 of aux[row0 + lane, n0 .. n0+32) (row-owner domain), fetched one chunk ahead like pf
+__device__ __forceinline__ void prefetch_rowdot(const GemmNtParams& p, int row0, int n0, int lane, uint4 (&po)[4]) {
+  const int row = row0 + lane;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) po[q] = make_uint4(0u, 0u, 0u, 0u);
+  if (row < p.M) {
+    const uint4* o4 = reinterpret_cast<const uint4*>(p.aux + (size_t)row * p.ldaux + n0);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) po[q] = __ldg(o4 + q);
+  }
+}
+
 template <int EPI>
 __device__ __forceinline__ void epilogue_chunk(const GemmNtParams& p, const uint32_t (&r)[32], int row0, int n0,
-                                               int lane, uint32_t stage, const float4 (&pf)[8], float4& csum) {
+                                               int lane, uint32_t stage, const float4 (&pf)[8], float4& csum,
+                                               const uint4 (&po)[4]) {
   // r: 32 consecutive fp32 accumulator columns [n0, n0+32) of output row (row0 + lane).
   float v[32];
 #pragma unroll
@@ -175,12 +188,10 @@ __device__ __forceinline__ void epilogue_chunk(const GemmNtParams& p, const uint
       // values the attention backward will read. A lane owns the row here; O's 64 bytes of the row are two full sectors.
       const int row = row0 + lane;
       if (row < p.M) {
-        const uint4* o4 = reinterpret_cast<const uint4*>(p.aux + (size_t)row * p.ldaux + n0);
         float acc = 0.f;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          const uint4 o = __ldg(o4 + q);
-          const uint32_t ow[4] = {o.x, o.y, o.z, o.w};
+          const uint32_t ow[4] = {po[q].x, po[q].y, po[q].z, po[q].w};
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const uint32_t g = pack_bf16(v[8 * q + 2 * j], v[8 * q + 2 * j + 1]);
@@ -363,7 +374,11 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const uint32_t aph = (uint32_t)(it >> 1) & 1u;
       const int row0 = m_blk * kBM + ew * 32;
       float4 pf[2][8];
+      uint4 po[2][4];
       if constexpr (kPrefetch) prefetch_chunk<EPI>(p, row0, n_blk * BN + eh * 32, lane, pf[0]);
+      if constexpr (EPI == HMA_EPI_BF16) {
+        if (p.rowdot != nullptr) prefetch_rowdot(p, row0, n_blk * BN + eh * 32, lane, po[0]);
+      }
       mbar_wait(smem_u32(&bar_tfull[as]), aph);
       tc_fence_after();
 #pragma unroll
@@ -372,10 +387,13 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if constexpr (kPrefetch) {
           if (j + 1 < kChunks) prefetch_chunk<EPI>(p, row0, n_blk * BN + (c + kColGroups) * 32, lane, pf[(j + 1) & 1]);
         }
+        if constexpr (EPI == HMA_EPI_BF16) {
+          if (p.rowdot != nullptr && j + 1 < kChunks) prefetch_rowdot(p, row0, n_blk * BN + (c + kColGroups) * 32, lane, po[(j + 1) & 1]);
+        }
         uint32_t r[32];
         tmem_ld_x32(tmem_addr(tmem_base, (uint32_t)(ew * 32), (uint32_t)(as * BN + c * 32)), r);
         tmem_ld_wait();
-        epilogue_chunk<EPI>(p, r, row0, n_blk * BN + c * 32, lane, stage_buf, pf[j & 1], csum[j]);
+        epilogue_chunk<EPI>(p, r, row0, n_blk * BN + c * 32, lane, stage_buf, pf[j & 1], csum[j], po[j & 1]);
       }
       tc_fence_before();
       mbar_arrive(smem_u32(&bar_tempty[as]));

@@ -450,9 +450,12 @@ class Engine:
         return g
 
     def backward(self, p: Dict[str, Tensor], sv: dict, dlogits: Tensor, flat: Optional[Tensor] = None, *,
-                 g: Optional[Dict[str, Tensor]] = None, front_bwd=None) -> Dict[str, Tensor]:
+                 g: Optional[Dict[str, Tensor]] = None, front_bwd=None, layer_hook=None) -> Dict[str, Tensor]:
         """dlogits: bf16 [B*T*S, nv*vs] (gradient of the out_x_proj output). Returns the gradient dict of alloc_grads
-        (`g`, if given, is used as is). `front_bwd(dx, dact)` replaces the token-embedding backward (mar.py)."""
+        (`g`, if given, is used as is). `front_bwd(dx, dact)` replaces the token-embedding backward (mar.py).
+        `layer_hook = (layers, fn)`: fn(i) is called on the main stream right after the backward of layer i has been
+        enqueued, for i in `layers` — every SHARED gradient of layers >= i is then final (train.py overlaps their all-reduce
+        with the rest of the backward, and splits CUDA-graph capture there; the side stream is joined around the call)."""
         d: Dims = sv["dims"]
         dom = sv["dom"]
         Wt = self.weights.trans
@@ -565,6 +568,17 @@ class Engine:
                 dy = ops.ln_bwd(da1, L["x0"], L["st1"], 1, dx, gamma=p[lp + "norm1.weight"], dgamma=g2(lp + "norm1.weight"),
                                 dbeta=g2(lp + "norm1.bias"), want_next=i > 0, colsum_next=g.get(nxt) if nxt else None)
             sv["layers"][i] = None  # release this layer's activations
+            if layer_hook is not None and i in layer_hook[0]:
+                if d.modulate:  # a capture segment must end with every forked stream joined
+                    join = torch.cuda.Event()
+                    join.record(side)
+                    main.wait_event(join)
+                layer_hook[1](i)
+                main = torch.cuda.current_stream()
+                if d.modulate:
+                    fork = torch.cuda.Event()
+                    fork.record(main)
+                    side.wait_event(fork)
         if d.modulate:
             join = torch.cuda.Event()
             join.record(side)

@@ -65,8 +65,42 @@ class ParamArena:
         self.max_dom_size = max([s for _, s in self.dom_range.values()], default=0)
 
 
+def shared_segment_ranges(names: Sequence[str], sizes: Sequence[int], num_layers: int, segments: int):
+    """Ranges of the shared gradient range that become final after each backward segment. The backward runs layers
+    L-1 .. 0; segment s covers layers [L - (s+1)*L/segments, L - s*L/segments); the readout and any loss-head parameters
+    (computed first) belong to segment 0, the front end (embeddings, positions: computed last) to the last segment.
+    names / sizes: the shared parameters in buffer order with their padded lengths. Returns
+    (first layer of each segment, [[(offset, length), ...] per segment]) with adjacent ranges merged."""
+    segments = max(1, min(segments, num_layers))
+    lows = [num_layers - (s + 1) * num_layers // segments for s in range(segments)]
+    lows[-1] = 0
+    front = ("pos_embed", "token_embed.", "action_mask_tokens", "z_proj", "mask_token", "diffusion_pos_embed")
+
+    def seg_of(name: str) -> int:
+        if name.startswith("decoder.layers."):
+            i = int(name.split(".")[2])
+            for s_, lo in enumerate(lows):
+                if i >= lo:
+                    return s_
+        if name.startswith(front):
+            return segments - 1
+        return 0
+
+    out = [[] for _ in range(segments)]
+    off = 0
+    for k, n in zip(names, sizes):
+        r = out[seg_of(k)]
+        if r and r[-1][0] + r[-1][1] == off:
+            r[-1] = (r[-1][0], r[-1][1] + n)
+        else:
+            r.append((off, n))
+        off += n
+    return lows, out
+
+
 def exchange_gradients(grad: torch.Tensor, shared_size: int, max_dom_size: int, dom_range: Dict[str, tuple],
-                       rank_domains: Sequence[Optional[str]], gathered: Optional[torch.Tensor], group=None):
+                       rank_domains: Sequence[Optional[str]], gathered: Optional[torch.Tensor], group=None,
+                       shared_done: bool = False):
     """Gradient exchange of one step (device- and backend-agnostic: NCCL on GPUs, gloo in the CPU tests).
 
     grad = [shared | this rank's domain block] (sums, not means). After the call grad[:shared_size] holds the
@@ -75,7 +109,8 @@ def exchange_gradients(grad: torch.Tensor, shared_size: int, max_dom_size: int, 
     reference's dense all-reduce over all parameters (train_multi.py:579,779-781), whose other entries are zero.
     """
     world = dist.get_world_size(group)
-    dist.all_reduce(grad[:shared_size], group=group)
+    if not shared_done:  # (the overlapped path all-reduced the shared range segment by segment during the backward)
+        dist.all_reduce(grad[:shared_size], group=group)
     updates = []
     if max_dom_size:
         send = grad[shared_size:shared_size + max_dom_size]
@@ -99,13 +134,19 @@ def exchange_gradients(grad: torch.Tensor, shared_size: int, max_dom_size: int, 
 class TrainStep:
     def __init__(self, model, lr: float = 1e-4, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.05,
                  max_grad_norm: Optional[float] = 1.0, process_group=None, cuda_graphs: bool = False,
-                 mu_transfer: bool = False):
+                 mu_transfer: bool = False, overlap_segments: int = 4):
         """The optimizer is the reference's (train_multi.py:899-922): AdamW over two parameter groups — names containing
         "bias" or "layer_norm.weight" get weight_decay 0, everything else `weight_decay`. `mu_transfer=True` selects the
         reference's `mup.MuAdamW`: it divides the learning rate of matrix-like parameters by their width multiplier
         relative to the base shapes, which the reference hard-codes to d_model=256, num_heads=8
         (st_mask_git.py:755-760) — the only width these kernels are built for, so every multiplier is 1 and MuAdamW's
         update is AdamW's; wider models are rejected by engine.check_config before they get here.
+
+        world_size > 1: the all-reduce of the shared gradient range is issued in `overlap_segments` pieces DURING the backward
+        — after the backward of layers 24..31 their gradients go on the wire while layers 23..0 are still being computed, and
+        so on (what DDP's buckets do in the reference, train_multi.py:779-781,990) — on NCCL's own stream; with CUDA graphs
+        the forward+backward is captured as one graph per segment and the collectives are launched between the replays.
+        overlap_segments=1 restores the single all-reduce after the backward.
 
         cuda_graphs=True: forward + loss + backward of each (domain, shape) is captured into a CUDA graph on its
         second use (or by precapture()) and replayed from static input buffers afterwards; the gradient exchange,
@@ -131,6 +172,9 @@ class TrainStep:
         self.rank = dist.get_rank(process_group) if self.world > 1 else 0
         self.gathered = (torch.zeros(self.world, self.arena.max_dom_size, device=dev, dtype=torch.float32)
                          if self.world > 1 else None)
+        self.overlap_segments = overlap_segments if self.world > 1 else 1
+        self._seg = None       # (first layer of each segment, ranges per segment), built on first use
+        self._works: list = []  # in-flight all-reduces of this step
         self._p = None
         # nn.Dropout(mlp_drop) (st_transformer.py:24-27): keep masks are keyed by (seed, element); the device-side part of
         # the seed is redrawn every step, so a CUDA-graph replay gets new masks
@@ -180,7 +224,21 @@ class TrainStep:
         self.betas, self.max_norm = tuple(hy.get("betas", self.betas)), hy.get("max_grad_norm", self.max_norm)
 
     # ------------------------------------------------------------------------------------------
-    def _fwd_bwd_eager(self, p, ids, labels, action_ids, dom, d) -> torch.Tensor:
+    def _segments(self, p, d):
+        if self._seg is None:
+            eng = self.engine
+            named = {k: v for k, v in self.model.named_parameters()}
+            names = eng.shared_param_names(named, d)
+            self._seg = shared_segment_ranges(names, [eng.padded_numel(named[k]) for k in names], d.num_layers, self.overlap_segments)
+        return self._seg
+
+    def _reduce_segment(self, s: int) -> None:
+        """All-reduce the shared gradient ranges that segment `s` of the backward has completed (async: NCCL's stream waits
+        for the work enqueued so far on the current stream, the backward goes on)."""
+        for off, n in self._seg[1][s]:
+            self._works.append(dist.all_reduce(self.grad[off:off + n], group=self.pg, async_op=True))
+
+    def _fwd_bwd_eager(self, p, ids, labels, action_ids, dom, d, seg_hook=None) -> torch.Tensor:
         eng = self.engine
         B, T, S = d.B, d.T, d.S
         mlp_drop = float(getattr(self.model.config, "mlp_drop", 0.0))
@@ -189,38 +247,71 @@ class TrainStep:
         loss_acc, lse, sums = ops.ce_fwd(logits, labels, ids, B, T, S, d.nv, d.vs, d.mask_id, SMOOTHING)
         dlogits = ops.ce_bwd(logits, labels, ids, B, T, S, d.nv, d.vs, d.mask_id, SMOOTHING, lse, sums, self.ones)
         self.grad.zero_()
-        eng.backward(p, sv, dlogits, flat=self.grad)
+        hook = None
+        if seg_hook is not None:  # segment s ends after the backward of its first layer
+            lows = self._segments(p, d)[0]
+            hook = (set(lows[:-1]), lambda i: seg_hook(lows.index(i)))
+        eng.backward(p, sv, dlogits, flat=self.grad, layer_hook=hook)
+        if seg_hook is not None:
+            seg_hook(self.overlap_segments - 1)
         return loss_acc
 
     def _fwd_bwd(self, p, ids, labels, action_ids, dom, d) -> torch.Tensor:
-        """Forward, fused loss and backward into self.grad; returns the device tensor [loss, acc]."""
+        """Forward, fused loss and backward into self.grad; returns the device tensor [loss, acc]. With world_size > 1 and
+        overlap_segments > 1 the shared-range all-reduces are in flight (self._works) when this returns."""
+        overlap = self.overlap_segments > 1
+        if overlap:
+            self._segments(p, d)
+            self._works = []
         if not self.cuda_graphs:
-            return self._fwd_bwd_eager(p, ids, labels, action_ids, dom, d)
+            return self._fwd_bwd_eager(p, ids, labels, action_ids, dom, d, self._reduce_segment if overlap else None)
         key = (dom, d.B, d.T, d.S, None if action_ids is None else tuple(action_ids.shape[1:]))
         rec = self._graphs.get(key)
         if rec is None:
             if key not in self._warm:  # first use: eager (fills the bf16 weight-cast tables, one-time kernel attributes)
                 self._warm.add(key)
-                return self._fwd_bwd_eager(p, ids, labels, action_ids, dom, d)
+                return self._fwd_bwd_eager(p, ids, labels, action_ids, dom, d, self._reduce_segment if overlap else None)
             rec = {"ids": ids.clone(), "labels": labels.clone(),
                    "actions": None if action_ids is None else action_ids.to(torch.float32).clone()}
             torch.cuda.synchronize()
-            g = torch.cuda.CUDAGraph()
             if self._pool is None:
                 self._pool = torch.cuda.graph_pool_handle()
             n0 = ops.LAUNCHES
-            with torch.cuda.graph(g, pool=self._pool):
-                rec["out"] = self._fwd_bwd_eager(p, rec["ids"], rec["labels"], rec["actions"], dom, d)
+            # one graph per backward segment (a single graph without overlap): the collectives are launched between replays
+            graphs = []
+            stream = torch.cuda.Stream()
+            stream.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(stream):
+                cur = torch.cuda.CUDAGraph()
+                cur.capture_begin(pool=self._pool)
+
+                def cut(s_):
+                    nonlocal cur
+                    cur.capture_end()
+                    graphs.append(cur)
+                    if s_ < self.overlap_segments - 1:
+                        cur = torch.cuda.CUDAGraph()
+                        cur.capture_begin(pool=self._pool)
+
+                if overlap:
+                    rec["out"] = self._fwd_bwd_eager(p, rec["ids"], rec["labels"], rec["actions"], dom, d, cut)
+                else:
+                    rec["out"] = self._fwd_bwd_eager(p, rec["ids"], rec["labels"], rec["actions"], dom, d)
+                    cut(0)
+            torch.cuda.current_stream().wait_stream(stream)
             rec["launches"] = ops.LAUNCHES - n0
             ops.LAUNCHES = n0  # counted per replay below
-            rec["graph"] = g
+            rec["graphs"] = graphs
             self._graphs[key] = rec
         else:
             rec["ids"].copy_(ids)
             rec["labels"].copy_(labels)
             if action_ids is not None:
                 rec["actions"].copy_(action_ids)
-        rec["graph"].replay()
+        for s_, g in enumerate(rec["graphs"]):
+            g.replay()
+            if overlap:
+                self._reduce_segment(s_)
         ops.LAUNCHES += rec["launches"]
         return rec["out"]
 
@@ -271,8 +362,12 @@ class TrainStep:
                 gathered: List[Optional[str]] = [None] * self.world
                 dist.all_gather_object(gathered, dom, group=self.pg)
                 rank_domains = gathered
+            for w in self._works:  # the segment-wise all-reduces of the shared range issued during the backward
+                w.wait()
+            shared_done = bool(self._works)
+            self._works = []
             updates = exchange_gradients(self.grad, shared, self.arena.max_dom_size, self.arena.dom_range, rank_domains,
-                                         self.gathered, self.pg)
+                                         self.gathered, self.pg, shared_done=shared_done)
         elif dom_n:
             updates.append((dom_lo, dom_n, g_dom))
         if self.max_norm is not None:

@@ -93,17 +93,33 @@ def main():
         for k, gk in dense.items():
             if k not in touched:
                 assert gk.abs().max().item() == 0.0, k
-        # (c) a full optimisation step keeps the replicas bit-identical
-        model2 = build_cuda_model(rec, sd, device=dev)
-        step2 = TrainStep(model2, lr=1e-3, weight_decay=0.05, max_grad_norm=1.0)
-        step2(ids, labels, acts, [dom, dom], rank_domains=rank_doms)
-        flat = step2.arena.flat.detach().clone()
-        other = [torch.empty_like(flat) for _ in range(world)]
-        dist.all_gather(other, flat)
-        assert torch.equal(other[0], other[1]), f"{case}: replicas diverged after one step"
+        # (c) full optimisation steps keep the replicas bit-identical, and the OVERLAPPED exchange (shared range all-reduced
+        # segment by segment during the backward; eager launches and one CUDA graph per segment) gives the parameters of the
+        # single all-reduce after the backward (a two-rank sum does not depend on how the range is cut)
+        finals = {}
+        for tag, kw2 in (("single all-reduce", dict(overlap_segments=1)), ("overlapped eager", dict(overlap_segments=2)),
+                         ("overlapped graphs", dict(overlap_segments=2, cuda_graphs=True))):
+            model2 = build_cuda_model(rec, sd, device=dev)
+            step2 = TrainStep(model2, lr=1e-3, weight_decay=0.05, max_grad_norm=1.0, **kw2)
+            for _ in range(3):  # graphs: eager warm-up, capture + replay, replay
+                step2(ids, labels, acts, [dom, dom], rank_domains=rank_doms)
+            flat = step2.arena.flat.detach().clone()
+            other = [torch.empty_like(flat) for _ in range(world)]
+            dist.all_gather(other, flat)
+            assert torch.equal(other[0], other[1]), f"{case} / {tag}: replicas diverged"
+            finals[tag] = flat
+            if tag == "overlapped graphs":
+                assert len(next(iter(step2._graphs.values()))["graphs"]) == 2
+        ref_flat = finals["single all-reduce"]
+        moved = (ref_flat - TrainStep(build_cuda_model(rec, sd, device=dev)).arena.flat).abs().mean().item()
+        for tag in ("overlapped eager", "overlapped graphs"):
+            diff = (finals[tag] - ref_flat).abs().mean().item()
+            # weight-gradient atomics make two runs of the same step differ in the last bits; three Adam steps later the
+            # parameters agree to a small fraction of the distance moved
+            assert diff <= 0.05 * moved, (case, tag, diff, moved)
         if rank == 0:
             print(f"[ddp parity] {case}: {checked} gradient tensors equal the dense all-reduce (worst rel err {worst:.2e}); "
-                  f"replicas bit-identical after clip + AdamW", flush=True)
+                  f"replicas bit-identical after clip + AdamW; overlapped exchange (eager, graphs) == single all-reduce", flush=True)
     dist.barrier()
     if rank == 0:
         print("DDP PARITY OK", flush=True)

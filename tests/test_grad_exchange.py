@@ -64,3 +64,31 @@ def test_exchange_equals_dense_allreduce(rank_domains):
         p.join(timeout=60)
     assert all(ok for _, ok, _ in results), results
     assert results[0][2] == results[1][2]  # every rank applies the same set of domain updates
+
+
+def test_shared_segment_ranges_cover_the_shared_range_once_in_backward_order():
+    """The overlapped exchange all-reduces the shared gradient range in pieces, each as soon as the backward has finished
+    the layers it belongs to: the pieces must tile the range exactly once; readout first, embeddings last."""
+    from hma_b200.train import shared_segment_ranges
+
+    L = 8
+    names = ["pos_embed_TSC", "token_embed.mask_token_embed", "token_embed.factored_embeds.0.weight"]
+    names += [f"decoder.layers.{i}.mlp.fc1.weight" for i in range(L)] + ["out_x_proj.weight"]
+    names += [f"decoder.layers.{i}.mlp.fc1.bias" for i in range(L)] + ["out_x_proj.bias"]  # [decayed | not decayed] layout
+    sizes = [12, 4, 8] + [16] * L + [20] + [4] * L + [4]
+    for segs in (1, 2, 4, 8, 16):
+        lows, ranges = shared_segment_ranges(names, sizes, L, segs)
+        assert lows[-1] == 0 and lows == sorted(lows, reverse=True) and len(ranges) == len(lows)
+        covered = sorted((o, n) for r in ranges for o, n in r)
+        pos = 0
+        for o, n in covered:
+            assert o == pos
+            pos += n
+        assert pos == sum(sizes)
+        offs = {k: sum(sizes[:i]) for i, k in enumerate(names)}
+        seg_of = lambda k: next(s for s, r in enumerate(ranges) if any(o <= offs[k] < o + n for o, n in r))  # noqa: E731
+        assert seg_of("out_x_proj.weight") == 0 and seg_of("out_x_proj.bias") == 0
+        assert seg_of("pos_embed_TSC") == len(ranges) - 1
+        assert seg_of(f"decoder.layers.{L - 1}.mlp.fc1.weight") == 0 and seg_of("decoder.layers.0.mlp.fc1.bias") == len(ranges) - 1
+        for i in range(L - 1):  # a later layer never lands in a later segment than an earlier one
+            assert seg_of(f"decoder.layers.{i + 1}.mlp.fc1.weight") <= seg_of(f"decoder.layers.{i}.mlp.fc1.weight")
