@@ -568,7 +568,8 @@ def main() -> None:
             if p.dim() >= 2:
                 p.normal_(0.0, 0.02)
     n_params = sum(p.numel() for p in model.parameters())
-    step_fn = TrainStep(model, lr=1e-4, weight_decay=0.05, max_grad_norm=1.0, cuda_graphs=not args.no_graphs)
+    step_fn = TrainStep(model, lr=1e-4, weight_decay=0.05, max_grad_norm=1.0, cuda_graphs=not args.no_graphs,
+                        overlap_segments=int(os.environ.get("HMA_B200_OVERLAP_SEGMENTS", "4")))  # env: A/B measurements only
 
     total = args.warmup + args.steps
     gen = torch.Generator().manual_seed(1234 + rank)
@@ -684,6 +685,7 @@ def main() -> None:
 
     # ---------------- HMA-MAR (continuous tokens + diffusion head): training step and sampling, BASELINE configs[3]
     graphs_on = step_fn.cuda_graphs
+    exchange_segments = step_fn.overlap_segments
     mar = None
     if not args.no_mar:
         del step_fn, run_resident
@@ -751,9 +753,12 @@ def main() -> None:
                    "global_batch": world * B_PER_GPU, "tokens_per_step": tokens_per_step, "parallelism": f"dp{world}",
                    "l2": "per-step working set (~19 GB of activations) >> 126 MB L2; no explicit flush needed",
                    "loss": loss_val, "model_tflops_per_gpu": step_tf,
-                   "cuda_graph": ("forward+loss+backward replayed from one CUDA graph per action domain (captured before the "
-                                  "timed region); gradient exchange, clip and AdamW launched from the host")
-                   if graphs_on else "off"},
+                   "cuda_graph": ("forward+loss+backward replayed from CUDA graphs per action domain (captured before the timed "
+                                  "region; N > 1: one graph per backward segment with the shared-gradient all-reduce of that "
+                                  "segment launched between replays, overlapping the rest of the backward); domain-block "
+                                  "all-gather, clip and AdamW launched from the host")
+                   if graphs_on else "off",
+                   "grad_exchange_segments": exchange_segments},
         "e2e": {"value": e2e, "unit": "tokens/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8,
                 "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": launches,

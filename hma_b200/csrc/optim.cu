@@ -1,7 +1,7 @@
 // Optimizer step over the flat parameter arena (reference:
 // train_multi.py:593-598 clip_grad_norm_ + AdamW). Parameters, gradients and both moments are
 // contiguous fp32 ranges with identical layout, so the step is two streaming kernels:
-//   sumsq      : partial sum of squares of a gradient range -> device scalar (atomicAdd)
+//   sumsq      : sum of squares of a gradient range added to a device scalar, in a fixed order (replicas stay bit-identical)
 //   adamw_step : p, m, v updated in place; the global-norm clip coefficient is computed on the
 //                device from that scalar, so no host synchronisation is needed
 // Only the ranges that received gradients this step (shared trunk + the active domain) are touched.
@@ -10,7 +10,14 @@
 
 namespace hma {
 
-__global__ void __launch_bounds__(256) sumsq_kernel(const float* g, long long n4, float* out) {
+// Deterministic: every block writes its partial sum to a fixed slot and a second, single-block launch adds the slots in
+// index order. (An atomicAdd of the partials summed in arrival order, so the clip coefficient — and with it every
+// parameter — differed in the last bit between data-parallel replicas holding bit-identical gradients, and the
+// replicas drifted apart; torch's clip_grad_norm_ in the reference trainer is deterministic.)
+constexpr int kSumsqMaxBlocks = 148 * 8;
+__device__ float g_sumsq_partial[kSumsqMaxBlocks];
+
+__global__ void __launch_bounds__(256) sumsq_kernel(const float* g, long long n4) {
   float acc = 0.f;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
     const float4 v = reinterpret_cast<const float4*>(g)[i];
@@ -24,8 +31,21 @@ __global__ void __launch_bounds__(256) sumsq_kernel(const float* g, long long n4
     float s = 0.f;
 #pragma unroll
     for (int w = 0; w < 8; ++w) s += part[w];
-    atomicAdd(out, s);
+    g_sumsq_partial[blockIdx.x] = s;
   }
+}
+
+__global__ void __launch_bounds__(256) sumsq_finalize_kernel(int blocks, float* out) {
+  __shared__ float part[256];
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < blocks; i += 256) acc += g_sumsq_partial[i];  // fixed assignment, fixed order
+  part[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) part[threadIdx.x] += part[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *out += part[0];  // ranges are accumulated by successive calls on one stream
 }
 
 struct AdamParams {
@@ -80,8 +100,9 @@ extern "C" int hma_sumsq(const float* g, long long n, float* out, void* stream_)
   HMA_REQUIRE(n % 4 == 0 && (reinterpret_cast<uintptr_t>(g) & 15) == 0, "sumsq: range must be 16-byte aligned");
   const long long n4 = n / 4;
   long long blocks = (n4 + 255) / 256;
-  if (blocks > 148 * 8) blocks = 148 * 8;
-  sumsq_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream_)>>>(g, n4, out);
+  if (blocks > kSumsqMaxBlocks) blocks = kSumsqMaxBlocks;
+  sumsq_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream_)>>>(g, n4);
+  sumsq_finalize_kernel<<<1, 256, 0, static_cast<cudaStream_t>(stream_)>>>((int)blocks, out);
   HMA_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

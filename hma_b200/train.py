@@ -230,6 +230,7 @@ class TrainStep:
             named = {k: v for k, v in self.model.named_parameters()}
             names = eng.shared_param_names(named, d)
             self._seg = shared_segment_ranges(names, [eng.padded_numel(named[k]) for k in names], d.num_layers, self.overlap_segments)
+            self.overlap_segments = len(self._seg[0])  # at most one segment per layer
         return self._seg
 
     def _reduce_segment(self, s: int) -> None:

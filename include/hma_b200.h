@@ -204,7 +204,8 @@ int hma_rank_remask(const float* keys, unsigned char* unmasked, const long long*
 /* ---------------------------------------------------------------------------------------------
  * Optimizer over contiguous fp32 ranges (train_multi.py:593-598: clip_grad_norm_ + AdamW)
  * ------------------------------------------------------------------------------------------- */
-/* *out += sum(g^2) */
+/* *out += sum(g^2), summed in a fixed order (bit-reproducible: data-parallel replicas must compute the same clip
+ * coefficient from the same gradients). Calls that accumulate into one scalar must be issued on one stream. */
 int hma_sumsq(const float* g, long long n, float* out, void* stream);
 /* AdamW with decoupled weight decay; gradient = g * grad_scale * clip where
  * clip = min(1, max_norm / (sqrt(*sumsq) * grad_scale + 1e-6)) if sumsq != NULL. step counts from 1.

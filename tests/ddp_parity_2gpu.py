@@ -54,7 +54,7 @@ def main():
             dense[k] = gk
         # (b) TrainStep: forward + loss + backward into the flat buffer, then the two-collective exchange
         model = build_cuda_model(rec, sd, device=dev)
-        step = TrainStep(model, lr=1e-3, weight_decay=0.05, max_grad_norm=1.0)
+        step = TrainStep(model, lr=1e-3, weight_decay=0.05, max_grad_norm=1.0, overlap_segments=1)  # exchange called by hand below
         p = step._params()
         d = step.engine.dims(2, cfg.T, cfg.S, True)
         step._fwd_bwd(p, ids.reshape(2, cfg.T, -1).contiguous(), labels.reshape(2, -1).contiguous(), acts, dom, d)
