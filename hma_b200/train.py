@@ -13,6 +13,7 @@ layout, which makes the optimizer two streaming kernels and the gradient exchang
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, List, Optional, Sequence
 
 import torch
@@ -172,7 +173,7 @@ class TrainStep:
         self.rank = dist.get_rank(process_group) if self.world > 1 else 0
         self.gathered = (torch.zeros(self.world, self.arena.max_dom_size, device=dev, dtype=torch.float32)
                          if self.world > 1 else None)
-        self.overlap_segments = overlap_segments if self.world > 1 else 1
+        self.overlap_segments = overlap_segments if (self.world > 1 or os.environ.get("HMA_B200_FORCE_SEGMENTS") == "1") else 1
         self._seg = None       # (first layer of each segment, ranges per segment), built on first use
         self._works: list = []  # in-flight all-reduces of this step
         self._p = None
@@ -183,6 +184,7 @@ class TrainStep:
         self._graphs: Dict[tuple, dict] = {}
         self._warm = set()
         self._pool = None
+        self._capture_stream = None
 
     def _params(self) -> Dict[str, torch.Tensor]:
         if self._p is None:
@@ -236,6 +238,8 @@ class TrainStep:
     def _reduce_segment(self, s: int) -> None:
         """All-reduce the shared gradient ranges that segment `s` of the backward has completed (async: NCCL's stream waits
         for the work enqueued so far on the current stream, the backward goes on)."""
+        if self.world == 1:  # HMA_B200_FORCE_SEGMENTS=1: segmented capture without a process group (single-GPU tests)
+            return
         for off, n in self._seg[1][s]:
             self._works.append(dist.all_reduce(self.grad[off:off + n], group=self.pg, async_op=True))
 
@@ -280,7 +284,9 @@ class TrainStep:
             n0 = ops.LAUNCHES
             # one graph per backward segment (a single graph without overlap): the collectives are launched between replays
             graphs = []
-            stream = torch.cuda.Stream()
+            if self._capture_stream is None:  # ONE capture stream for every graph: the caching allocator reuses a freed
+                self._capture_stream = torch.cuda.Stream()  # block only on the stream it was allocated on
+            stream = self._capture_stream
             stream.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(stream):
                 cur = torch.cuda.CUDAGraph()
