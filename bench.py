@@ -726,20 +726,23 @@ def main() -> None:
             traffic = json.load(f).get("traffic_bytes")  # dram read+write of one launch, from the committed ncu capture
     except Exception:
         pass
-    rec = prof.get(dominant, {"launches": 0, "total_ms": 0.0, "work": 0.0})
+    rec = prof.get(dominant, {"launches": 0, "total_ms": 0.0, "robust_ms": 0.0, "work": 0.0})
     achieved = rec["work"] / (rec["total_ms"] / 1e3) / 1e12 if rec["total_ms"] else 0.0
     # every stage of the step, for context: share of the summed kernel time and achieved rate on its own bound
-    # (work = algorithmic FLOPs for the contractions, algorithmic bytes for the streaming stages; hma_b200/ops.py)
+    # (work = algorithmic FLOPs for the contractions, algorithmic bytes for the streaming stages; hma_b200/ops.py). Shares and
+    # rates use median launch time x launches (robust_ms): in this host-launched pass a kernel's event pair occasionally
+    # includes a host stall
     hbm_gbs = peaks.get("hbm_gbs", 6650.0)
-    tot_ms = sum(v["total_ms"] for v in prof.values() if v["launches"] and v["work"] / v["launches"] >= 1e8) or 1.0
-    stages = []
     main_stream = {k: v for k, v in prof.items() if v["launches"] and v["work"] / v["launches"] >= 1e8}  # drop the
     # one-tile adaLN chain: it runs on a side stream, where event pairs also time its waits on the main stream
-    for kind, v in sorted(main_stream.items(), key=lambda kv: -kv[1]["total_ms"])[:12]:
+    tot_ms = sum(v["robust_ms"] for v in main_stream.values()) or 1.0
+    stages = []
+    for kind, v in sorted(main_stream.items(), key=lambda kv: -kv[1]["robust_ms"])[:14]:
         is_flops = kind.startswith(("gemm", "attn_spatial"))
-        rate = v["work"] / (v["total_ms"] / 1e3) if v["total_ms"] else 0.0
-        stages.append({"stage": kind, "share": round(v["total_ms"] / tot_ms, 4), "launches": v["launches"],
-                       "avg_us": round(v["total_ms"] / max(v["launches"], 1) * 1e3, 1),
+        rate = v["work"] / (v["robust_ms"] / 1e3) if v["robust_ms"] else 0.0
+        stages.append({"stage": kind, "share": round(v["robust_ms"] / tot_ms, 4), "launches": v["launches"],
+                       "median_us": round(v["robust_ms"] / max(v["launches"], 1) * 1e3, 1),
+                       "mean_us": round(v["total_ms"] / max(v["launches"], 1) * 1e3, 1),
                        "achieved": round(rate / 1e12, 1) if is_flops else round(rate / 1e9, 0),
                        "unit": "TFLOP/s" if is_flops else "GB/s",
                        "frac_of_peak": round(rate / 1e12 / peak_tf, 3) if is_flops else round(rate / 1e9 / hbm_gbs, 3)})

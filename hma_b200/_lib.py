@@ -76,6 +76,8 @@ _SIGNATURES = {
     "hma_adamw_step": [c_fp, c_fp, c_fp, c_fp, c_ll, c_ll, c_float, c_float, c_float, c_float, c_float, c_int, c_float, c_fp,
                        c_float, c_void_p],
     "hma_gemm_wgrad": [c_void_p, c_ll, c_void_p, c_ll, c_int, c_int, c_int, c_fp, c_ll, c_void_p],
+    "hma_gemm_wgrad_grouped": [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                               c_void_p],
     "hma_mar_embed_fwd": [c_fp, c_void_p, c_fp, c_fp, c_fp, c_fp, c_fp, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                           c_int, c_fp, c_fp, c_fp, c_void_p],
     "hma_mar_embed_bwd": [c_fp, c_fp, c_void_p, c_fp, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_fp, c_fp, c_fp,

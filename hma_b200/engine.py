@@ -488,6 +488,14 @@ class Engine:
         for i in reversed(range(d.num_layers)):
             L = sv["layers"][i]
             lp = f"decoder.layers.{i}."
+            # The seven weight gradients of the block are collected and contracted by ONE persistent launch at the end of
+            # the block (ops.gemm_wgrad_grouped): nothing in the backward chain waits for them, their operands (the dy / dz /
+            # dqkv of each stage and the saved activations) are not touched again, and one launch of ~3 long work items per
+            # CTA replaces seven single-wave launches that are mostly prologue and atomics.
+            wg = []
+
+            def wgrad(G, X, dW, wg=wg):
+                wg.append((G, X, dW))
             # ---- MLP
             if drop is not None:  # x4 = x3 + drop(fc2(drop(gelu(z)))): the keep masks are regenerated from the seeds
                 dy = ops.dropout_cast_bf16(dx, drop[0], drop[1] + 2 * i + 1, drop[2])
@@ -495,14 +503,14 @@ class Engine:
                     ops.colsum_bf16(dy, g[lp + "mlp.fc2.bias"])
             elif dy is None:
                 dy = ops.cast_colsum(dx, g.get(lp + "mlp.fc2.bias"))
-            ops.gemm_wgrad(dy, L["h"], g2(lp + "mlp.fc2.weight"))
+            wgrad(dy, L["h"], g2(lp + "mlp.fc2.weight"))
             dz = ops.gemm_nt(dy, Wt[lp + "mlp.fc2.weight"], EPI_DGELU, aux=L["z"],
                              colsum=g.get(lp + "mlp.fc1.bias") if drop is None else None)
             if drop is not None:  # the GELU-output dropout mask applies to dz: fc1's bias gradient is taken after it
                 ops.dropout_bf16_(dz, drop[0], drop[1] + 2 * i, drop[2])
                 if lp + "mlp.fc1.bias" in g:
                     ops.colsum_bf16(dz, g[lp + "mlp.fc1.bias"])
-            ops.gemm_wgrad(dz, L["a2"], g2(lp + "mlp.fc1.weight"))
+            wgrad(dz, L["a2"], g2(lp + "mlp.fc1.weight"))
             da2 = ops.gemm_nt(dz, Wt[lp + "mlp.fc1.weight"], EPI_BF16)
             if qk:
                 dy = ops.ln_bwd(da2, None, None, 0, dx, want_next=True, colsum_next=g.get(lp + "temporal_attn.proj.bias"))
@@ -510,13 +518,13 @@ class Engine:
                 dy = ops.ln_bwd(da2, L["x3"], L["st2"], 1, dx, gamma=p[lp + "norm2.weight"], dgamma=g2(lp + "norm2.weight"),
                                 dbeta=g2(lp + "norm2.bias"), want_next=True, colsum_next=g.get(lp + "temporal_attn.proj.bias"))
             # ---- temporal attention
-            ops.gemm_wgrad(dy, L["att_t"], g2(lp + "temporal_attn.proj.weight"))
+            wgrad(dy, L["att_t"], g2(lp + "temporal_attn.proj.weight"))
             datt = ops.gemm_nt(dy, Wt[lp + "temporal_attn.proj.weight"], EPI_BF16)
             dqkv = ops.attn_temporal_bwd(L["qkv_t"], L["att_t"], datt, L["lse_t"], B, T, n, d.heads, d.scale)
             if qk:
                 ops.qk_norm_bwd(L["qkv_t_raw"], p[lp + "temporal_attn.norm.weight"], dqkv, g2(lp + "temporal_attn.norm.weight"),
                                 g2(lp + "temporal_attn.norm.bias"))
-            ops.gemm_wgrad(dqkv, L["at"], g2(lp + "temporal_attn.qkv.weight"))
+            wgrad(dqkv, L["at"], g2(lp + "temporal_attn.qkv.weight"))
             if lp + "temporal_attn.qkv.bias" in g:
                 ops.colsum_bf16(dqkv, g2(lp + "temporal_attn.qkv.bias"))
             # dx += dqkv . W; its bf16 copy and column sums (operand and bias gradient of the stage below) come out of
@@ -527,7 +535,7 @@ class Engine:
             # ---- modulate
             if d.modulate:
                 ap = lp + f"action_projectors.{dom}."
-                ops.gemm_wgrad(dy, L["am"], g2(ap + "linear_out.weight"))
+                wgrad(dy, L["am"], g2(ap + "linear_out.weight"))
                 dam = ops.gemm_nt(dy, Wt[ap + "linear_out.weight"], EPI_BF16)
                 dmod = torch.zeros(M, 2 * C, device=dev, dtype=torch.float32)
                 dy = ops.ln_bwd(dam, L["x1"], L["stm"], 2, dx, mod=L["mod"], rows_per_group=n, dmod=dmod, want_next=True,
@@ -548,7 +556,7 @@ class Engine:
             elif d.additive:
                 ops.group_colsum(dx, dact, n)
             # ---- spatial attention
-            ops.gemm_wgrad(dy, L["att_s"], g2(lp + "spatial_attn.proj.weight"))
+            wgrad(dy, L["att_s"], g2(lp + "spatial_attn.proj.weight"))
             # delta = rowsum(dO * O) per (token, head) comes out of the epilogue of the GEMM that produces dO (a head's 32
             # channels are one epilogue chunk), so the attention kernel's prologue reads 8 bytes per row instead of 128
             delta = torch.empty(N, d.heads, device=dev, dtype=torch.float32)
@@ -557,7 +565,7 @@ class Engine:
             if qk:
                 ops.qk_norm_bwd(L["qkv_s_raw"], p[lp + "spatial_attn.norm.weight"], dqkv, g2(lp + "spatial_attn.norm.weight"),
                                 g2(lp + "spatial_attn.norm.bias"))
-            ops.gemm_wgrad(dqkv, L["a1"], g2(lp + "spatial_attn.qkv.weight"))
+            wgrad(dqkv, L["a1"], g2(lp + "spatial_attn.qkv.weight"))
             if lp + "spatial_attn.qkv.bias" in g:
                 ops.colsum_bf16(dqkv, g2(lp + "spatial_attn.qkv.bias"))
             da1 = ops.gemm_nt(dqkv, Wt[lp + "spatial_attn.qkv.weight"], EPI_BF16)
@@ -567,6 +575,7 @@ class Engine:
             else:
                 dy = ops.ln_bwd(da1, L["x0"], L["st1"], 1, dx, gamma=p[lp + "norm1.weight"], dgamma=g2(lp + "norm1.weight"),
                                 dbeta=g2(lp + "norm1.bias"), want_next=i > 0, colsum_next=g.get(nxt) if nxt else None)
+            ops.gemm_wgrad_grouped(wg)
             sv["layers"][i] = None  # release this layer's activations
             if layer_hook is not None and i in layer_hook[0]:
                 if d.modulate:  # a capture segment must end with every forked stream joined

@@ -34,7 +34,11 @@ class Profiler:
         out = {}
         for kind, recs in self.records.items():
             ms = [a.elapsed_time(b) for a, b, _ in recs]
-            out[kind] = {"launches": len(ms), "total_ms": sum(ms), "work": sum(w for _, _, w in recs)}
+            srt = sorted(ms)
+            # robust total: median x launches (an event pair also times whatever else delays its kernel when the host, not
+            # the GPU, is the bottleneck of an eagerly launched step; a few such outliers must not define a stage's share)
+            out[kind] = {"launches": len(ms), "total_ms": sum(ms), "robust_ms": srt[len(srt) // 2] * len(ms),
+                         "max_ms": srt[-1], "work": sum(w for _, _, w in recs)}
         return out
 
 
@@ -86,6 +90,35 @@ def gemm_wgrad(G: torch.Tensor, X: torch.Tensor, dW: torch.Tensor) -> None:
     assert X.shape[0] == tokens and dW.shape == (Mw, Nw) and dW.dtype == F32 and dW.stride(1) == 1
     _call(f"gemm_wgrad[{Mw}x{Nw}]", 2.0 * tokens * Mw * Nw, "hma_gemm_wgrad", G.data_ptr(), G.stride(0), X.data_ptr(), X.stride(0), tokens, Mw, Nw, dW.data_ptr(),
               dW.stride(0), _s())
+
+
+def gemm_wgrad_grouped(group) -> None:
+    """group: list of (G [tokens, Mw] bf16, X [tokens, Nw] bf16, dW [Mw, Nw] fp32), all over the same tokens:
+    dW += G^T @ X for every entry in ONE persistent launch (the weight gradients of an ST block). Entries whose shape the
+    grouped kernel does not take (Nw % 256 != 0) go through gemm_wgrad."""
+    import ctypes
+    take = []
+    for G, X, dW in group:
+        tokens, Mw = G.shape
+        Nw = X.shape[1]
+        assert X.shape[0] == tokens and dW.shape == (Mw, Nw) and dW.dtype == F32 and dW.stride(1) == 1
+        if Mw % 128 == 0 and Nw % 256 == 0 and (not take or take[0][0].shape[0] == tokens):
+            take.append((G, X, dW))
+        else:
+            gemm_wgrad(G, X, dW)
+    for lo in range(0, len(take), 8):
+        part = take[lo:lo + 8]
+        n = len(part)
+        vp, ll, ci = ctypes.c_void_p * n, ctypes.c_longlong * n, ctypes.c_int * n
+        args = (vp(*[g.data_ptr() for g, _, _ in part]), ll(*[g.stride(0) for g, _, _ in part]),
+                vp(*[x.data_ptr() for _, x, _ in part]), ll(*[x.stride(0) for _, x, _ in part]),
+                ci(*[g.shape[1] for g, _, _ in part]), ci(*[x.shape[1] for _, x, _ in part]),
+                vp(*[w.data_ptr() for _, _, w in part]), ll(*[w.stride(0) for _, _, w in part]))
+        tokens = part[0][0].shape[0]
+        flops = sum(2.0 * tokens * g.shape[1] * x.shape[1] for g, x, _ in part)
+        cast = lambda a: ctypes.cast(a, ctypes.c_void_p)  # noqa: E731
+        _call("gemm_wgrad_grouped", flops, "hma_gemm_wgrad_grouped", n, cast(args[0]), cast(args[1]), cast(args[2]), cast(args[3]),
+              tokens, cast(args[4]), cast(args[5]), cast(args[6]), cast(args[7]), _s())
 
 
 def ln_fwd(x: torch.Tensor, mode: int, *, gamma=None, beta=None, mod=None, rows_per_group: int = 0, eps: float = 1e-5,

@@ -63,6 +63,12 @@ int hma_gemm_nt(const void* A, long long lda, const void* B, long long ldb, int 
 int hma_gemm_wgrad(const void* G, long long ldg, const void* X, long long ldx, int tokens, int Mw, int Nw,
                    float* dW, long long ldw, void* stream);
 
+/* The same contraction for up to 8 Linears that share the token dimension, in ONE persistent launch (the seven weight
+ * gradients of an ST block): dW[j][Mw[j], Nw[j]] (fp32) += G[j][tokens, Mw[j]]^T . X[j][tokens, Nw[j]]. All array arguments
+ * are HOST arrays of `count` entries. Mw[j] % 128 == 0, Nw[j] % 256 == 0. Accumulates (caller zeroes dW). */
+int hma_gemm_wgrad_grouped(int count, const void* const* G, const long long* ldg, const void* const* X, const long long* ldx,
+                           int tokens, const int* Mw, const int* Nw, float* const* dW, const long long* ldw, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Attention
  * ------------------------------------------------------------------------------------------- */

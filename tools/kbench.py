@@ -59,6 +59,14 @@ def stages():
     dw2 = torch.zeros(C, C, device=DEV)
     st["wgrad_1024x256"] = (lambda: ops.gemm_wgrad(a1024, a256, dw), 2.0 * N * 4 * C * C, "flop")
     st["wgrad_256x256"] = (lambda: ops.gemm_wgrad(a256, dout, dw2), 2.0 * N * C * C, "flop")
+    shapes = [(C, 4 * C), (4 * C, C), (C, C), (3 * C, C), (C, C), (C, C), (3 * C, C)]
+    grp = [(rnd(N, mw), rnd(N, nw), torch.zeros(mw, nw, device=DEV)) for mw, nw in shapes]
+    st["wgrad_layer_grouped"] = (lambda: ops.gemm_wgrad_grouped(grp), sum(2.0 * N * mw * nw for mw, nw in shapes), "flop")
+
+    def seven():
+        for G_, X_, W_ in grp:
+            ops.gemm_wgrad(G_, X_, W_)
+    st["wgrad_layer_seven_launches"] = (seven, sum(2.0 * N * mw * nw for mw, nw in shapes), "flop")
     gam, bet = torch.ones(C, device=DEV), torch.zeros(C, device=DEV)
     st["ln_fwd"] = (lambda: ops.ln_fwd(x32, 1, gamma=gam, beta=bet, want_stats=True), N * C * 6.0, "byte")
     _, stats = ops.ln_fwd(x32, 1, gamma=gam, beta=bet, want_stats=True)
