@@ -609,7 +609,7 @@ def main() -> None:
     sampler = ClockSampler(local)
     sampler.start()
     launches0 = ops.LAUNCHES
-    dominant = "attn_spatial_bwd"  # largest share of the step (profiles/r01b_launches_summary.txt); DESIGN.md §3.2
+    dominant = "attn_spatial_bwd"  # largest share of the step (profiles/r02a_launches_summary.txt); DESIGN.md §3.2
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.profiler.start()  # no-op unless run as `ncu --profile-from-start off ...` (profiles/ recipes)
     e0.record()
@@ -722,7 +722,7 @@ def main() -> None:
     peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)"
     traffic = None
     try:
-        with open(os.path.join(ROOT, "profiles", "r01b_roofline_kernel.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r02_roofline_kernel.json")) as f:
             traffic = json.load(f).get("traffic_bytes")  # dram read+write of one launch, from the committed ncu capture
     except Exception:
         pass
@@ -767,7 +767,8 @@ def main() -> None:
         "gpu_launches": launches,
         "clocks": clocks,
         "roofline": {"bound": "tensor", "kernel": "attn_spatial_bwd_kernel (per-frame attention backward, 128 frames x 8 heads x 320 tokens, "
-                                                    "head_dim 32: 33.55 algorithmic GFLOP and 168 MB per launch, AI ~ the ridge)",
+                                                    "head_dim 32: 33.55 algorithmic GFLOP and 150 MB per launch (qkv + dO + lse + delta in, dqkv "
+                                                    "out), AI ~ the ridge)",
                      "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf if peak_tf else None,
                      "traffic": traffic, "traffic_unit": "bytes/launch (ncu dram read+write)", "launches_timed": rec["launches"], "timed_in": roofline_pass, "avg_launch_us": (rec["total_ms"] / max(rec["launches"], 1)) * 1e3,
                      "peak_source": peak_src, "stages": stages},

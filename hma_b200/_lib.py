@@ -100,6 +100,12 @@ _SIGNATURES = {
     "hma_mar_scatter_rows": [c_fp, c_void_p, c_ll, c_int, c_fp, c_void_p],
     "hma_gather_token_windows": [c_void_p, c_int, c_ll, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p],
     "hma_gather_rows_f32": [c_fp, c_ll, c_ll, c_void_p, c_int, c_ll, c_fp, c_void_p],
+    "hma_conv3x3_nhwc": [c_void_p, c_ll, c_void_p, c_ll, c_int, c_int, c_int, c_int, c_void_p, c_ll, c_fp, c_fp, c_ll, c_void_p],
+    "hma_lfq_entry": [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p],
+    "hma_gn_stats": [c_fp, c_int, c_int, c_int, c_int, c_fp, c_fp, c_void_p],
+    "hma_gn_swish": [c_fp, c_fp, c_fp, c_fp, c_int, c_int, c_int, c_int, c_float, c_int, c_void_p, c_void_p],
+    "hma_depth_to_space": [c_fp, c_int, c_int, c_int, c_int, c_fp, c_void_p],
+    "hma_to_uint8": [c_fp, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p],
     "hma_dropout_bf16": [c_void_p, c_ll, c_float, c_u64, c_void_p, c_void_p],
     "hma_dropout_add_f32": [c_fp, c_fp, c_fp, c_ll, c_float, c_u64, c_void_p, c_void_p],
     "hma_dropout_cast_bf16": [c_fp, c_void_p, c_ll, c_float, c_u64, c_void_p, c_void_p],

@@ -36,6 +36,11 @@ struct GemmNtParams {
   float alpha;
   float* colsum;  // d-activation epilogues: colsum[N] += column sums of the output (the bias gradient of the Linear below)
   float* rowdot;  // EPI_BF16: rowdot[row, N/32] = sum over each 32-column chunk of bf16(out) * aux (attention backward's delta)
+  // 3x3 convolution as ONE contraction (hma_conv3x3_nhwc): A is a zero-bordered NHWC image [rows, Cin] and K = 9 * Cin; the
+  // k-blocks of tap (ky, kx) are the SAME columns of A read (ky - 1) * conv_wp + (kx - 1) rows further down — a TMA
+  // coordinate, not an im2col copy. conv_kb_per_tap = Cin / 64; 0 = ordinary GEMM.
+  int conv_kb_per_tap;
+  int conv_wp;
 };
 
 constexpr int kBM = 128;
@@ -323,7 +328,13 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1u);
           const uint32_t full = smem_u32(&bar_full[stage]);
           mbar_expect_tx(full, (uint32_t)(kAStage + (STAT ? 0 : kBStage)));
-          tma_load_2d(smemA + stage * kAStage, &tmA, full, kb * kBK, m_blk * kBM);
+          int a_col = kb * kBK, a_row = m_blk * kBM;
+          if (p.conv_kb_per_tap > 0) {
+            const int tap = kb / p.conv_kb_per_tap;
+            a_col = (kb - tap * p.conv_kb_per_tap) * kBK;
+            a_row += (tap / 3 - 1) * p.conv_wp + (tap % 3 - 1);  // rows before the image / past its end read as zero
+          }
+          tma_load_2d(smemA + stage * kAStage, &tmA, full, a_col, a_row);
           if constexpr (!STAT) tma_load_2d(smemB + stage * kBStage, &tmB, full, kb * kBK, n_blk * BN);
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
@@ -478,10 +489,10 @@ static int dispatch_nt(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
 
 }  // namespace hma
 
-extern "C" int hma_gemm_nt(const void* A, long long lda, const void* B, long long ldb, int M, int N, int K,
-                           int epi, void* out, long long ldo, void* out2, long long ldo2, const float* bias,
-                           const float* resid, long long ldr, const void* aux, long long ldaux, float alpha,
-                           float* colsum, float* rowdot, void* stream_) {
+static int gemm_nt_impl(const void* A, long long lda, const void* B, long long ldb, int M, int N, int K,
+                        int epi, void* out, long long ldo, void* out2, long long ldo2, const float* bias,
+                        const float* resid, long long ldr, const void* aux, long long ldaux, float alpha,
+                        float* colsum, float* rowdot, int conv_cin, int conv_wp, void* stream_) {
   using namespace hma;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (M == 0) return 0;
@@ -495,7 +506,7 @@ extern "C" int hma_gemm_nt(const void* A, long long lda, const void* B, long lon
   // CTA's k-loop is latency-bound, so halve the tile width to double the CTAs in flight.
   if (bn == 256 && (long long)((M + kBM - 1) / kBM) * (N / 256) * 2 <= hma_host::sm_count()) bn = 128;
   CUtensorMap tmA, tmB;
-  int rc = hma_host::make_tmap_bf16_2d(&tmA, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda * 2, kBK, kBM);
+  int rc = hma_host::make_tmap_bf16_2d(&tmA, A, (uint64_t)(conv_cin > 0 ? conv_cin : K), (uint64_t)M, (uint64_t)lda * 2, kBK, kBM);
   if (rc) return rc;
   rc = hma_host::make_tmap_bf16_2d(&tmB, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb * 2, kBK, bn);
   if (rc) return rc;
@@ -507,6 +518,8 @@ extern "C" int hma_gemm_nt(const void* A, long long lda, const void* B, long lon
   p.alpha = alpha;
   p.colsum = colsum;
   p.rowdot = rowdot;
+  p.conv_kb_per_tap = conv_cin > 0 ? conv_cin / kBK : 0;
+  p.conv_wp = conv_wp;
   HMA_REQUIRE(rowdot == nullptr || (epi == HMA_EPI_BF16 && aux != nullptr && ldaux % 8 == 0),
               "gemm_nt: rowdot needs the plain bf16 epilogue and a bf16 aux matrix with 16-byte aligned rows");
   HMA_REQUIRE(colsum == nullptr || epi == HMA_EPI_DGELU_BF16 || epi == HMA_EPI_DSILU_BF16 ||
@@ -526,4 +539,25 @@ extern "C" int hma_gemm_nt(const void* A, long long lda, const void* B, long lon
     default: break;
   }
   HMA_REQUIRE(false, "gemm_nt: unknown epilogue %d", epi);
+}
+
+extern "C" int hma_gemm_nt(const void* A, long long lda, const void* B, long long ldb, int M, int N, int K,
+                           int epi, void* out, long long ldo, void* out2, long long ldo2, const float* bias,
+                           const float* resid, long long ldr, const void* aux, long long ldaux, float alpha,
+                           float* colsum, float* rowdot, void* stream_) {
+  return gemm_nt_impl(A, lda, B, ldb, M, N, K, epi, out, ldo, out2, ldo2, bias, resid, ldr, aux, ldaux, alpha, colsum, rowdot, 0, 0,
+                      stream_);
+}
+
+// 3x3 convolution, stride 1, zero padding 1 (nn.Conv2d(k=3, padding=1): external/magvit2 improved_model.py:27-28,135,160,228)
+// over zero-bordered NHWC images: X is bf16 [images * (H+2) * (W+2), Cin] with every border pixel zero, Wt is bf16
+// [Cout, 9 * Cin] (k index = (ky * 3 + kx) * Cin + ci), out fp32 [images * (H+2) * (W+2), Cout] = resid + conv + bias on the
+// interior pixels (border rows of `out` receive values that mean nothing: the next stage re-zeroes them).
+extern "C" int hma_conv3x3_nhwc(const void* X, long long ldx, const void* Wt, long long ldw, int rows, int Cin, int Cout,
+                                int padded_width, void* out, long long ldo, const float* bias, const float* resid,
+                                long long ldr, void* stream_) {
+  HMA_REQUIRE(Cin > 0 && Cin % hma::kBK == 0, "conv3x3: Cin=%d must be a multiple of 64", Cin);
+  HMA_REQUIRE(padded_width >= 3, "conv3x3: bad padded width %d", padded_width);
+  return gemm_nt_impl(X, ldx, Wt, ldw, rows, Cout, 9 * Cin, HMA_EPI_RESID_F32, out, ldo, nullptr, 0, bias, resid, ldr, nullptr, 0,
+                      1.0f, nullptr, nullptr, Cin, padded_width, stream_);
 }

@@ -314,6 +314,32 @@ int hma_gather_token_windows(const void* video, int elem_bytes, long long num_im
 int hma_gather_rows_f32(const float* table, long long num_rows, long long row_elems, const long long* starts, int B,
                         long long rows_per_sample, float* out, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Token -> pixel decode (hma/visualize.py:136-151; external/magvit2 lookup_free_quantize.py:181-194,
+ * improved_model.py:12-51,124-234). Activations are NHWC with a one-pixel zero border per image:
+ * [images * (H+2) * (W+2), C]; fp32 where convolutions accumulate, bf16 for their operands.
+ * ------------------------------------------------------------------------------------------- */
+/* nn.Conv2d(Cin, Cout, 3, padding=1) as one tcgen05 contraction with K = 9 * Cin: X bf16 [rows, Cin] (zero-bordered NHWC,
+ * rows = images * (H+2) * (W+2), padded_width = W+2), Wt bf16 [Cout, 9 * Cin] with k = (ky * 3 + kx) * Cin + ci,
+ * out fp32 [rows, Cout] = resid (optional) + conv + bias (optional); border rows of out are meaningless.
+ * Cin % 64 == 0, Cout % 128 == 0. */
+int hma_conv3x3_nhwc(const void* X, long long ldx, const void* Wt, long long ldw, int rows, int Cin, int Cout,
+                     int padded_width, void* out, long long ldo, const float* bias, const float* resid, long long ldr,
+                     void* stream);
+/* LFQ code lookup + visualize.py's channel flip: out bf16 [images * (H+2) * (W+2), ldc], channel c = +-1 by bit c of the
+ * token id for c < bits, zero for c >= bits and on the border. tokens: i64 [images, H, W]. */
+int hma_lfq_entry(const long long* tokens, int images, int H, int W, int bits, int ldc, void* out, void* stream);
+/* GroupNorm(32, C) statistics: sums[images, 32, 2] (fp32) = (sum, sum of squares) over interior pixels, summed in a fixed
+ * order (bit-reproducible). scratch: fp32 [images, 64, 64] work space. C in {128, 256, 512}. */
+int hma_gn_stats(const float* x, int images, int H, int W, int C, float* scratch, float* sums, void* stream);
+/* mode 0: out(bf16) = swish(GroupNorm(x) * gamma + beta) from those sums; mode 1: out = bf16(x). Border pixels -> 0. */
+int hma_gn_swish(const float* x, const float* sums, const float* gamma, const float* beta, int images, int H, int W, int C,
+                 float eps, int mode, void* out, void* stream);
+/* depth_to_space(block 2), DCR order: in fp32 [images*(H+2)*(W+2), 4*Co] -> out fp32 [images*(2H+2)*(2W+2), Co], border 0. */
+int hma_depth_to_space(const float* in, int images, int H, int W, int Co, float* out, void* stream);
+/* unnormalize_imgs (visualize.py:112-121): channels [0, ch) of x fp32 [images*(H+2)*(W+2), ldc] -> uint8 [images, ch, H, W]. */
+int hma_to_uint8(const float* x, int images, int H, int W, int ldc, int ch, void* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

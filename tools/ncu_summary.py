@@ -31,6 +31,7 @@ WANT = [("gpu__time_duration.sum", "duration"), ("dram__bytes_read.sum", "dram_r
         ("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "tensor_pipe_pct"),
         ("sm__inst_executed_pipe_tensor.sum", "tensor_inst"),
         ("sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm_pct"),
+        ("sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "mufu_pipe_pct"),
         ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue_active_pct"),
         ("sm__warps_active.avg.pct_of_peak_sustained_active", "warps_active_pct"),
         ("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "smem_wavefronts"),
@@ -39,7 +40,12 @@ WANT = [("gpu__time_duration.sum", "duration"), ("dram__bytes_read.sum", "dram_r
         ("launch__shared_mem_per_block_dynamic", "dyn_smem")]
 
 def full(path):
-    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    """path: an .ncu-rep (read through `ncu -i`) or the `--page raw --csv` text already exported on the GPU box (a full-set
+    report of 10+ launches is larger than gpurun's 64 MiB return limit; its CSV is not)."""
+    if path.endswith(".csv"):
+        out = open(path).read()
+    else:
+        out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
     hdr, units = rows[0], rows[1]
     ki = hdr.index("Kernel Name")
