@@ -415,6 +415,39 @@ def config5_leg(dev, world: int, rank: int, sync_all, layers: int, steps: int = 
             "domains_visited": len(seen), "loss": loss, "model_tflops_per_gpu": 3.0 * fwd * B_PER_GPU / (ms / 1e3) / 1e12}
 
 
+def decoder_leg(dev, batch: int = 16, reps: int = 5):
+    """token -> pixel decode (visualize.py:124-169 / the simulator's display path): 16x16 token grids ->
+    256x256 uint8 frames through MagVitDecoder.decode_tokens, host tokens in, host frames out inside the timed region."""
+    from hma_b200.tokenizer import MagVitDecoder, VQConfig
+    torch.manual_seed(0)
+    with torch.device(dev):
+        dec = MagVitDecoder(VQConfig())
+    g = torch.Generator().manual_seed(5)
+    tokens = torch.randint(0, 262144, (batch, 16, 16), generator=g).pin_memory()
+    flops = 0.0
+    for name, m in dec.named_modules():
+        if isinstance(m, torch.nn.Conv2d):
+            lvl = int(name.split(".")[1]) if name.startswith("up.") else (0 if name == "conv_out" else 4)
+            side = 16 * 2 ** (4 - lvl)
+            flops += 2.0 * side * side * m.weight.numel()
+    for _ in range(2):
+        dec.decode_tokens(tokens.to(dev, non_blocking=True)).cpu()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        frames = dec.decode_tokens(tokens.to(dev, non_blocking=True)).cpu()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    del dec
+    torch.cuda.empty_cache()
+    return {"metric": "decoded_frames_per_s", "value": batch / (ms / 1e3), "unit": "frames/s", "ms_per_batch": ms, "batch": batch,
+            "frame": list(frames.shape[1:]), "gflop_per_frame": flops / 1e9, "achieved_tflops": flops * batch / (ms / 1e3) / 1e12,
+            "what": "LFQ code lookup + MagViT2 decoder (40.5 M parameters, 19 3x3 convolutions as tcgen05 contractions with "
+                    "TMA-offset taps) + uint8 mapping; random weights (the checkpoint is not available offline)"}
+
+
 def gpu_reference_leg(dev, steps: int = 3, warmup: int = 1):
     """SURVEY.md §8(d) / BASELINE.md §5, "the bar to beat on the same box": the reference's algorithm in plain PyTorch on the
     SAME B200 under torch.autocast(bf16) — cuBLAS GEMMs, ATen element-wise kernels and (i) the reference's own math attention
@@ -667,10 +700,11 @@ def main() -> None:
             gen_strong = generation_leg(model, dev, world, rank, domains, d_actions, sync_all, per_gpu=False)
 
     # ---------------- interactive single-frame loop (B=1) and the on-device data pipeline (rank 0 only: no collective)
-    interactive = pipeline = None
+    interactive = pipeline = pixel_decode = None
     if not args.no_extras and rank == 0:
         interactive = interactive_leg(model, dev, domains, d_actions)
         pipeline = pipeline_leg(dev)
+        pixel_decode = decoder_leg(dev)
     sync_all()
 
     # ---------------- optional per-stage breakdown (one extra, untimed step)
@@ -798,6 +832,8 @@ def main() -> None:
     if pipeline is not None:
         pipeline["train_step_consumes_samples_per_s"] = B_PER_GPU * args.steps / (ms_resident / 1e3)
         line["pipeline"] = pipeline
+    if pixel_decode is not None:
+        line["pixel_decode"] = pixel_decode
     if gpu_ref is not None:
         gpu_ref["speedup_train_vs_sdpa"] = value / gpu_ref["train_sdpa"]["value"]
         gpu_ref["speedup_train_vs_math"] = value / gpu_ref["train_math"]["value"]
