@@ -602,7 +602,7 @@ def main() -> None:
                 p.normal_(0.0, 0.02)
     n_params = sum(p.numel() for p in model.parameters())
     step_fn = TrainStep(model, lr=1e-4, weight_decay=0.05, max_grad_norm=1.0, cuda_graphs=not args.no_graphs,
-                        overlap_segments=int(os.environ.get("HMA_B200_OVERLAP_SEGMENTS", "4")))  # env: A/B measurements only
+                        overlap_segments=int(os.environ.get("HMA_B200_OVERLAP_SEGMENTS", "1")))  # env: A/B measurements only
 
     total = args.warmup + args.steps
     gen = torch.Generator().manual_seed(1234 + rank)
@@ -790,10 +790,10 @@ def main() -> None:
                    "global_batch": world * B_PER_GPU, "tokens_per_step": tokens_per_step, "parallelism": f"dp{world}",
                    "l2": "per-step working set (~19 GB of activations) >> 126 MB L2; no explicit flush needed",
                    "loss": loss_val, "model_tflops_per_gpu": step_tf,
-                   "cuda_graph": ("forward+loss+backward replayed from CUDA graphs per action domain (captured before the timed "
-                                  "region; N > 1: one graph per backward segment with the shared-gradient all-reduce of that "
-                                  "segment launched between replays, overlapping the rest of the backward); domain-block "
-                                  "all-gather, clip and AdamW launched from the host")
+                   "cuda_graph": ("forward+loss+backward replayed from one CUDA graph per action domain (captured before the timed "
+                                  "region; with grad_exchange_segments > 1: one graph per backward segment and the shared-gradient "
+                                  "all-reduce of each segment launched between the replays); gradient exchange, clip and AdamW "
+                                  "launched from the host")
                    if graphs_on else "off",
                    "grad_exchange_segments": exchange_segments},
         "e2e": {"value": e2e, "unit": "tokens/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8,

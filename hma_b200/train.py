@@ -135,7 +135,7 @@ def exchange_gradients(grad: torch.Tensor, shared_size: int, max_dom_size: int, 
 class TrainStep:
     def __init__(self, model, lr: float = 1e-4, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.05,
                  max_grad_norm: Optional[float] = 1.0, process_group=None, cuda_graphs: bool = False,
-                 mu_transfer: bool = False, overlap_segments: int = 4):
+                 mu_transfer: bool = False, overlap_segments: int = 1):
         """The optimizer is the reference's (train_multi.py:899-922): AdamW over two parameter groups — names containing
         "bias" or "layer_norm.weight" get weight_decay 0, everything else `weight_decay`. `mu_transfer=True` selects the
         reference's `mup.MuAdamW`: it divides the learning rate of matrix-like parameters by their width multiplier
@@ -143,11 +143,14 @@ class TrainStep:
         (st_mask_git.py:755-760) — the only width these kernels are built for, so every multiplier is 1 and MuAdamW's
         update is AdamW's; wider models are rejected by engine.check_config before they get here.
 
-        world_size > 1: the all-reduce of the shared gradient range is issued in `overlap_segments` pieces DURING the backward
-        — after the backward of layers 24..31 their gradients go on the wire while layers 23..0 are still being computed, and
-        so on (what DDP's buckets do in the reference, train_multi.py:779-781,990) — on NCCL's own stream; with CUDA graphs
-        the forward+backward is captured as one graph per segment and the collectives are launched between the replays.
-        overlap_segments=1 restores the single all-reduce after the backward.
+        world_size > 1, overlap_segments > 1: the all-reduce of the shared gradient range is issued in that many pieces
+        DURING the backward — after the backward of layers 24..31 their gradients go on the wire while layers 23..0 are still
+        being computed, and so on (what DDP's buckets do in the reference, train_multi.py:779-781,990) — on NCCL's own stream;
+        with CUDA graphs the forward+backward is captured as one graph per segment and the collectives are launched between
+        the replays. Parity-tested on two GPUs (tests/ddp_parity_2gpu.py). It is OFF by default because it measured no gain
+        on B200: 31.64 vs 31.65 ms/step at N=2 and 32.24 vs 32.12 at N=8 (4 segments vs 1) — the persistent GEMM / attention
+        CTAs fill every SM's register file, so an NCCL kernel only gets SMs at kernel boundaries and then delays the compute
+        CTAs queued behind it by as much as it hides.
 
         cuda_graphs=True: forward + loss + backward of each (domain, shape) is captured into a CUDA graph on its
         second use (or by precapture()) and replayed from static input buffers afterwards; the gradient exchange,
