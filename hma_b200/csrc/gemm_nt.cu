@@ -41,6 +41,7 @@ struct GemmNtParams {
   // coordinate, not an im2col copy. conv_kb_per_tap = Cin / 64; 0 = ordinary GEMM.
   int conv_kb_per_tap;
   int conv_wp;
+  int stages;  // depth of the A (and streamed B) ring, 2..kMaxStages: as deep as shared memory allows (bytes in flight per SM)
 };
 
 constexpr int kBM = 128;
@@ -56,6 +57,7 @@ template <int EPI> struct StageBytes {
 constexpr int kStageF32Row = 144;           // 32 fp32 + 16 B pad: conflict-free 16-byte row writes
 constexpr int kStageBf16Row = 80;           // 32 bf16 + 16 B pad
 constexpr int kSmemLimit = 227 * 1024 - 1024;
+constexpr int kMaxStages = 8;
 
 __device__ __forceinline__ void sts_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
@@ -256,7 +258,6 @@ template <int BN, int EPI, bool STAT>
 __global__ void __launch_bounds__(128 + 32 * EpiWarps<EPI>::value, 1)
 gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const GemmNtParams p) {
-  constexpr int kStages = (BN == 256) ? 3 : 4;
   constexpr int kBStage = BN * kBK * 2;
   constexpr int kEpiWarps = EpiWarps<EPI>::value;
   constexpr int kStageBytes = StageBytes<EPI>::value;
@@ -265,14 +266,15 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   constexpr uint32_t kIdesc = umma_idesc_bf16(kBM, BN, 0, 0);
 
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t bar_full[kStages];
-  __shared__ __align__(8) uint64_t bar_empty[kStages];
+  __shared__ __align__(8) uint64_t bar_full[kMaxStages];
+  __shared__ __align__(8) uint64_t bar_empty[kMaxStages];
   __shared__ __align__(8) uint64_t bar_bfull;
   __shared__ __align__(8) uint64_t bar_tfull[2];
   __shared__ __align__(8) uint64_t bar_tempty[2];
   __shared__ uint32_t tmem_base_slot;
 
   const int KB = p.K / kBK;
+  const int kStages = p.stages;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t smemA = smem_base;
   const uint32_t smemB = smem_base + kStages * kAStage;
@@ -447,16 +449,28 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 }
 
 template <int BN, int EPI>
-static size_t smem_need(int KB, bool stat) {
-  constexpr int kStages = (BN == 256) ? 3 : 4;
+static size_t smem_need(int KB, bool stat, int stages) {
   constexpr int kBStage = BN * kBK * 2;
-  return 1024 + (size_t)kStages * kAStage + (size_t)(stat ? KB : kStages) * kBStage +
+  return 1024 + (size_t)stages * kAStage + (size_t)(stat ? KB : stages) * kBStage +
          (size_t)EpiWarps<EPI>::value * StageBytes<EPI>::value;
+}
+// Deepest ring that fits: the kernels are HBM-bound and a CTA's bytes in flight are what it can ask of the memory system
+// (3 x 16 KB was ~Little's-law minimum at an unloaded latency; under load the latency doubles).
+template <int BN, int EPI>
+static int pick_stages(int KB, bool stat) {
+  // measured (tools/kbench.py, config-2 shapes): the deep ring helps where A dominates the traffic (bf16 epilogues 18.6 ->
+  // 16.7 us, the K = 1024 residual GEMM 50 -> 45 us) and HURTS the stationary-B residual GEMM (28.6 -> 31.6 us with 7 stages):
+  // there the fp32 residual read by the epilogue is twice the A traffic and sits on the critical path
+  int st = (EPI == HMA_EPI_RESID_F32 && stat) ? 4 : kMaxStages;
+  while (st > 2 && smem_need<BN, EPI>(KB, stat, st) > (size_t)kSmemLimit) --st;
+  return st;
 }
 
 template <int BN, int EPI, bool STAT>
-static int launch_nt(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmNtParams& p, cudaStream_t stream) {
-  const size_t smem = smem_need<BN, EPI>(p.K / kBK, STAT);
+static int launch_nt(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmNtParams& p_in, cudaStream_t stream) {
+  GemmNtParams p = p_in;
+  p.stages = pick_stages<BN, EPI>(p.K / kBK, STAT);
+  const size_t smem = smem_need<BN, EPI>(p.K / kBK, STAT, p.stages);
   auto kern = gemm_nt_kernel<BN, EPI, STAT>;
   static hma_host::PerDeviceFlag attr_flag;  // function attributes are per device (context)
   bool& attr_done = attr_flag.get();  // idempotent; racing threads set the same value
@@ -480,10 +494,10 @@ static int dispatch_nt(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
                        cudaStream_t stream) {
   const int KB = p.K / kBK;
   if (bn == 256) {
-    const bool stat = smem_need<256, EPI>(KB, true) <= (size_t)kSmemLimit;
+    const bool stat = smem_need<256, EPI>(KB, true, 2) <= (size_t)kSmemLimit;
     return stat ? launch_nt<256, EPI, true>(tmA, tmB, p, stream) : launch_nt<256, EPI, false>(tmA, tmB, p, stream);
   }
-  const bool stat = smem_need<128, EPI>(KB, true) <= (size_t)kSmemLimit;
+  const bool stat = smem_need<128, EPI>(KB, true, 2) <= (size_t)kSmemLimit;
   return stat ? launch_nt<128, EPI, true>(tmA, tmB, p, stream) : launch_nt<128, EPI, false>(tmA, tmB, p, stream);
 }
 
