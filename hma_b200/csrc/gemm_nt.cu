@@ -17,6 +17,7 @@
 // through a per-warp padded shared-memory buffer, and residual / saved-activation reads and all
 // stores are issued in the transposed domain, where a warp instruction touches whole 64/128-byte
 // row segments.
+#include <cstdlib>
 #include "common.cuh"
 #include "../../include/hma_b200.h"
 
@@ -49,7 +50,7 @@ constexpr int kBK = 64;
 constexpr int kAStage = kBM * kBK * 2;      // 16 KB
 // Epilogue warps: 8 (two per TMEM lane quarter), or 16 for the GELU epilogue, whose arithmetic (erf, two bf16
 // outputs per accumulator) is issue- and latency-bound with only two warps per scheduler.
-template <int EPI> struct EpiWarps { static constexpr int value = (EPI == HMA_EPI_GELU_BF16) ? 16 : 8; };
+template <int EPI> struct EpiWarps { static constexpr int value = (EPI == HMA_EPI_GELU_BF16 || EPI == HMA_EPI_DGELU_BF16) ? 16 : 8; };
 // Per-warp staging buffer: 32 padded fp32 rows when the epilogue transposes fp32 (residual / d-activation), else bf16 rows.
 template <int EPI> struct StageBytes {
   static constexpr int value = (EPI == HMA_EPI_RESID_F32 || EPI == HMA_EPI_DGELU_BF16 || EPI == HMA_EPI_DSILU_BF16) ? 32 * 144 : 32 * 80;
@@ -519,6 +520,9 @@ static int gemm_nt_impl(const void* A, long long lda, const void* B, long long l
   // Few rows (decode / sampler shapes, M <= a few hundred): 256-wide tiles would occupy a fraction of the SMs and each
   // CTA's k-loop is latency-bound, so halve the tile width to double the CTAs in flight.
   if (bn == 256 && (long long)((M + kBM - 1) / kBM) * (N / 256) * 2 <= hma_host::sm_count()) bn = 128;
+  // dGELU: the epilogue (3 loads, 2 MUFU ops, ~16 instructions per element) is latency-bound with two warps per scheduler;
+  // sixteen epilogue warps need their fp32 staging buffers (74 KB), which only fits beside a stationary B with 128-wide tiles
+  if (epi == HMA_EPI_DGELU_BF16) bn = 128;  // (the same change for the forward GELU epilogue measured worse: 52.7 vs 50.3 us)
   CUtensorMap tmA, tmB;
   int rc = hma_host::make_tmap_bf16_2d(&tmA, A, (uint64_t)(conv_cin > 0 ? conv_cin : K), (uint64_t)M, (uint64_t)lda * 2, kBK, kBM);
   if (rc) return rc;
