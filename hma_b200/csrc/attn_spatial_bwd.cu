@@ -8,7 +8,7 @@
 //   dV, dK       : A = P^T / dS^T read MN-major from the bf16 tiles the compute warps wrote,
 //                  B = dO / Q read MN-major (reduction over query rows)
 //   dQ           : A = dS K-major, B = K MN-major (reduction over keys)
-// Accumulators live in TMEM (S 128 + dP 128 + dQ 3x32 + dK 32 + dV 32 columns).
+// Accumulators live in TMEM (S 128 + dP 128 + dQ 3x32 + 2 x (dK 32 + dV 32) columns).
 //
 // The element-wise work is a two-stage, warp-specialised pipeline (both stages: warp w owns TMEM lane quarter w%4
 // and a 64-key column half):
@@ -73,7 +73,7 @@ attn_spatial_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
                         const AttnBwdParams p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar_load[3], bar_s, bar_dp, bar_sfree, bar_dpfree, bar_p[2], bar_ds[2], bar_pfree[2], bar_dsfree[2], bar_kv,
-      bar_epi, bar_final;
+      bar_epi[2], bar_final;
   __shared__ uint32_t tmem_base_slot;
   __shared__ float s_lse[kBMaxN];
   __shared__ float s_delta[kBMaxN];
@@ -107,7 +107,8 @@ attn_spatial_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
       mbar_init(smem_u32(&bar_dsfree[i]), 2);  // dK and dQ have consumed dS[i]
     }
     mbar_init(smem_u32(&bar_kv), 2);  // dV issuer + dK issuer: both accumulators of the key tile are final
-    mbar_init(smem_u32(&bar_epi), kStageThreads);
+    mbar_init(smem_u32(&bar_epi[0]), kStageThreads);
+    mbar_init(smem_u32(&bar_epi[1]), kStageThreads);
     mbar_init(smem_u32(&bar_final), 1);
     fence_barrier_init();
   }
@@ -163,6 +164,9 @@ attn_spatial_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
   tc_fence_after();
   if (threadIdx.x == 0) HMA_TL(0, 4);
   const uint32_t tmem_base = tmem_base_slot;
+  // dK / dV accumulators are double-buffered over key tiles (buffer kt & 1, kAccBuf columns apart): the contractions of
+  // key tile kt + 1 start while tile kt's accumulators are still waiting to be written out
+  constexpr uint32_t kAccBuf = 64;
   const uint32_t tS = tmem_base, tDP = tmem_base + 128, tDQ = tmem_base + 256, tDK = tmem_base + 352,
                  tDV = tmem_base + 384;
 
@@ -230,18 +234,19 @@ attn_spatial_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
           mbar_wait(smem_u32(&bar_load[qt]), 0);  // dO tile qt (long since landed: S of this pair needed it too)
           mbar_wait(smem_u32(&bar_p[bsel]), (uint32_t)((it >> 1) & 1));
           HMA_TL(2, it);
-          if (qt == 0 && kt > 0) {  // dV of the last key tile has been read out of TMEM
-            mbar_wait(smem_u32(&bar_epi), (uint32_t)((kt - 1) & 1));
+          const uint32_t tD = tDV + (uint32_t)(kt & 1) * kAccBuf;
+          if (qt == 0 && kt >= 2) {  // the dV that last used this accumulator buffer has been read out of TMEM
+            mbar_wait(smem_u32(&bar_epi[kt & 1]), (uint32_t)(((kt >> 1) - 1) & 1));
             tc_fence_after();
           }
           if (kq16 == 8) {
-            umma_ss(tDV, mk(pl, kHi128), mk(dl, kHi64), idesc_t, acc0);
+            umma_ss(tD, mk(pl, kHi128), mk(dl, kHi64), idesc_t, acc0);
 #pragma unroll
             for (int kk = 1; kk < 8; ++kk)
-              umma_ss(tDV, mk(pl + (uint32_t)(kk * 2048 >> 4), kHi128), mk(dl + (uint32_t)(kk * 1024 >> 4), kHi64), idesc_t, 1u);
+              umma_ss(tD, mk(pl + (uint32_t)(kk * 2048 >> 4), kHi128), mk(dl + (uint32_t)(kk * 1024 >> 4), kHi64), idesc_t, 1u);
           } else {
             for (int kk = 0; kk < kq16; ++kk)
-              umma_ss(tDV, mk(pl + (uint32_t)kk * (2048u >> 4), kHi128), mk(dl + (uint32_t)kk * (1024u >> 4), kHi64), idesc_t,
+              umma_ss(tD, mk(pl + (uint32_t)kk * (2048u >> 4), kHi128), mk(dl + (uint32_t)kk * (1024u >> 4), kHi64), idesc_t,
                       kk == 0 ? acc0 : 1u);
           }
           umma_commit(smem_u32(&bar_pfree[bsel]));
@@ -263,18 +268,19 @@ attn_spatial_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
           const uint32_t acc0 = (uint32_t)(qt != 0);
           mbar_wait(smem_u32(&bar_load[qt]), 0);
           mbar_wait(smem_u32(&bar_ds[bsel]), (uint32_t)((it >> 1) & 1));
-          if (qt == 0 && kt > 0) {  // dK of the last key tile has been read out of TMEM
-            mbar_wait(smem_u32(&bar_epi), (uint32_t)((kt - 1) & 1));
+          const uint32_t tD = tDK + (uint32_t)(kt & 1) * kAccBuf;
+          if (qt == 0 && kt >= 2) {  // the dK that last used this accumulator buffer has been read out of TMEM
+            mbar_wait(smem_u32(&bar_epi[kt & 1]), (uint32_t)(((kt >> 1) - 1) & 1));
             tc_fence_after();
           }
           if (kq16 == 8) {
-            umma_ss(tDK, mk(sl, kHi128), mk(ql, kHi64), idesc_t, acc0);
+            umma_ss(tD, mk(sl, kHi128), mk(ql, kHi64), idesc_t, acc0);
 #pragma unroll
             for (int kk = 1; kk < 8; ++kk)
-              umma_ss(tDK, mk(sl + (uint32_t)(kk * 2048 >> 4), kHi128), mk(ql + (uint32_t)(kk * 1024 >> 4), kHi64), idesc_t, 1u);
+              umma_ss(tD, mk(sl + (uint32_t)(kk * 2048 >> 4), kHi128), mk(ql + (uint32_t)(kk * 1024 >> 4), kHi64), idesc_t, 1u);
           } else {
             for (int kk = 0; kk < kq16; ++kk)
-              umma_ss(tDK, mk(sl + (uint32_t)kk * (2048u >> 4), kHi128), mk(ql + (uint32_t)kk * (1024u >> 4), kHi64), idesc_t,
+              umma_ss(tD, mk(sl + (uint32_t)kk * (2048u >> 4), kHi128), mk(ql + (uint32_t)kk * (1024u >> 4), kHi64), idesc_t,
                       kk == 0 ? acc0 : 1u);
           }
           umma_commit(smem_u32(&bar_dsfree[bsel]));
@@ -333,10 +339,8 @@ attn_spatial_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
             mbar_wait(smem_u32(&bar_pfree[bsel]), (uint32_t)(((it - 2) >> 1) & 1));
             mbar_wait(smem_u32(&bar_ds[bsel]), (uint32_t)(((it - 2) >> 1) & 1));
           }
-          if (threadIdx.x == 0) HMA_TL(5, it);
           mbar_wait(smem_u32(&bar_s), (uint32_t)(it & 1));
           tc_fence_after();
-          if (threadIdx.x == 0) HMA_TL(6, it);
           const int qi = qt * 128 + row;
           const float L = qi < n ? s_lse[qi] : 0.f;
           // warp-uniform: rows past the frame are never read by the dV / dK contractions and only produce dQ rows
@@ -351,7 +355,6 @@ attn_spatial_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
           tmem_ld_wait();
           tc_fence_before();
           mbar_arrive(smem_u32(&bar_sfree));
-          if (threadIdx.x == 0) HMA_TL(7, it);
           auto exp_chunk = [&](const uint32_t (&sv)[32], int c) {
             if (rows_live && half * 64 + c * 32 < nk) {
               uint32_t pk[16];
@@ -371,7 +374,7 @@ attn_spatial_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
           exp_chunk(s1, 1);
           fence_proxy_async();
           mbar_arrive(smem_u32(&bar_p[bsel]));
-          if (threadIdx.x == 0) HMA_TL(8, it);
+          if (lane == 0) { if (warp == 0) HMA_TL(5, it); if (warp == 3) HMA_TL(6, it); if (warp == 4) HMA_TL(7, it); if (warp == 7) HMA_TL(8, it); }
         }
       }
     } else {
@@ -380,10 +383,10 @@ attn_spatial_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
         mbar_wait(smem_u32(&bar_kv), (uint32_t)(kt & 1));
         tc_fence_after();
         uint32_t r[32];
-        tmem_ld_x32((half == 0 ? tDK : tDV) + lane_addr, r);
+        tmem_ld_x32((half == 0 ? tDK : tDV) + (uint32_t)(kt & 1) * kAccBuf + lane_addr, r);
         tmem_ld_wait();
         tc_fence_before();
-        mbar_arrive(smem_u32(&bar_epi));
+        mbar_arrive(smem_u32(&bar_epi[kt & 1]));
         const int ki = kt * 128 + row;
         if (ki < n)
           store_head_row(p.dqkv + (size_t)(row0 + ki) * p.ld_dqkv + (half == 0 ? p.k_col : p.v_col) + head * 32, r);
@@ -395,12 +398,9 @@ attn_spatial_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
         for (int qt = 0; qt < ntile; ++qt, ++it) {
           const int bsel = it & 1;
           if (it >= 2) mbar_wait(smem_u32(&bar_dsfree[bsel]), (uint32_t)(((it - 2) >> 1) & 1));  // dS[bsel] consumed by dK, dQ
-          if (threadIdx.x == kStageThreads) HMA_TL(12, it);
           mbar_wait(smem_u32(&bar_dp), (uint32_t)(it & 1));
           tc_fence_after();
-          if (threadIdx.x == kStageThreads) HMA_TL(13, it);
           mbar_wait(smem_u32(&bar_p[bsel]), (uint32_t)((it >> 1) & 1));  // P of this pair is in shared memory
-          if (threadIdx.x == kStageThreads) HMA_TL(14, it);
           const int qi = qt * 128 + row;
           const float delta = qi < n ? s_delta[qi] : 0.f;
           const float nds = -delta * p.scale;
@@ -437,7 +437,7 @@ attn_spatial_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
           }
           fence_proxy_async();
           mbar_arrive(smem_u32(&bar_ds[bsel]));
-          if (threadIdx.x == kStageThreads) HMA_TL(15, it);
+          if (lane == 0) { if (warp == 8) HMA_TL(12, it); if (warp == 9) HMA_TL(13, it); if (warp == 12) HMA_TL(14, it); if (warp == 15) HMA_TL(15, it); }
           // dK / dV of a finished key tile are written out one iteration late, after the dS of the next tile pair has
           // been handed to the tensor core, so the stores overlap its contractions
           if (pending_kt >= 0) {

@@ -16,8 +16,8 @@ KERNELS = {
     "gemm_nt": dict(single=(0, 10), names={0: "start", 10: "end", 1: "mma:top", 2: "mma:tmem_free", 3: "mma:committed", 4: "epi:top",
                                            5: "epi:acc_ready", 6: "epi:done"}),
     "gemm_wgrad": dict(single=(0, 3, 4, 5), names={0: "start", 3: "mma_done", 4: "red_issued", 5: "end", 1: "tma_issued", 2: "full"}),
-    "attn_spatial_bwd": dict(names={0: "start", 11: "loaded", 1: "SdP_issued", 5: "A:top", 6: "A:S_ready", 7: "A:S_freed",
-                                    8: "A:P_arrived", 12: "B:top", 13: "B:dP_ready", 14: "B:P_seen", 15: "B:dS_arrived",
+    "attn_spatial_bwd": dict(names={0: "start", 11: "loaded", 1: "SdP_issued", 5: "A0:P", 6: "A3:P", 7: "A4:P", 8: "A7:P",
+                                    12: "B8:dS", 13: "B9:dS", 14: "B12:dS", 15: "B15:dS",
                                     2: "dV:go", 3: "dV:issued", 4: "dK:issued", 9: "final", 10: "end"}),
 }
 
