@@ -31,6 +31,8 @@ _SIGNATURES = {
     "hma_device_check": [],
     "hma_gemm_nt": [c_void_p, c_ll, c_void_p, c_ll, c_int, c_int, c_int, c_int, c_void_p, c_ll, c_void_p, c_ll,
                     c_fp, c_fp, c_ll, c_void_p, c_ll, c_float, c_fp, c_fp, c_void_p],
+    "hma_gemm_nt_ln": [c_void_p, c_ll, c_void_p, c_ll, c_int, c_int, c_int, c_void_p, c_ll, c_fp, c_fp, c_ll, c_float, c_int,
+                       c_fp, c_fp, c_fp, c_int, c_float, c_void_p, c_ll, c_fp, c_void_p],
     "hma_attn_spatial_fwd": [c_void_p, c_ll, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p, c_ll, c_fp,
                              c_void_p],
     "hma_attn_spatial_bwd": [c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_ll, c_fp, c_int, c_int, c_int, c_int, c_int,

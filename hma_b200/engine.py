@@ -19,6 +19,8 @@ import math
 from dataclasses import dataclass
 from typing import Dict, List, Optional
 
+import os
+
 import torch
 
 from . import ops
@@ -157,6 +159,11 @@ class Engine:
         self.weights = Weights()
         self._stem_w0: Dict[str, tuple] = {}
         self._side: Dict[int, torch.cuda.Stream] = {}
+        # HMA_B200_FUSE_LN=1: LayerNorms emitted by the preceding residual GEMM's epilogue (ops.gemm_nt_ln) instead of separate
+        # row-wise kernels. Off by default: measured on config 2 the fused step is 30.37 ms against 30.04 ms — inside a step
+        # the row-wise kernel finds the stream in L2, while the epilogue's extra work sits on the GEMM's critical path
+        # (DESIGN.md 3.9).
+        self.fuse_ln = os.environ.get("HMA_B200_FUSE_LN", "0") == "1"
 
     @staticmethod
     def check(cfg) -> None:
@@ -300,12 +307,18 @@ class Engine:
                 hmods, zmods, mods, mod_events = self.modulation_all_layers(p, c_bf, dom, d.num_layers, training)
         layers = []
         qk = bool(self.cfg.qk_norm)  # norm1 / norm2 are Identity and q, k get a shared per-head LayerNorm (attention.py:32-35)
+        # Every LayerNorm of the trunk follows a residual Linear with 256 output columns: that GEMM's epilogue emits the
+        # normalised bf16 operand of the next stage itself (ops.gemm_nt_ln), so the stream is not re-read by a row-wise pass.
+        fuse_ln = self.fuse_ln and not qk
+        a1_next = None  # (LN1 output, stats) of the layer about to run, when the previous layer's fc2 produced them
         for i in range(d.num_layers):
             lp = f"decoder.layers.{i}."
             L = {}
             # ---- spatial attention, pre-norm (st_transformer.py:85-86)
             if qk:
                 a1, st1 = ops.ln_fwd(x, 0), None
+            elif a1_next is not None:
+                (a1, st1), a1_next = a1_next, None
             else:
                 a1, st1 = ops.ln_fwd(x, 1, gamma=p[lp + "norm1.weight"], beta=p[lp + "norm1.bias"], eps=1e-5, want_stats=True)
             qkv_s = ops.gemm_nt(a1, Wp[lp + "spatial_attn.qkv.weight"], EPI_BF16, bias=p.get(lp + "spatial_attn.qkv.bias"))
@@ -316,17 +329,24 @@ class Engine:
             att_s, lse = ops.attn_spatial_fwd(qkv_s, M, n, d.heads, d.scale, want_lse=training)
             plain = not d.modulate and not d.additive  # x2 is x1: the temporal stage's bf16 operand comes out of this GEMM
             at = torch.empty(N, C, device=x.device, dtype=torch.bfloat16)
-            x1 = ops.gemm_nt(att_s, Wp[lp + "spatial_attn.proj.weight"], EPI_RESID, bias=p.get(lp + "spatial_attn.proj.bias"),
-                             resid=x, out=None if training else x, out2=at if plain else None)
+            if d.modulate and mod_events:
+                torch.cuda.current_stream().wait_event(mod_events[i])
+            if d.modulate and fuse_ln:  # the projection's epilogue also emits ModulateLayer's (1 + scale) * LN(x1) + shift
+                x1, am, stm = ops.gemm_nt_ln(att_s, Wp[lp + "spatial_attn.proj.weight"], resid=x, out=None if training else x,
+                                             bias=p.get(lp + "spatial_attn.proj.bias"), ln_mode=2, mod=mods[i], rows_per_group=n,
+                                             eps=1e-6, want_stats=True)
+            else:
+                am = None
+                x1 = ops.gemm_nt(att_s, Wp[lp + "spatial_attn.proj.weight"], EPI_RESID, bias=p.get(lp + "spatial_attn.proj.bias"),
+                                 resid=x, out=None if training else x, out2=at if plain else None)
             # ---- per-layer action conditioning (st_transformer.py:102-104; st_mask_git.py:66-76)
             if d.modulate:
                 ap = lp + f"action_projectors.{dom}."
-                if mod_events:
-                    torch.cuda.current_stream().wait_event(mod_events[i])
                 mod = mods[i]
                 hmod = hmods[i] if training else None
                 zmod = zmods[i] if training else None
-                am, stm = ops.ln_fwd(x1, 2, mod=mod, rows_per_group=n, eps=1e-6, want_stats=True)
+                if am is None:
+                    am, stm = ops.ln_fwd(x1, 2, mod=mod, rows_per_group=n, eps=1e-6, want_stats=True)
                 x2 = ops.gemm_nt(am, Wp[ap + "linear_out.weight"], EPI_RESID, bias=p[ap + "linear_out.bias"], resid=x1,
                                  out=None if training else x1, out2=at)
                 if training:
@@ -352,19 +372,30 @@ class Engine:
                 ops.kv_cache_append(qkv_t, B, T, n, kv[i], t0)
                 if i == d.num_layers - 1:
                     return None, None  # nothing downstream of the last layer's K/V is needed
-            x3 = ops.gemm_nt(att_t, Wp[lp + "temporal_attn.proj.weight"], EPI_RESID, bias=p.get(lp + "temporal_attn.proj.bias"),
-                             resid=x2, out=None if training else x2)
-            # ---- MLP, pre-norm, erf-GELU (st_transformer.py:24-27,112)
-            if qk:
-                a2, st2 = ops.ln_fwd(x3, 0), None
+            # ---- MLP, pre-norm, erf-GELU (st_transformer.py:24-27,112); norm2 comes out of the temporal projection
+            if fuse_ln:
+                x3, a2, st2 = ops.gemm_nt_ln(att_t, Wp[lp + "temporal_attn.proj.weight"], resid=x2, out=None if training else x2,
+                                             bias=p.get(lp + "temporal_attn.proj.bias"), ln_mode=1, gamma=p[lp + "norm2.weight"],
+                                             beta=p[lp + "norm2.bias"], eps=1e-5, want_stats=True)
             else:
-                a2, st2 = ops.ln_fwd(x3, 1, gamma=p[lp + "norm2.weight"], beta=p[lp + "norm2.bias"], eps=1e-5, want_stats=True)
+                x3 = ops.gemm_nt(att_t, Wp[lp + "temporal_attn.proj.weight"], EPI_RESID, bias=p.get(lp + "temporal_attn.proj.bias"),
+                                 resid=x2, out=None if training else x2)
+                if qk:
+                    a2, st2 = ops.ln_fwd(x3, 0), None
+                else:
+                    a2, st2 = ops.ln_fwd(x3, 1, gamma=p[lp + "norm2.weight"], beta=p[lp + "norm2.bias"], eps=1e-5, want_stats=True)
             z = torch.empty(N, 1024, device=x.device, dtype=torch.bfloat16) if training else None
             h = ops.gemm_nt(a2, Wp[lp + "mlp.fc1.weight"], EPI_GELU, bias=p.get(lp + "mlp.fc1.bias"), out2=z)
             if drop_p > 0.0:
                 ops.dropout_bf16_(h, drop_p, drop[1] + 2 * i, drop[2])
                 x4 = ops.dropout_add_f32(ops.gemm_nt(h, Wp[lp + "mlp.fc2.weight"], EPI_RESID, bias=p.get(lp + "mlp.fc2.bias")),
                                          x3, drop_p, drop[1] + 2 * i + 1, seed_dev=drop[2])
+            elif fuse_ln and i + 1 < d.num_layers:  # fc2's epilogue emits the next layer's norm1
+                nl = f"decoder.layers.{i + 1}."
+                x4, a_n, st_n = ops.gemm_nt_ln(h, Wp[lp + "mlp.fc2.weight"], resid=x3, out=None if training else x3,
+                                               bias=p.get(lp + "mlp.fc2.bias"), ln_mode=1, gamma=p[nl + "norm1.weight"],
+                                               beta=p[nl + "norm1.bias"], eps=1e-5, want_stats=True)
+                a1_next = (a_n, st_n)
             else:
                 x4 = ops.gemm_nt(h, Wp[lp + "mlp.fc2.weight"], EPI_RESID, bias=p.get(lp + "mlp.fc2.bias"), resid=x3,
                                  out=None if training else x3)

@@ -83,6 +83,24 @@ def gemm_nt(A: torch.Tensor, B: torch.Tensor, epi: int, *, out: Optional[torch.T
     return out
 
 
+def gemm_nt_ln(A: torch.Tensor, B: torch.Tensor, *, resid: Optional[torch.Tensor], ln_mode: int, out: Optional[torch.Tensor] = None,
+               bias: Optional[torch.Tensor] = None, alpha: float = 1.0, gamma=None, beta=None, mod=None, rows_per_group: int = 0,
+               eps: float = 1e-5, want_stats: bool = False):
+    """x = resid + A[M,K] @ B[256,K]^T + bias (fp32) and, from the same epilogue, y = bf16(LayerNorm(x)) for the next stage
+    (ln_mode 1: affine; 2: (1 + scale) * LN(x) + shift per group of rows_per_group rows). Returns (x, y, stats or None)."""
+    M, K = A.shape
+    N = B.shape[0]
+    assert N == 256 and B.shape[1] == K and A.dtype == BF16 and B.dtype == BF16 and A.stride(1) == 1 and B.stride(1) == 1
+    if out is None:
+        out = torch.empty(M, N, device=A.device, dtype=F32)
+    y = torch.empty(M, N, device=A.device, dtype=BF16)
+    stats = torch.empty(M, 2, device=A.device, dtype=F32) if want_stats else None
+    _call(f"gemm_nt_ln[K={K},mode={ln_mode}]", 2.0 * M * N * K, "hma_gemm_nt_ln", A.data_ptr(), A.stride(0), B.data_ptr(), B.stride(0),
+          M, N, K, out.data_ptr(), out.stride(0), _p(bias), _p(resid), resid.stride(0) if resid is not None else 0, float(alpha),
+          ln_mode, _p(gamma), _p(beta), _p(mod), rows_per_group, float(eps), y.data_ptr(), y.stride(0), _p(stats), _s())
+    return out, y, stats
+
+
 def gemm_wgrad(G: torch.Tensor, X: torch.Tensor, dW: torch.Tensor) -> None:
     """dW[Mw,Nw] (fp32) += G[tokens,Mw]^T @ X[tokens,Nw]."""
     tokens, Mw = G.shape

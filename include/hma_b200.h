@@ -58,6 +58,16 @@ int hma_gemm_nt(const void* A, long long lda, const void* B, long long ldb, int 
                 void* out, long long ldo, void* out2, long long ldo2, const float* bias, const float* resid,
                 long long ldr, const void* aux, long long ldaux, float alpha, float* colsum, float* rowdot, void* stream);
 
+/* Residual Linear whose epilogue also emits the NEXT stage's pre-norm: out[M,256] (fp32) = resid + alpha * A . B^T + bias and
+ * ln_out[M,256] (bf16) = LayerNorm(out) — ln_mode 1: affine with gamma/beta (norm1 / norm2, st_transformer.py:85-86,112);
+ * ln_mode 2: no affine, (1 + scale) * LN + shift with mod[group] = shift[256] | scale[256] per group of rows_per_group rows
+ * (ModulateLayer, st_mask_git.py:66-76). stats (optional, fp32 [M,2]) = (mean, rstd) per row as hma_ln_bwd reads them.
+ * N must be 256 (a CTA owns whole rows: the statistics never leave the SM). Replaces hma_gemm_nt(RESID) + hma_ln_fwd. */
+int hma_gemm_nt_ln(const void* A, long long lda, const void* B, long long ldb, int M, int N, int K, void* out, long long ldo,
+                   const float* bias, const float* resid, long long ldr, float alpha, int ln_mode, const float* gamma,
+                   const float* beta, const float* mod, int rows_per_group, float eps, void* ln_out, long long ld_ln,
+                   float* stats, void* stream);
+
 /* dW[Mw,Nw] (fp32) += G[tokens,Mw]^T . X[tokens,Nw]; G, X bf16 row-major. The weight gradient of
  * the same Linears. Mw % 128 == 0, Nw % 128 == 0. Accumulates (caller zeroes dW). */
 int hma_gemm_wgrad(const void* G, long long ldg, const void* X, long long ldx, int tokens, int Mw, int Nw,

@@ -153,3 +153,57 @@ def test_gemm_wgrad_grouped_matches_fp32_reference(tokens):
     for (G, X, dW), ref, shp in zip(group, refs, shapes):
         err = (dW - ref).abs().max().item()
         assert err <= 2e-3 * ref.abs().max().item() + 1e-3, (shp, err, ref.abs().max().item())
+
+
+@pytest.mark.parametrize("M,K,mode", [(1300, 256, 1), (1300, 256, 2), (41, 1024, 1), (640, 1024, 2), (40960, 256, 1)])
+def test_gemm_nt_ln_epilogue_emits_the_next_prenorm(M, K, mode):
+    """hma_gemm_nt_ln: the fp32 residual output is bit-identical to the plain residual epilogue, and the bf16 LayerNorm it
+    emits (affine / modulated per row group) plus the (mean, rstd) rows match fp32 torch on that output."""
+    torch.manual_seed(5)
+    N, rpg = 256, 320
+    A = torch.randn(M, K, device="cuda").bfloat16()
+    B = (torch.randn(N, K, device="cuda") * 0.1).bfloat16()
+    bias = torch.randn(N, device="cuda")
+    resid = torch.randn(M, N, device="cuda") * 3 + 0.5
+    gamma, beta = torch.randn(N, device="cuda"), torch.randn(N, device="cuda")
+    groups = (M + rpg - 1) // rpg
+    mod = torch.randn(groups, 2 * N, device="cuda") * 0.3
+    eps = 1e-5 if mode == 1 else 1e-6
+    x = torch.empty(M, N, device="cuda")
+    y = torch.full((M, N), float("nan"), device="cuda").bfloat16()
+    stats = torch.full((M, 2), float("nan"), device="cuda")
+    _lib.call("hma_gemm_nt_ln", A.data_ptr(), K, B.data_ptr(), K, M, N, K, x.data_ptr(), N, _lib.ptr(bias), _lib.ptr(resid), N, 1.0,
+              mode, _lib.ptr(gamma), _lib.ptr(beta), _lib.ptr(mod), rpg, eps, y.data_ptr(), N, _lib.ptr(stats), _lib.current_stream())
+    plain, _ = gemm_nt(A, B, EPI_RESID, bias=bias, resid=resid)
+    assert torch.equal(x, plain)
+    mean = x.mean(-1, keepdim=True)
+    rstd = (x.var(-1, unbiased=False, keepdim=True) + eps).rsqrt()
+    assert torch.allclose(stats[:, :1], mean, rtol=1e-5, atol=1e-5)
+    assert torch.allclose(stats[:, 1:], rstd, rtol=1e-4, atol=1e-6)
+    xh = (x - mean) * rstd
+    if mode == 1:
+        want = xh * gamma + beta
+    else:
+        g = torch.arange(M, device="cuda") // rpg
+        want = xh * (1 + mod[g, N:]) + mod[g, :N]
+    err = (y.float() - want).abs().max().item()
+    assert err <= 2e-2 * want.abs().max().item() and torch.isfinite(y.float()).all(), err
+    # and the separate kernel it replaces rounds to the same bf16 values up to the last place
+    from hma_b200 import ops
+    ref = ops.ln_fwd(x, mode, gamma=gamma, beta=beta, mod=mod, rows_per_group=rpg, eps=eps)
+    assert (y.float() - ref.float()).abs().max().item() <= 4e-2 * want.abs().max().item() / 4
+
+
+def test_gemm_nt_ln_in_place_residual():
+    """Inference writes the stream in place (out == resid)."""
+    torch.manual_seed(6)
+    M, K, N = 700, 256, 256
+    A = torch.randn(M, K, device="cuda").bfloat16()
+    B = (torch.randn(N, K, device="cuda") * 0.1).bfloat16()
+    x0 = torch.randn(M, N, device="cuda")
+    gamma, beta = torch.randn(N, device="cuda"), torch.randn(N, device="cuda")
+    from hma_b200 import ops
+    x_ref, y_ref, _ = ops.gemm_nt_ln(A, B, resid=x0, ln_mode=1, gamma=gamma, beta=beta)
+    x1 = x0.clone()
+    x_out, y, _ = ops.gemm_nt_ln(A, B, resid=x1, out=x1, ln_mode=1, gamma=gamma, beta=beta)
+    assert x_out.data_ptr() == x1.data_ptr() and torch.equal(x1, x_ref) and torch.equal(y, y_ref)

@@ -294,3 +294,31 @@ def test_additive_action_network_vs_oracle(net):
     got = sess.step(x[:, -1], T - 1).float()
     assert (got - want).abs().max() <= 1e-2 * want.abs().max()
     model._sessions.clear()
+
+
+def test_layernorms_emitted_by_the_residual_gemm_epilogue_match_the_rowwise_kernels():
+    """HMA_B200_FUSE_LN path (ops.gemm_nt_ln: norm1 / norm2 / ModulateLayer's LayerNorm out of the preceding residual GEMM's
+    epilogue, row sums exchanged between the two CTAs of a cluster): same forward and backward as the default path with
+    separate row-wise kernels, to the rounding of one-pass vs two-pass variance, and the same fixture tolerances."""
+    rec, cfg, sd = golden()
+    plain, fused = build_cuda_model(rec, sd), build_cuda_model(rec, sd)
+    fused._engine.fuse_ln = True
+    dom = rec["domains"][0]
+    r = rec[dom]
+    outs = []
+    for m in (plain, fused):
+        m.zero_grad(set_to_none=True)
+        out = m(r["input_ids"].cuda(), r["labels"].cuda(), action_ids=r["actions"].cuda(), domain=[dom, dom])
+        out.loss.backward()
+        outs.append(out)
+    a, b = outs
+    assert abs(b.loss.item() - r["loss"].item()) <= 1e-2 * abs(r["loss"].item())
+    assert abs(a.loss.item() - b.loss.item()) <= 2e-3 * abs(a.loss.item())
+    d = (a.logits.float() - b.logits.float()).abs().max().item()
+    assert d <= 1e-2 * a.logits.float().abs().max().item(), d
+    for (k, p), q in zip(plain.named_parameters(), fused.parameters()):
+        if p.grad is None:
+            assert q.grad is None or q.grad.abs().max().item() == 0.0, k
+            continue
+        gn = p.grad.norm().item()
+        assert abs(q.grad.norm().item() - gn) <= 2e-2 * max(gn, 1e-12), k

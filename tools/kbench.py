@@ -54,6 +54,15 @@ def stages():
     st["gemm_fc1_gelu"] = (lambda: ops.gemm_nt(a256, w_fc1, EPI_GELU, out2=z), 2.0 * N * 4 * C * C, "flop")
     st["gemm_fc2_resid"] = (lambda: ops.gemm_nt(a1024, w_fc2, EPI_RESID, resid=x32), 2.0 * N * 4 * C * C, "flop")
     st["gemm_proj_resid"] = (lambda: ops.gemm_nt(a256, w_proj, EPI_RESID, resid=x32), N * C * (2.0 + 4 + 4), "byte")
+    gam, bet = rnd(C, dtype=torch.float32), rnd(C, dtype=torch.float32)
+    mod = rnd(M, 2 * C, dtype=torch.float32, s=0.2)
+    st["gemm_proj_resid_ln1"] = (lambda: ops.gemm_nt_ln(a256, w_proj, resid=x32, ln_mode=1, gamma=gam, beta=bet, want_stats=True),
+                                 N * C * (2.0 + 4 + 4 + 2), "byte")
+    st["gemm_proj_resid_ln2"] = (lambda: ops.gemm_nt_ln(a256, w_proj, resid=x32, ln_mode=2, mod=mod, rows_per_group=n, eps=1e-6,
+                                                        want_stats=True), N * C * (2.0 + 4 + 4 + 2), "byte")
+    st["gemm_fc2_resid_ln1"] = (lambda: ops.gemm_nt_ln(a1024, w_fc2, resid=x32, ln_mode=1, gamma=gam, beta=bet, want_stats=True),
+                                2.0 * N * 4 * C * C, "flop")
+    st["ln_fwd_mode1"] = (lambda: ops.ln_fwd(x32, 1, gamma=gam, beta=bet, want_stats=True), N * C * 6.0, "byte")
     st["gemm_dgelu"] = (lambda: ops.gemm_nt(a256, w_fc2.t().contiguous(), EPI_DGELU, aux=z), 2.0 * N * 4 * C * C, "flop")
     dw = torch.zeros(4 * C, C, device=DEV)
     dw2 = torch.zeros(C, C, device=DEV)

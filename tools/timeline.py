@@ -14,7 +14,7 @@ KERNELS = {
                                     6: "O_ready", 7: "stored", 10: "end", 12: "i:Sa_issued", 13: "i:Pa_seen", 14: "i:PVa+Sb_issued",
                                     15: "i:Pb_seen"}, single=(0, 10, 11)),
     "gemm_nt": dict(single=(0, 10), names={0: "start", 10: "end", 1: "mma:top", 2: "mma:tmem_free", 3: "mma:committed", 4: "epi:top",
-                                           5: "epi:acc_ready", 6: "epi:done"}),
+                                           5: "epi:acc_ready", 6: "epi:done", 7: "ln:sent", 8: "ln:wait", 9: "ln:got", 11: "ln:done"}),
     "gemm_wgrad": dict(single=(0, 3, 4, 5), names={0: "start", 3: "mma_done", 4: "red_issued", 5: "end", 1: "tma_issued", 2: "full"}),
     "attn_spatial_bwd": dict(names={0: "start", 11: "loaded", 1: "SdP_issued", 5: "A0:P", 6: "A3:P", 7: "A4:P", 8: "A7:P",
                                     12: "B8:dS", 13: "B9:dS", 14: "B12:dS", 15: "B15:dS",
@@ -46,6 +46,11 @@ def run_gemm_nt():
     bias = torch.randn(N, device="cuda")
     outs = [torch.empty(M, N, device="cuda", dtype=torch.float32 if epi == 3 else torch.bfloat16) for _ in range(2)]
     out2 = [torch.empty(M, N, device="cuda", dtype=torch.bfloat16) for _ in range(2)]
+    if os.environ.get("LN"):
+        gam, bet = torch.randn(N, device="cuda"), torch.randn(N, device="cuda")
+        for i in range(4):
+            ops.gemm_nt_ln(As[i], W, resid=outs[(i + 1) % 2], out=outs[i % 2], bias=bias, ln_mode=1, gamma=gam, beta=bet, want_stats=True)
+        return
     for i in range(4):
         ops.gemm_nt(As[i], W, epi, out=outs[i % 2], bias=bias, out2=out2[i % 2] if epi == 1 else None,
                     aux=out2[i % 2] if epi == 2 else None, resid=outs[(i + 1) % 2] if epi == 3 else None)
