@@ -358,10 +358,13 @@ attn_spatial_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
           auto exp_chunk = [&](const uint32_t (&sv)[32], int c) {
             if (rows_live && half * 64 + c * 32 < nk) {
               uint32_t pk[16];
+              const f32x2 sc2 = dup2(p.scale_log2), nl2 = dup2(-L);
 #pragma unroll
-              for (int j = 0; j < 32; j += 2)
-                pk[j >> 1] = pack_bf16(fast_ex2(fmaf(__uint_as_float(sv[j]), p.scale_log2, -L)),
-                                       fast_ex2(fmaf(__uint_as_float(sv[j + 1]), p.scale_log2, -L)));
+              for (int j = 0; j < 32; j += 2) {  // one packed FFMA2 per two scores (issue slots are what this stage is short of)
+                float a, b;
+                upk2(fma2(pk2(__uint_as_float(sv[j]), __uint_as_float(sv[j + 1])), sc2, nl2), a, b);
+                pk[j >> 1] = pack_bf16(fast_ex2(a), fast_ex2(b));
+              }
 #pragma unroll
               for (int q = 0; q < 4; ++q) {
                 const uint32_t off = sw128_offset((uint32_t)row, (uint32_t)(c * 32 + q * 8));
@@ -403,7 +406,7 @@ attn_spatial_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
           mbar_wait(smem_u32(&bar_p[bsel]), (uint32_t)((it >> 1) & 1));  // P of this pair is in shared memory
           const int qi = qt * 128 + row;
           const float delta = qi < n ? s_delta[qi] : 0.f;
-          const float nds = -delta * p.scale;
+          const f32x2 sc2 = dup2(p.scale), nds2 = dup2(-delta * p.scale);
           const bool rows_live = quarter * 32 < min(128, n - qt * 128);
           const uint32_t sP = sP0 + (uint32_t)bsel * kPdsBuf + pan;
           const uint32_t sDS = sP + 2 * kBPanel;
@@ -425,11 +428,10 @@ attn_spatial_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
                              : "r"(sP + off) : "memory");
                 uint32_t dk[4];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
+                for (int j = 0; j < 4; ++j) {  // dS = P * (scale * dP - scale * delta), two elements per instruction
                   const int e = q * 8 + 2 * j;
-                  const float d0 = bf16_lo(pk[j]) * fmaf(__uint_as_float(dp[e]), p.scale, nds);
-                  const float d1 = bf16_hi(pk[j]) * fmaf(__uint_as_float(dp[e + 1]), p.scale, nds);
-                  dk[j] = pack_bf16(d0, d1);
+                  const f32x2 t = fma2(pk2(__uint_as_float(dp[e]), __uint_as_float(dp[e + 1])), sc2, nds2);
+                  dk[j] = pack_bf16(mul2(pk2(bf16_lo(pk[j]), bf16_hi(pk[j])), t));
                 }
                 asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sDS + off), "r"(dk[0]), "r"(dk[1]), "r"(dk[2]), "r"(dk[3]) : "memory");
               }
