@@ -723,6 +723,12 @@ template <int EPI>
 static int dispatch_nt(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmNtParams& p, int bn,
                        cudaStream_t stream) {
   const int KB = p.K / kBK;
+  if constexpr (EpiWarps<EPI>::value == 8) {  // 64-wide tiles: one 32-column chunk per epilogue warp
+    if (bn == 64) {
+      const bool stat = smem_need<64, EPI>(KB, true, 2) <= (size_t)kSmemLimit;
+      return stat ? launch_nt<64, EPI, true>(tmA, tmB, p, stream) : launch_nt<64, EPI, false>(tmA, tmB, p, stream);
+    }
+  }
   if (bn == 256) {
     const bool stat = smem_need<256, EPI>(KB, true, 2) <= (size_t)kSmemLimit;
     return stat ? launch_nt<256, EPI, true>(tmA, tmB, p, stream) : launch_nt<256, EPI, false>(tmA, tmB, p, stream);
@@ -752,6 +758,12 @@ static int gemm_nt_impl(const void* A, long long lda, const void* B, long long l
   if (bn == 256 && (long long)((M + kBM - 1) / kBM) * (N / 256) * 2 <= hma_host::sm_count()) bn = 128;
   // dGELU: the epilogue (3 loads, 2 MUFU ops, ~16 instructions per element) is latency-bound with two warps per scheduler;
   // sixteen epilogue warps need their fp32 staging buffers (74 KB), which only fits beside a stationary B with 128-wide tiles
+  // Very few rows (the diffusion sampler's <= 512-row GEMMs, the one-frame decode passes at small batch): even 128-wide tiles
+  // leave most SMs idle and every CTA's k-loop (K = 1024: 16 k-blocks) is a latency chain, so go to 64-wide tiles — 4x the
+  // CTAs of the 256-wide choice, each streaming 24 KB instead of 48 KB per k-block and issuing N = 64 MMAs (49 vs 127 cycles).
+  if (bn == 128 && conv_cin == 0 && (epi == HMA_EPI_BF16 || epi == HMA_EPI_RESID_F32 || epi == HMA_EPI_SILU_BF16) &&
+      (long long)((M + kBM - 1) / kBM) * (N / 128) * 2 <= hma_host::sm_count())
+    bn = 64;
   if (ln != nullptr) bn = 128;
   if (epi == HMA_EPI_DGELU_BF16) bn = 128;  // (the same change for the forward GELU epilogue measured worse: 52.7 vs 50.3 us)
   CUtensorMap tmA, tmB;
