@@ -17,8 +17,12 @@
 // through a per-warp padded shared-memory buffer, and residual / saved-activation reads and all
 // stores are issued in the transposed domain, where a warp instruction touches whole 64/128-byte
 // row segments.
+//
+// Tile width BN: 256 for N >= 512, 128 otherwise, 64 when the launch has so few row tiles that wider tiles would leave most
+// SMs idle (sampler / small-batch decode shapes). Element-wise epilogue arithmetic works on packed fp32 pairs (FFMA2).
+// LN = true (hma_gemm_nt_ln): the residual epilogue also emits the next stage's LayerNorm; the two 128-column CTAs of a row
+// tile form a thread-block cluster and exchange their halves of the row sums through distributed shared memory.
 #include <cstdio>
-#include <cstdlib>
 #include <cstdlib>
 #include "common.cuh"
 #include "../../include/hma_b200.h"
