@@ -46,6 +46,10 @@ def stages():
     out_t, _ = ops.attn_temporal_fwd(qkv, B, T, n, H, SCALE)
     st["attn_temporal_fwd"] = (lambda: ops.attn_temporal_fwd(qkv, B, T, n, H, SCALE), N * C * 2.0 * 4, "byte")
     st["attn_temporal_bwd"] = (lambda: ops.attn_temporal_bwd(qkv, out_t, dout, None, B, T, n, H, SCALE), N * C * 2.0 * 7, "byte")
+    rows_dec = 64 * n  # one frame of a batch-64 decode pass against 11 cached frames (the mean of config 3)
+    kv = rnd(16, rows_dec, 2 * C)
+    qkv_dec = rnd(rows_dec, 3 * C)
+    st["attn_temporal_cached"] = (lambda: ops.attn_temporal_cached(qkv_dec, kv, 11, H, SCALE), rows_dec * C * 2.0 * (2 * 11 + 4), "byte")
     a256, a1024 = rnd(N, C), rnd(N, 4 * C)
     w_qkv, w_fc1, w_fc2, w_proj = rnd(3 * C, C, s=0.05), rnd(4 * C, C, s=0.05), rnd(C, 4 * C, s=0.05), rnd(C, C, s=0.05)
     x32 = rnd(N, C, dtype=torch.float32)
