@@ -125,7 +125,7 @@ class Tables:
 
 
 def _ex(arr: np.ndarray, t: Tensor) -> Tensor:  # gaussian_diffusion.py:817-829
-    return torch.from_numpy(arr)[t].float()[:, None]
+    return torch.from_numpy(arr).to(t.device)[t].float()[:, None]  # (device-aware: the checker also runs on the GPU)
 
 
 # --------------------------------------------------------------------------------------------
@@ -133,7 +133,7 @@ def _ex(arr: np.ndarray, t: Tensor) -> Tensor:  # gaussian_diffusion.py:817-829
 # --------------------------------------------------------------------------------------------
 def timestep_embedding(t: Tensor, dim: int = 256, max_period: int = 10000) -> Tensor:  # diffloss.py:80-100
     half = dim // 2
-    freqs = torch.exp(-math.log(max_period) * torch.arange(half, dtype=torch.float32) / half)
+    freqs = torch.exp(-math.log(max_period) * torch.arange(half, dtype=torch.float32, device=t.device) / half)
     args = t[:, None].float() * freqs[None]
     return torch.cat([torch.cos(args), torch.sin(args)], dim=-1)
 
@@ -199,7 +199,7 @@ def diffloss_forward(z: Tensor, target: Tensor, mask: Optional[Tensor], t: Tenso
                      tb: Tables, prefix: str = "diffloss.net.") -> Tensor:
     """diffloss.py:28-35."""
     x_t = _ex(tb.sqrt_acp, t) * target + _ex(tb.sqrt_1m_acp, t) * noise
-    tm = torch.tensor(tb.timestep_map)[t]  # respace.py:112-117 (identity for the training diffusion)
+    tm = torch.tensor(tb.timestep_map, device=t.device)[t]  # respace.py:112-117 (identity for the training diffusion)
     out = mlp_adaln(x_t, tm, z, sd, prefix, cfg.diffloss_d)
     rows = diffusion_row_losses(out, target, noise, t, tb)
     if mask is not None:
