@@ -432,5 +432,33 @@ def test_config4_mar_training_step_matches_fp32_oracle_full_size():
               f"{worst:.2e} ({worst_k})")
         assert checked >= 32 * 18
         worst_all = max(worst_all, worst)
+    # ---- the sampler's network at its real depth and 512 rows: eps-hat | learned-variance channel of single ancestral steps
+    # (early, middle, late, last) against the oracle's SimpleMLPAdaLN on the same x_t, timestep and condition, within 1e-2 of
+    # the output range (everything after it in p_sample is closed-form fp32 arithmetic, tests/test_mar_gpu.py)
+    from hma_b200 import ops
+    from hma_b200.mar import KPAD
+    m.zero_grad(set_to_none=True)
+    m.eval()
+    dev = torch.device("cuda")
+    eng, p = m._engine, m._inference_params()
+    eng.prepare_diffloss(p, False)
+    n, D = 512, 16
+    zs = torch.randn(n, 256, generator=g).cuda()
+    x_t = (torch.randn(n, D, generator=g) * 2).cuda()
+    tb = M.Tables(cfg.num_sampling_steps)
+    te_tab = eng.time_table(p, cfg.num_sampling_steps, dev)
+    c = eng.sample_cond(p, zs.bfloat16())
+    sdp = {k: v.detach() for k, v in m.state_dict().items()}
+    x16 = ops.mar_q_sample(x_t, None, None, None, KPAD)
+    worst_net = 0.0
+    for i in (tb.num_timesteps - 1, 75, 50, 25, 3, 0):
+        with torch.no_grad():
+            ref = M.mlp_adaln(x_t, torch.full((n,), tb.timestep_map[i], dtype=torch.long, device=dev), zs.bfloat16().float(), sdp,
+                              "diffloss.net.", cfg.diffloss_d)
+        got = eng._mlp(p, x16, ops.mar_silu_fwd(c, te_tab[i]), None)[:, : 2 * D].float()
+        e = ((got - ref).abs().max() / ref.abs().max()).item()
+        worst_net = max(worst_net, e)
+        assert e <= 1e-2, (i, e)
+    print(f"[fullsize HMA-MAR sampler network, depth {cfg.diffloss_d}, {n} rows] worst |d| / range over 6 spaced steps: {worst_net:.2e}")
     del m
     torch.cuda.empty_cache()
