@@ -43,7 +43,7 @@ _SIGNATURES = {
                               c_int, c_int, c_float, c_void_p, c_ll, c_void_p],
     "hma_kv_cache_append": [c_void_p, c_ll, c_int, c_int, c_int, c_int, c_int, c_void_p, c_ll, c_int, c_void_p],
     "hma_attn_temporal_cached": [c_void_p, c_ll, c_int, c_int, c_int, c_void_p, c_ll, c_int, c_int, c_int, c_float,
-                                 c_void_p, c_ll, c_void_p],
+                                 c_void_p, c_ll, c_int, c_int, c_void_p],
     "hma_qk_norm_fwd": [c_void_p, c_ll, c_int, c_fp, c_fp, c_float, c_void_p, c_ll, c_void_p],
     "hma_qk_norm_bwd": [c_void_p, c_ll, c_int, c_fp, c_float, c_void_p, c_ll, c_fp, c_fp, c_void_p],
     "hma_ln_fwd": [c_fp, c_ll, c_int, c_int, c_fp, c_fp, c_fp, c_int, c_float, c_void_p, c_ll, c_fp, c_int, c_int,

@@ -8,6 +8,9 @@
 // and a decode step only runs the ONE frame being generated through the network. This kernel is the
 // temporal attention of that frame: the query of token (b, s) attends to the cached K/V of the same
 // slot in frames [0, n_prev) plus its own K/V (causal "<=").
+// A pass may also carry `frames` consecutive window frames per sample ((b, f, s) row order; their K/V are appended to the
+// cache BEFORE this kernel runs): frame f then attends to cache frames [0, n_prev + f) plus itself — how a finished frame
+// (f = 0) is committed in the same pass that runs the first MaskGIT step of the next one (f = 1).
 //
 // HBM-bound by the cache read (n_prev * 1 KB per token), so it runs on the CUDA cores: one warp per
 // token, lane l owns channels [8l, 8l+8) of all 8 heads' 256 channels (head = l / 4), every K/V row
@@ -26,8 +29,9 @@ struct TemporalCachedParams {
   int q_col, k_col, v_col;
   const __nv_bfloat16* kv;   // cache base
   long long frame_stride;    // elements between consecutive frames of the cache
-  int rows;                  // B * n tokens of the frame
-  int n_prev;                // cached frames to attend to
+  int rows;                  // B * frames * n tokens of the pass
+  int n_prev;                // cached frames the first frame of the pass attends to
+  int frames, n;             // frames per sample in this pass; tokens per frame
   float scale_log2;
   __nv_bfloat16* out;        // [rows, ldo]
   long long ldo;
@@ -79,9 +83,16 @@ __global__ void __launch_bounds__(256) attn_temporal_cached_kernel(const Tempora
     m = mn;
   };
 
-  const __nv_bfloat16* base = p.kv + row * (2 * kTC) + lane * 8;
+  long long crow = row;  // row of this token's slot in a cache frame: b * n + s
+  int n_prev = p.n_prev;
+  if (p.frames > 1) {
+    const long long bf = row / p.n;
+    crow = (bf / p.frames) * p.n + (row - bf * p.n);
+    n_prev += (int)(bf % p.frames);
+  }
+  const __nv_bfloat16* base = p.kv + crow * (2 * kTC) + lane * 8;
   int f = 0;
-  for (; f + 4 <= p.n_prev; f += 4) {  // four frames of loads in flight per lane
+  for (; f + 4 <= n_prev; f += 4) {  // four frames of loads in flight per lane
     uint4 ku[4], vu[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
@@ -92,7 +103,7 @@ __global__ void __launch_bounds__(256) attn_temporal_cached_kernel(const Tempora
 #pragma unroll
     for (int u = 0; u < 4; ++u) fold(ku[u], vu[u]);
   }
-  for (; f < p.n_prev; ++f) {
+  for (; f < n_prev; ++f) {
     const __nv_bfloat16* r = base + (long long)f * p.frame_stride;
     fold(__ldg(reinterpret_cast<const uint4*>(r)), __ldg(reinterpret_cast<const uint4*>(r + kTC)));
   }
@@ -136,7 +147,7 @@ __global__ void __launch_bounds__(256) kv_append_kernel(const KvAppendParams p) 
 
 extern "C" int hma_attn_temporal_cached(const void* qkv, long long ld_qkv, int q_col, int k_col, int v_col, const void* kv,
                                         long long frame_stride, int rows, int n_prev, int heads, float scale, void* out,
-                                        long long ldo, void* stream_) {
+                                        long long ldo, int frames, int n, void* stream_) {
   using namespace hma;
   if (rows == 0) return 0;
   HMA_REQUIRE(heads == 8, "attn_temporal_cached: built for 8 heads of 32 channels (got %d heads)", heads);
@@ -148,6 +159,9 @@ extern "C" int hma_attn_temporal_cached(const void* qkv, long long ld_qkv, int q
   p.q_col = q_col; p.k_col = k_col; p.v_col = v_col;
   p.kv = static_cast<const __nv_bfloat16*>(kv); p.frame_stride = frame_stride;
   p.rows = rows; p.n_prev = n_prev;
+  HMA_REQUIRE(frames >= 1 && (frames == 1 || (n > 0 && rows % (frames * n) == 0)),
+              "attn_temporal_cached: rows=%d is not a whole number of %d-frame samples of %d tokens", rows, frames, n);
+  p.frames = frames; p.n = n > 0 ? n : 1;
   p.scale_log2 = scale * 1.4426950408889634f;
   p.out = static_cast<__nv_bfloat16*>(out); p.ldo = ldo;
   HMA_CHECK_CUDA(hma_host::launch_pdl(attn_temporal_cached_kernel, dim3((rows + 7) / 8), dim3(256), 0,

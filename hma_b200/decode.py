@@ -7,7 +7,10 @@ spatial attention per-frame, they influence frame `out_t` only through their tem
 A `DecodeSession` therefore
   * runs the context frames through the network ONCE ("prefill"), keeping every layer's temporal K/V;
   * runs only the frame being generated for each MaskGIT step ("step": 1/T of the reference's work);
-  * runs a finished frame once more to add its K/V to the cache before the next frame ("commit").
+  * runs a finished frame once more to add its K/V to the cache before the next frame ("commit") — together with the
+    first MaskGIT step of that next frame, whose input (a fully masked frame) is known in advance ("commit_step": one
+    pass over two frames instead of two passes over one; the logits wait in the session until `step(first=True)`);
+  * likewise the prefill can carry the frame to generate as one more, fully masked, frame ("prefill_step").
 Same logits as the full-window recompute up to bf16 summation order (tests/test_decode_gpu.py).
 
 A one-frame pass is ~450 launches of a few microseconds each, i.e. CPU-launch-bound, so each
@@ -37,12 +40,20 @@ class DecodeSession:
         n, L = self.d1.n, cfg.num_layers
         self.kv = torch.zeros(L, T, B * n, 512, device=device, dtype=torch.bfloat16)
         self.ids = torch.zeros(B, 1, S, device=device, dtype=torch.long)
+        self.d2 = self.eng.dims(B, 2, S, dom is not None)
+        self.ids2 = torch.zeros(B, 2, S, device=device, dtype=torch.long)
+        self.mask_id = cfg.image_vocab_size
+        self.first_logits: Optional[torch.Tensor] = None  # logits of the first MaskGIT step of frame `first_t`, computed
+        self.first_t = -1                                 # by the pass that committed the frame before it
+        self.act2 = self.mods2 = None
         self.act_tb = self.hmods_tb = self.mods_tb = None
         if dom is not None:
             self.act_tb = torch.zeros(T * B, 256, device=device, dtype=torch.float32)
             if self.d1.modulate:
                 self.hmods_tb = torch.zeros(L, T * B, 256, device=device, dtype=torch.bfloat16)
                 self.mods_tb = torch.zeros(L, T * B, 512, device=device, dtype=torch.float32)
+                self.mods2 = torch.zeros(L, B * 2, 512, device=device, dtype=torch.float32)
+            self.act2 = torch.zeros(B * 2, 256, device=device, dtype=torch.float32)
         self.graphs: Dict[Tuple[int, str], torch.cuda.CUDAGraph] = {}
         self.outputs: Dict[Tuple[int, str], Optional[torch.Tensor]] = {}
         self.warm = set()
@@ -108,6 +119,18 @@ class DecodeSession:
                     rec["actions"].copy_(actions)
             rec["graph"].replay()
         self.filled = n_ctx
+        self.first_t = -1
+
+    def _cond2(self, t: int):
+        """Action conditioning of frames t, t + 1 in (b, t) row order (the tables are (t, b)); static buffers."""
+        if self.dom is None:
+            return None
+        B = self.B
+        self.act2.view(B, 2, 256).copy_(self.act_tb[t * B:(t + 2) * B].view(2, B, 256).transpose(0, 1))
+        if self.mods2 is not None:
+            L = self.mods2.shape[0]
+            self.mods2.view(L, B, 2, 512).copy_(self.mods_tb[:, t * B:(t + 2) * B].view(L, 2, B, 512).transpose(1, 2))
+        return (self.act2, self.mods2)
 
     def _cond(self, t: int):
         if self.dom is None:
@@ -118,13 +141,21 @@ class DecodeSession:
         return (act, mods)
 
     def _run(self, t: int, mode: str):
+        if mode == "commit_step":
+            logits, _ = self.eng.forward(self._p, self.ids2, None, self.dom, self.d2, False, t0=t, kv=self.kv, mode=mode,
+                                         frame_cond=self._cond2(t))
+            return logits
         logits, _ = self.eng.forward(self._p, self.ids, None, self.dom, self.d1, False, t0=t, kv=self.kv, mode=mode,
                                      frame_cond=self._cond(t))
         return logits
 
     def _pass(self, frame_ids: torch.Tensor, t: int, mode: str) -> Optional[torch.Tensor]:
         assert t == self.filled, f"decode session holds {self.filled} frames of context, asked for frame {t}"
-        self.ids.copy_(frame_ids.reshape(self.B, 1, self.S))
+        if mode == "commit_step":
+            self.ids2[:, 0].copy_(frame_ids.reshape(self.B, self.S))
+            self.ids2[:, 1].fill_(self.mask_id)
+        else:
+            self.ids.copy_(frame_ids.reshape(self.B, 1, self.S))
         key = (t, mode)
         if not self.use_graphs:
             return self._run(t, mode)
@@ -144,11 +175,23 @@ class DecodeSession:
         g.replay()
         return self.outputs[key]
 
-    def step(self, frame_ids: torch.Tensor, t: int) -> torch.Tensor:
-        """Logits fp32 [B*S, nv*vs] of window frame t given the cached context (valid until the next pass)."""
+    def step(self, frame_ids: torch.Tensor, t: int, first: bool = False) -> torch.Tensor:
+        """Logits fp32 [B*S, nv*vs] of window frame t given the cached context (valid until the next pass). `first`: this
+        is the first MaskGIT step of the frame, i.e. `frame_ids` is fully masked — then the logits the previous frame's
+        commit pass already produced are returned without another pass."""
+        if first and self.first_t == t and self.first_logits is not None:
+            self.first_t = -1
+            return self.first_logits
+        self.first_t = -1
         return self._pass(frame_ids, t, "step")
 
-    def commit(self, frame_ids: torch.Tensor, t: int) -> None:
-        """Add finished frame t to the context."""
-        self._pass(frame_ids, t, "commit")
+    def commit(self, frame_ids: torch.Tensor, t: int, prefetch_next: bool = False) -> None:
+        """Add finished frame t to the context. `prefetch_next`: the same pass also runs frame t + 1 as a fully masked frame
+        and keeps its logits for `step(..., first=True)`."""
+        if prefetch_next and t + 1 < self.T:
+            self.first_logits = self._pass(frame_ids, t, "commit_step")
+            self.first_t = t + 1
+        else:
+            self._pass(frame_ids, t, "commit")
+            self.first_t = -1
         self.filled = t + 1

@@ -257,14 +257,20 @@ class Engine:
           mode "step"   : T == 1, the frame is window frame t0; temporal attention reads cache frames [0, t0).
           mode "commit" : as "step", but appends this frame's K/V to the cache and skips everything after
                           the last layer's temporal K/V (no logits).
-        `frame_cond` (step/commit): precomputed (act fp32 [B,256] or None, mods fp32 [L,B,512] or None) of the frame,
-        replacing the action stem + adaLN chain. `actions`, if given, must hold exactly the T frames computed.
+          mode "commit_step": T == 2 = a finished frame t0 and the (still fully masked) frame t0 + 1 in ONE pass: frame t0's
+                          K/V join the cache layer by layer and frame t0 + 1 attends to them, so the pass both commits t0 and
+                          returns the logits of t0 + 1's first MaskGIT step — two passes of B*n rows become one of 2*B*n.
+          mode "prefill_step": as "prefill", but the last of the T frames is the (fully masked) frame to generate: no early
+                          exit, and the logits of that frame are returned (the reference's first full-window step).
+        `frame_cond` (step/commit/commit_step): precomputed (act fp32 [B*T,256] or None, mods fp32 [L,B*T,512] or None) of the
+        frame(s) in (b, t) row order, replacing the action stem + adaLN chain. `actions`, if given, must hold exactly the T
+        frames computed. With commit_step / prefill_step the logits cover the LAST frame only: fp32 [B*S, nv*vs].
 
         Other front ends / heads over the same trunk (STMAR, mar.py): `front(act)` returns the fp32 residual stream
         [B*T*n, 256] in place of the token embedding (`ids` is then ignored); `head=False` returns the trunk output
         instead of logits. `drop = (p, seed, seed_dev)`: nn.Dropout(p) after the GELU and after fc2
         (st_transformer.py:24-27; training only); seed_dev is an optional device u64 mixed into the seed at run time."""
-        assert mode in ("full", "prefill", "step", "commit")
+        assert mode in ("full", "prefill", "step", "commit", "commit_step", "prefill_step")
         assert mode == "full" or (not training and kv is not None)
         W = self.weights
         has_act = actions is not None or frame_cond is not None
@@ -274,7 +280,7 @@ class Engine:
         B, T, S, n, M, N = d.B, d.T, d.S, d.n, d.M, d.N
         act = c_bf = None
         if frame_cond is not None:
-            assert mode in ("step", "commit") and T == 1
+            assert (mode in ("step", "commit") and T == 1) or (mode == "commit_step" and T == 2)
             act = frame_cond[0]
         elif actions is not None:
             a2d = actions.reshape(M, -1).to(torch.float32).contiguous()
@@ -366,11 +372,17 @@ class Engine:
             if mode in ("step", "commit"):
                 lse_t = None
                 att_t = ops.attn_temporal_cached(qkv_t, kv[i], t0, d.heads, d.scale)
+            elif mode == "commit_step":
+                # both frames' K/V go to the cache first (frame t0 + 1's are provisional: its own commit overwrites them),
+                # then frame f of the pass attends to cache frames [0, t0 + f) and to itself
+                lse_t = None
+                ops.kv_cache_append(qkv_t, B, T, n, kv[i], t0)
+                att_t = ops.attn_temporal_cached(qkv_t, kv[i], t0, d.heads, d.scale, frames=T, n=n)
             else:
                 att_t, lse_t = ops.attn_temporal_fwd(qkv_t, B, T, n, d.heads, d.scale, want_lse=False)  # bwd recomputes the rows
-            if mode in ("prefill", "commit"):
+            if mode in ("prefill", "commit", "prefill_step"):
                 ops.kv_cache_append(qkv_t, B, T, n, kv[i], t0)
-                if i == d.num_layers - 1:
+                if i == d.num_layers - 1 and mode != "prefill_step":
                     return None, None  # nothing downstream of the last layer's K/V is needed
             # ---- MLP, pre-norm, erf-GELU (st_transformer.py:24-27,112); norm2 comes out of the temporal projection
             if fuse_ln:
@@ -405,7 +417,10 @@ class Engine:
                 layers.append(L)
             x = x4
         # ---- head on the video tokens only (st_mask_git.py:681-683)
-        ah = ops.ln_fwd(x, 0, rows=M * S, src_group=n, dst_group=S) if d.A else ops.ln_fwd(x, 0)
+        if mode in ("commit_step", "prefill_step"):  # the last frame of every sample only: row (b, T-1, s) of (b, t, s)
+            ah = ops.ln_fwd(x[(T - 1) * n:], 0, rows=B * S, src_group=T * n, dst_group=S)
+        else:
+            ah = ops.ln_fwd(x, 0, rows=M * S, src_group=n, dst_group=S) if d.A else ops.ln_fwd(x, 0)
         logits = ops.gemm_nt(ah, Wp["out_x_proj.weight"], EPI_RESID, bias=p["out_x_proj.bias"], alpha=d.readout_alpha)
         if training:
             sv.update(layers=layers, ah=ah, ids=ids, dom=dom, dims=d, pos_n=pos_n, has_actions=actions is not None,

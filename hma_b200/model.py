@@ -446,7 +446,9 @@ class STMaskGIT(nn.Module, PyTorchModelHubMixin):
             session = self._decode_session(prompt_THW, out_t, action_ids, domain, kwargs)
         for step in range(maskgit_steps):
             if session is not None:
-                logits = session.step(frame, out_t)  # only frame out_t runs; context comes from the K/V cache
+                # only frame out_t runs; context comes from the K/V cache (and the first step's logits from the pass that
+                # committed the previous frame, when generate() asked for them)
+                logits = session.step(frame, out_t, first=step == 0)
                 lf = logits.view(B, S, nv * vs)
             else:
                 logits, _ = self._logits_nograd(prompt_THW, action_ids, domain, kwargs)
@@ -501,7 +503,8 @@ class STMaskGIT(nn.Module, PyTorchModelHubMixin):
             full[:, t] = sample_HW
             all_logits.append(fl)
             if session is not None and t != last:
-                session.commit(full[:, t], t)  # the finished frame joins the context of the next one
+                # the finished frame joins the context of the next one; the same pass runs the next frame's first step
+                session.commit(full[:, t], t, prefetch_next=True)
         tokens = full.reshape(B, -1)
         if return_logits:
             return tokens, torch.stack(all_logits, dim=3)

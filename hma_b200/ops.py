@@ -313,14 +313,17 @@ def kv_cache_append(qkv: torch.Tensor, B: int, frames: int, n: int, kv: torch.Te
           B, frames, n, kv.data_ptr(), kv.stride(0), t0, _s())
 
 
-def attn_temporal_cached(qkv: torch.Tensor, kv: Optional[torch.Tensor], n_prev: int, heads: int, scale: float) -> torch.Tensor:
-    """Temporal attention of ONE frame ([B*n, 768] q|k|v) over cache frames [0, n_prev) + itself."""
+def attn_temporal_cached(qkv: torch.Tensor, kv: Optional[torch.Tensor], n_prev: int, heads: int, scale: float,
+                         frames: int = 1, n: int = 0) -> torch.Tensor:
+    """Temporal attention of a pass of `frames` window frames per sample ([B*frames*n, 768] q|k|v, (b, f, s) order): frame f
+    attends to cache frames [0, n_prev + f) + itself (the pass has appended its own frames to the cache already)."""
     C = heads * 32
     rows = qkv.shape[0]
     out = torch.empty(rows, C, device=qkv.device, dtype=BF16)
-    _call("attn_temporal_cached", rows * C * 2.0 * (2 * n_prev + 4), "hma_attn_temporal_cached", qkv.data_ptr(), qkv.stride(0),
-          0, C, 2 * C, _p(kv) if n_prev else None, kv.stride(0) if kv is not None else 0, rows, n_prev, heads, float(scale),
-          out.data_ptr(), C, _s())
+    reads = n_prev + (frames - 1) / 2.0
+    _call("attn_temporal_cached", rows * C * 2.0 * (2 * reads + 4), "hma_attn_temporal_cached", qkv.data_ptr(), qkv.stride(0),
+          0, C, 2 * C, _p(kv) if (n_prev or frames > 1) else None, kv.stride(0) if kv is not None else 0, rows, n_prev, heads,
+          float(scale), out.data_ptr(), C, frames, n, _s())
     return out
 
 

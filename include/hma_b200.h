@@ -112,13 +112,14 @@ int hma_attn_temporal_bwd(const void* qkv, long long ld_qkv, const void* out, lo
  * the frames that cannot change; same results because st_transformer.py:111 is causal).
  * kv cache: bf16, frame f at kv + f*frame_stride, token (b, s) at row b*n + s of [B*n, 512] = K | V.
  * hma_kv_cache_append copies the K/V columns of `frames` frames of a (b, t, s)-ordered qkv matrix into
- * cache frames [t0, t0+frames). hma_attn_temporal_cached: qkv holds ONE frame ([rows = B*n, ld_qkv]);
- * each token attends to the cached K/V of its slot in frames [0, n_prev) and to its own K/V. 8 heads x 32. */
+ * cache frames [t0, t0+frames). hma_attn_temporal_cached: qkv holds `frames` consecutive window frames per sample
+ * ([rows = B*frames*n, ld_qkv], (b, f, s) order; frames = 1 for an ordinary one-frame pass); the token of frame f attends to
+ * the cached K/V of its slot in frames [0, n_prev + f) and to its own K/V (the pass appends its frames first). 8 heads x 32. */
 int hma_kv_cache_append(const void* qkv, long long ld_qkv, int k_col, int v_col, int B, int frames, int n, void* kv,
                         long long frame_stride, int t0, void* stream);
 int hma_attn_temporal_cached(const void* qkv, long long ld_qkv, int q_col, int k_col, int v_col, const void* kv,
                              long long frame_stride, int rows, int n_prev, int heads, float scale, void* out,
-                             long long ldo, void* stream);
+                             long long ldo, int frames, int n, void* stream);
 
 /* Per-head LayerNorm of q and k (qk_norm=True, attention.py:32-35,47-52): out = [LN32(q) | LN32(k) | v] from the bf16
  * projection output qkv [rows, >= 768]; one affine LayerNorm(32, eps) shared by all heads of q and k. The backward

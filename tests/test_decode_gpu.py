@@ -170,3 +170,62 @@ def test_interactive_sliding_window_graph_prefill_matches_eager(setup):
     finally:
         model.decode_cuda_graphs = True
         model._sessions.clear()
+
+
+def test_attn_temporal_cached_two_frames_per_sample():
+    """frames = 2: rows in (b, f, s) order; frame f attends to cache frames [0, n_prev + f) (the pass appended both of its
+    frames first) and to itself — exactly what two one-frame passes with a commit in between compute."""
+    from hma_b200 import ops
+    torch.manual_seed(4)
+    B, n, Tc, C = 3, 40, 5, 256
+    rows = B * n
+    qkv_all = (torch.randn(B, Tc + 2, n, 3 * C, device="cuda") * 0.7).to(torch.bfloat16)
+    kv = torch.zeros(Tc + 2, rows, 2 * C, device="cuda", dtype=torch.bfloat16)
+    ops.kv_cache_append(qkv_all[:, :Tc].contiguous().view(-1, 3 * C), B, Tc, n, kv, 0)
+    scale = 32 ** -0.5
+    # reference: one-frame passes
+    fa = qkv_all[:, Tc].contiguous().view(rows, 3 * C)
+    fb = qkv_all[:, Tc + 1].contiguous().view(rows, 3 * C)
+    kv_ref = kv.clone()
+    out_a = ops.attn_temporal_cached(fa, kv_ref, Tc, 8, scale)
+    ops.kv_cache_append(fa, B, 1, n, kv_ref, Tc)
+    out_b = ops.attn_temporal_cached(fb, kv_ref, Tc + 1, 8, scale)
+    # one two-frame pass
+    both = qkv_all[:, Tc:Tc + 2].contiguous().view(2 * rows, 3 * C)
+    ops.kv_cache_append(both, B, 2, n, kv, Tc)
+    out = ops.attn_temporal_cached(both, kv, Tc, 8, scale, frames=2, n=n).view(B, 2, n, C)
+    assert torch.equal(out[:, 0].reshape(rows, C), out_a)
+    assert torch.equal(out[:, 1].reshape(rows, C), out_b)
+    assert torch.equal(kv[:Tc + 1], kv_ref[:Tc + 1])
+
+
+def test_commit_and_first_step_in_one_pass_equal_two_passes(setup):
+    """DecodeSession.commit(prefetch_next=True): the finished frame's K/V and the next frame's first-step logits from ONE
+    two-frame pass are bit-identical to commit() followed by step() (every kernel on the path computes a row from that
+    row's operands only, in an order that does not depend on how many rows the launch has)."""
+    rec, cfg, sd, model = setup
+    dom = rec["domains"][0]
+    r = rec[dom]
+    B, T, S = 2, cfg.T, 256
+    acts = r["actions"].cuda()
+    g = torch.Generator().manual_seed(5)
+    full = torch.randint(0, 262144, (B, T, 16, 16), generator=g).cuda()
+    n_ctx = T - 2
+    masked = torch.full((B, S), cfg.mask_token_id, dtype=torch.long, device="cuda")
+    try:
+        for graphs in (False, True):
+            model.decode_cuda_graphs = graphs
+            res = {}
+            for merged in (False, True):
+                for rep in range(3 if graphs else 1):  # graph path: eager warm-up, capture, replay
+                    model._sessions.clear() if rep == 0 else None
+                    sess = model._decode_session(full, n_ctx, acts, [dom] * B, {})
+                    sess.commit(full[:, n_ctx], n_ctx, prefetch_next=merged)
+                    logits = sess.step(masked, n_ctx + 1, first=True).clone()
+                    kv = sess.kv[:, : n_ctx + 1].clone()
+                res[merged] = (logits, kv)
+            assert torch.equal(res[False][1], res[True][1])
+            assert torch.equal(res[False][0], res[True][0])
+    finally:
+        model.decode_cuda_graphs = True
+        model._sessions.clear()
