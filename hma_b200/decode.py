@@ -70,23 +70,31 @@ class DecodeSession:
         return tuple(p[k].data_ptr() for k in ("pos_embed_TSC", "out_x_proj.bias", "decoder.layers.0.mlp.fc1.bias")
                      if k in p)
 
-    def _begin_eager(self, p, ids: torch.Tensor, actions: Optional[torch.Tensor], n_ctx: int, skip_normalization: bool) -> None:
+    def _begin_eager(self, p, ids: torch.Tensor, actions: Optional[torch.Tensor], n_ctx: int, skip_normalization: bool):
+        """`ids` holds the n_ctx context frames plus the (fully masked) frame to generate: one "prefill_step" pass fills the
+        cache AND returns that frame's first-step logits (its provisional K/V at cache frame n_ctx are never read: every
+        later pass reads [0, n_prev) and the frame's own commit overwrites them)."""
         eng, B, T, S, dom = self.eng, self.B, self.T, self.S, self.dom
-        dp = eng.dims(B, n_ctx, S, dom is not None)
-        a_ctx = actions[:, :n_ctx].contiguous() if actions is not None else None
-        eng.forward(p, ids, a_ctx, dom, dp, False, skip_normalization, t0=0, kv=self.kv, mode="prefill")
+        nf = ids.shape[1]
+        dp = eng.dims(B, nf, S, dom is not None)
+        a_ctx = actions[:, :nf].contiguous() if actions is not None else None
+        logits, _ = eng.forward(p, ids, a_ctx, dom, dp, False, skip_normalization, t0=0, kv=self.kv,
+                                mode="prefill_step" if nf == n_ctx + 1 else "prefill")
         if dom is not None:
             a_tb = actions.transpose(0, 1).reshape(T * B, -1).to(torch.float32).contiguous()  # (t, b) row order
             act, c_bf = eng.action_stem(p, a_tb, dom, skip_normalization)
             self.act_tb.copy_(act)
             if self.d1.modulate:
                 eng.modulation_all_layers(p, c_bf, dom, self.d1.num_layers, False, hmods=self.hmods_tb, mods=self.mods_tb)
+        return logits
 
     def begin(self, p: Dict[str, torch.Tensor], prompt_THW: torch.Tensor, n_ctx: int, actions: Optional[torch.Tensor],
-              skip_normalization: bool) -> None:
+              skip_normalization: bool, first_step: bool = True) -> None:
         """Prefill: context frames [0, n_ctx) -> K/V cache; action conditioning of every frame of the window. With CUDA
         graphs the whole prefill is replayed from static inputs from its third use on (the interactive loop of
-        sim/simulator.py:233-372 re-prompts a sliding window every step: at B=1 it is purely launch-bound)."""
+        sim/simulator.py:233-372 re-prompts a sliding window every step: at B=1 it is purely launch-bound).
+        `first_step`: the pass also carries frame n_ctx as a fully masked frame and keeps its logits for
+        `step(..., first=True)` — the first MaskGIT step of the frame about to be generated costs no pass of its own."""
         eng, B, T, S, dom = self.eng, self.B, self.T, self.S, self.dom
         sig = self.signature(p)
         if sig != self._sig:  # parameters were re-allocated: captured graphs point at dead memory
@@ -95,13 +103,17 @@ class DecodeSession:
             self._prefill.clear()
             self._sig = sig
         self._p = p
+        first_step = bool(first_step and n_ctx < T)
         ids = prompt_THW[:, :n_ctx].reshape(B, n_ctx, S)
-        key = (n_ctx, bool(skip_normalization))
+        if first_step:
+            ids = torch.cat([ids, torch.full((B, 1, S), self.mask_id, dtype=ids.dtype, device=ids.device)], dim=1)
+        nf = ids.shape[1]
+        key = (n_ctx, bool(skip_normalization), first_step)
         if not self.use_graphs or key not in self._prefill_warm:
             self._prefill_warm.add(key)
-            self._begin_eager(p, ids.contiguous(), actions, n_ctx, skip_normalization)
+            logits = self._begin_eager(p, ids.contiguous(), actions, n_ctx, skip_normalization)
         else:
-            eng.prepare_weights(p, eng.dims(B, n_ctx, S, dom is not None), dom, False)  # refresh bf16 copies outside the graph
+            eng.prepare_weights(p, eng.dims(B, nf, S, dom is not None), dom, False)  # refresh bf16 copies outside the graph
             rec = self._prefill.get(key)
             if rec is None:
                 rec = {"ids": ids.contiguous().clone(), "actions": None if actions is None else actions.to(torch.float32).clone()}
@@ -110,7 +122,7 @@ class DecodeSession:
                 if self.pool is None:
                     self.pool = torch.cuda.graph_pool_handle()
                 with torch.cuda.graph(g, pool=self.pool):
-                    self._begin_eager(p, rec["ids"], rec["actions"], n_ctx, skip_normalization)
+                    rec["logits"] = self._begin_eager(p, rec["ids"], rec["actions"], n_ctx, skip_normalization)
                 rec["graph"] = g
                 self._prefill[key] = rec
             else:
@@ -118,8 +130,9 @@ class DecodeSession:
                 if actions is not None:
                     rec["actions"].copy_(actions)
             rec["graph"].replay()
+            logits = rec["logits"]
         self.filled = n_ctx
-        self.first_t = -1
+        self.first_logits, self.first_t = (logits, n_ctx) if first_step else (None, -1)
 
     def _cond2(self, t: int):
         """Action conditioning of frames t, t + 1 in (b, t) row order (the tables are (t, b)); static buffers."""
