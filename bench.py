@@ -823,7 +823,8 @@ def main() -> None:
             "bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf if peak_tf else None,
             "traffic": None, "flops_per_generate_call": gflops,
             "what": "FLOPs the frame-incremental decode executes per generate() call (prefill of 8 frames + per new frame K one-frame "
-                    "passes with the head + one commit pass) / device time of the call, H2D prompt and D2H tokens included"}
+                    "passes with the head + one commit pass; the first step of a frame shares a launch with the prefill / the "
+                    "previous frame's commit, same FLOPs) / device time of the call, H2D prompt and D2H tokens included"}
         if gen_strong is not None:
             line["generation"]["strong_scaling_total_batch_64"] = {"value": gen_strong[0], "unit": "frames/s",
                                                                     "ms_per_generate_call": gen_strong[1], "batch_per_gpu": gen_strong[2]}
