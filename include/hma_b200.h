@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define HMA_B200_ABI_VERSION 2
+#define HMA_B200_ABI_VERSION 3
 
 int hma_abi_version(void);
 const char* hma_last_error(void);

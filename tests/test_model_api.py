@@ -60,7 +60,7 @@ def test_c_abi_exports_every_declared_symbol():
     assert len(names) >= 20
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/hma_b200.h but not exported"
-    assert lib.hma_abi_version() == 2
+    assert lib.hma_abi_version() == 3
 
 
 def test_forward_consumes_cpu_rng_like_the_reference(monkeypatch):
