@@ -33,6 +33,9 @@ _SIGNATURES = {
                     c_fp, c_fp, c_ll, c_void_p, c_ll, c_float, c_fp, c_fp, c_void_p],
     "hma_gemm_nt_ln": [c_void_p, c_ll, c_void_p, c_ll, c_int, c_int, c_int, c_void_p, c_ll, c_fp, c_fp, c_ll, c_float, c_int,
                        c_fp, c_fp, c_fp, c_int, c_float, c_void_p, c_ll, c_fp, c_void_p],
+    "hma_mar_sampler": [c_int, c_int, c_int, c_int, c_int, c_float, c_int, c_fp, c_fp, c_fp, c_void_p, c_ll, c_int,
+                        c_void_p, c_fp, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_fp, c_fp,
+                        c_void_p, c_void_p, c_void_p, c_fp, c_void_p, c_void_p],
     "hma_attn_spatial_fwd": [c_void_p, c_ll, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p, c_ll, c_fp,
                              c_void_p],
     "hma_attn_spatial_bwd": [c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_ll, c_fp, c_int, c_int, c_int, c_int, c_int,

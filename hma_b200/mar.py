@@ -456,6 +456,9 @@ class MarEngine(Engine):
         ops.mar_p_sample(out, x, noise_i, tb, i, temperature, clip, x_next, x16_next)
 
     MOD_CHUNK_BYTES = 2 << 30
+    # True: the whole ancestral loop of a chunk of steps as one persistent kernel (csrc/mar_sampler.cu); False: the
+    # kernel-by-kernel loop (16 launches per ancestral step)
+    persistent_sampler = False
 
     def sample(self, p, z16: Tensor, x_init: Tensor, noise: Tensor, te_tab: Tensor, respacing: str, temperature: float,
                clip: bool) -> Tensor:
@@ -472,6 +475,27 @@ class MarEngine(Engine):
         sy_all = ops.mar_silu_steps(c, te_tab)
         ada_w, ada_b = self._pad["ada_w"], self._pad["ada_b"]
         per = max(1, min(steps, self.MOD_CHUNK_BYTES // max(1, n * ada_w.shape[0] * 2)))
+        if self.persistent_sampler and self.cfg.diffloss_d <= 8 and x_init.shape[1] <= 16:
+            # the whole loop of a chunk of steps as ONE persistent launch (csrc/mar_sampler.cu): 16 launches per step -> 0
+            x = x_init.contiguous().clone()
+            dev, w = x.device, self.cfg.diffloss_w
+            work = dict(x=torch.empty(n, w, device=dev, dtype=torch.float32), barrier=torch.zeros(1, device=dev, dtype=torch.int32),
+                        **{k: torch.empty(n, w, device=dev, dtype=torch.bfloat16) for k in ("u16", "a16", "h2")})
+            q, Wp = self.NET, self.weights.plain
+            blocks = [q + f"res_blocks.{i}." for i in range(self.cfg.diffloss_d)]
+            if "in_t" not in self._pad:  # input projection transposed [D, 1024] (bulk-copied into shared memory per step)
+                self._pad["in_t"] = self._pad["in"][:, : x.shape[1]].t().contiguous()
+            args = dict(w_in_t=self._pad["in_t"], b_in=p[q + "input_proj.bias"], w1=[Wp[b + "mlp.0.weight"] for b in blocks],
+                        w2=[Wp[b + "mlp.2.weight"] for b in blocks], ln_g=[p[b + "in_ln.weight"] for b in blocks],
+                        ln_b=[p[b + "in_ln.bias"] for b in blocks], b1=[p[b + "mlp.0.bias"] for b in blocks],
+                        b2=[p[b + "mlp.2.bias"] for b in blocks], w_f=self._pad["fl"], b_f=self._pad["fl_bias"], work=work)
+            hi = steps
+            while hi > 0:
+                lo = max(0, hi - per)
+                mods = ops.gemm_nt(sy_all[lo * n: hi * n], ada_w, EPI_BF16, bias=ada_b)
+                ops.mar_sampler(x, noise, tb, mods, lo, hi, lo, temperature, clip, **args)
+                hi = lo
+            return x
         x = x_init.contiguous()
         x16 = ops.mar_q_sample(x, None, None, None, KPAD)
         nxt, nxt16 = torch.empty_like(x), torch.empty_like(x16)

@@ -517,6 +517,33 @@ def mar_p_sample(out: torch.Tensor, x: torch.Tensor, noise, tables, step: int, t
           float(temperature), int(clip), x_next.data_ptr(), _p(x16), x16.shape[1] if x16 is not None else D, _s())
 
 
+def mar_sampler(xt: torch.Tensor, noise: torch.Tensor, tables: torch.Tensor, mods: torch.Tensor, mods_step0: int, step_hi: int,
+                step_lo: int, temperature: float, clip: bool, w_in_t: torch.Tensor, b_in: torch.Tensor, w1, w2, ln_g, ln_b, b1, b2,
+                w_f: torch.Tensor, b_f: torch.Tensor, work: dict, dbg_out: Optional[torch.Tensor] = None) -> None:
+    """Ancestral steps step_hi-1 ... step_lo of the diffusion head's sampler in ONE persistent launch (csrc/mar_sampler.cu);
+    xt fp32 [R, D] is updated in place. w1 / w2 / ln_g / ln_b / b1 / b2: lists of `depth` tensors. work: dict of workspaces
+    (x fp32, u16 / a16 / h2 bf16 [R, 1024], barrier int32 [1]) owned by the caller (static under graph capture)."""
+    import ctypes
+    R, D = xt.shape
+    depth = len(w1)
+    assert xt.dtype == F32 and xt.is_contiguous() and noise.dtype == F32 and noise.is_contiguous() and noise.shape[1:] == (R, D)
+    assert mods.dtype == BF16 and mods.stride(1) == 1 and tables.dtype == F32 and tables.is_contiguous()
+    for t in list(w1) + list(w2):
+        assert t.dtype == BF16 and t.shape == (1024, 1024) and t.is_contiguous()
+    for t in list(ln_g) + list(ln_b) + list(b1) + list(b2):
+        assert t.dtype == F32 and t.numel() == 1024 and t.is_contiguous()
+    assert w_in_t.dtype == BF16 and w_in_t.shape == (D, 1024) and w_in_t.is_contiguous() and w_f.dtype == BF16 and w_f.is_contiguous()
+    assert w_f.shape[0] >= 2 * D and w_f.shape[1] == 1024 and b_f.numel() >= 2 * D
+    vp = ctypes.c_void_p * depth
+    arr = lambda ts: ctypes.cast(vp(*[t.data_ptr() for t in ts]), ctypes.c_void_p)  # noqa: E731
+    import os
+    _call("mar_sampler", 0.0, "hma_mar_sampler", R, D, depth, step_hi, step_lo, float(temperature), int(clip) | int(os.environ.get("HMA_SAMPLER_DBG", "0")), xt.data_ptr(),
+          noise.data_ptr(), tables.data_ptr(), mods.data_ptr(), mods.stride(0), mods_step0, w_in_t.data_ptr(),
+          b_in.data_ptr(), arr(w1), arr(w2), arr(ln_g), arr(ln_b), arr(b1), arr(b2), w_f.data_ptr(), b_f.data_ptr(),
+          work["x"].data_ptr(), work["u16"].data_ptr(), work["a16"].data_ptr(), work["h2"].data_ptr(), _p(dbg_out),
+          work["barrier"].data_ptr(), _s())
+
+
 def mar_gather_rows(src: torch.Tensor, idx: torch.Tensor, want32: bool, want16: bool):
     assert src.dtype == F32 and src.is_contiguous() and idx.dtype == torch.int32
     n, C = idx.numel(), src.shape[-1]

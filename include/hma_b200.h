@@ -325,6 +325,22 @@ int hma_gather_token_windows(const void* video, int elem_bytes, long long num_im
 int hma_gather_rows_f32(const float* table, long long num_rows, long long row_elems, const long long* starts, int B,
                         long long rows_per_sample, float* out, void* stream);
 
+/* The ancestral sampling loop of the diffusion head as ONE persistent kernel (DiffLoss.sample / p_sample_loop:
+ * hma/model/diffloss.py:37-59,163-233; hma/diffusion/gaussian_diffusion.py:237-314,358-392,394-490): spaced steps
+ * step_hi-1 ... step_lo for R rows; x_t [R, D] fp32 is updated in place. mods: bf16 adaLN modulations of every step
+ * (row (step - mods_step0) * R + r; columns per residual block shift | scale | gate (3 x 1024), then the final layer's
+ * shift | scale), noise fp32 [steps, R, D], tables fp32 [steps, 8] as hma_mar_p_sample. w1 / w2 / ln_g / ln_b / b1 / b2: HOST
+ * arrays of `depth` device pointers (mlp.0 / mlp.2 weights bf16 [1024, 1024]; in_ln weight / bias and the two biases fp32
+ * [1024]). w_in_t bf16 [D, 1024] (the input projection transposed, contiguous), w_f bf16 [>= 2D, 1024] contiguous. Workspaces x fp32 and u16 / a16 / h2 bf16:
+ * [R, 1024]; barrier: one device word. dbg_out (optional) fp32 [R, 2D]: the network output of the last step processed.
+ * At most one CTA per SM is launched (the stages of a step meet at a grid-wide barrier). */
+int hma_mar_sampler(int R, int D, int depth, int step_hi, int step_lo, float temperature, int clip, float* xt,
+                    const float* noise, const float* tables, const void* mods, long long ldmod, int mods_step0,
+                    const void* w_in_t, const float* b_in, const void* const* w1, const void* const* w2,
+                    const float* const* ln_g, const float* const* ln_b, const float* const* b1, const float* const* b2,
+                    const void* w_f, const float* b_f, float* x, void* u16, void* a16, void* h2, float* dbg_out,
+                    unsigned* barrier, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Token -> pixel decode (hma/visualize.py:136-151; external/magvit2 lookup_free_quantize.py:181-194,
  * improved_model.py:12-51,124-234). Activations are NHWC with a one-pixel zero border per image:

@@ -429,9 +429,11 @@ def test_mar_sampler_teacher_forced_against_oracle():
             worst = max(worst, err.max().item())
             assert err.max().item() <= 5e-2, (i, err.max().item())
     print("worst well-conditioned teacher-forced step error", worst, "| worst network-output error / range", worst_net)
-    # the product loop (adaLN modulations of all steps hoisted into one GEMM) == the step-by-step chain, bit for bit
+    # the kernel-by-kernel product loop (adaLN modulations of all steps hoisted into one GEMM) == the step-by-step chain, bit
+    # for bit (the persistent kernel, the default, has its own test: test_persistent_sampler_kernel_matches_...)
     noise = torch.stack([t[2] for t in sorted(trace, key=lambda t: t[0])]).to(DEV)
     z16 = z.bfloat16().to(DEV)
+    eng.persistent_sampler = False
     got = eng.sample(p, z16, x0.to(DEV), noise, te_tab, cfg.num_sampling_steps, 0.9, True)
     x = x0.to(DEV).contiguous()
     x16 = ops.mar_q_sample(x, None, None, None, KPAD)
@@ -445,6 +447,7 @@ def test_mar_sampler_teacher_forced_against_oracle():
         assert torch.equal(eng.sample(p, z16, x0.to(DEV), noise, te_tab, cfg.num_sampling_steps, 0.9, True), x)
     finally:
         del eng.MOD_CHUNK_BYTES
+        del eng.persistent_sampler
 
 
 def test_mar_maskgit_generate_matches_reference_fixture():
@@ -623,3 +626,64 @@ def test_mar_edge_cases_against_oracle():
             assert math.isclose(o.loss.item(), want.item(), rel_tol=1e-2) and gmax > 0
         else:
             assert o.loss.item() == 0.0 == want.item() and gmax == 0.0
+
+
+@pytest.mark.skipif(__import__("os").environ.get("HMA_B200_TEST_PERSISTENT") != "1", reason="opt-in until validated on the GPU")
+def test_persistent_sampler_kernel_matches_the_kernel_by_kernel_steps():
+    """csrc/mar_sampler.cu (the whole ancestral loop as one persistent kernel, stages separated by a grid barrier) against the
+    kernel-by-kernel path it replaces, step by step and teacher-forced (both are fed the same x_t): network output (eps | v)
+    and x_{t-1} of every spaced step, for row counts that fill one tile, several tiles and a ragged last tile."""
+    from hma_b200 import ops
+    from hma_b200.mar import KPAD
+
+    rec, cfg, sd = mar_golden()
+    model = build_model(rec, sd).eval()
+    eng, p = model._engine, model._inference_params()
+    eng.prepare_diffloss(p, False)
+    dev = torch.device(DEV)
+    tabs, _, steps = eng.tables(cfg.num_sampling_steps, dev)
+    te_tab = eng.time_table(p, cfg.num_sampling_steps, dev)
+    D = cfg.token_dim
+    g = torch.Generator().manual_seed(33)
+    q, Wp = eng.NET, eng.weights.plain
+    blocks = [q + f"res_blocks.{i}." for i in range(cfg.diffloss_d)]
+    for n in (40, 300, 512):
+        z16 = torch.randn(n, 256, generator=g).bfloat16().to(dev)
+        noise = torch.randn(steps, n, D, generator=g).to(dev)
+        c = eng.sample_cond(p, z16)
+        sy_all = ops.mar_silu_steps(c, te_tab)
+        mods = ops.gemm_nt(sy_all, eng._pad["ada_w"], 0, bias=eng._pad["ada_b"])
+        work = dict(x=torch.empty(n, 1024, device=dev), barrier=torch.zeros(1, device=dev, dtype=torch.int32),
+                    **{k: torch.empty(n, 1024, device=dev, dtype=torch.bfloat16) for k in ("u16", "a16", "h2")})
+        args = dict(w_in_t=eng._pad["in"][:, :D].t().contiguous(), b_in=p[q + "input_proj.bias"], w1=[Wp[b + "mlp.0.weight"] for b in blocks],
+                    w2=[Wp[b + "mlp.2.weight"] for b in blocks], ln_g=[p[b + "in_ln.weight"] for b in blocks],
+                    ln_b=[p[b + "in_ln.bias"] for b in blocks], b1=[p[b + "mlp.0.bias"] for b in blocks],
+                    b2=[p[b + "mlp.2.bias"] for b in blocks], w_f=eng._pad["fl"], b_f=eng._pad["fl_bias"], work=work)
+        x_t = (torch.randn(n, D, generator=g) * 1.5).to(dev)
+        worst_net = worst_x = 0.0
+        for i in reversed(range(steps)):
+            x16 = ops.mar_q_sample(x_t, None, None, None, KPAD)
+            want_net = eng._mlp(p, x16, None, None, mods=mods[i * n:(i + 1) * n])[:, : 2 * D].float()
+            want_x, w16 = torch.empty_like(x_t), torch.empty_like(x16)
+            eng.sample_step(p, c, te_tab, tabs, i, x_t, x16, noise[i], 0.9, True, want_x, w16)
+            got_x = x_t.clone()
+            dbg = torch.full((n, 2 * D), float("nan"), device=dev)
+            ops.mar_sampler(got_x, noise, tabs, mods, 0, i + 1, i, 0.9, True, dbg_out=dbg, **args)
+            e_net = ((dbg - want_net).abs().max() / want_net.abs().max()).item()
+            worst_net = max(worst_net, e_net)
+            assert e_net <= 2e-3, (n, i, e_net)
+            # x0 = sqrt(1/acp) x_t - sqrt(1/acp - 1) eps multiplies the (tiny) eps difference by up to 1e4 at the first steps
+            scale = max(want_x.abs().max().item(), 1.0)
+            e_x = ((got_x - want_x).abs().max() / scale).item()
+            if tabs[i, 3].item() <= 5.0:
+                worst_x = max(worst_x, e_x)
+                assert e_x <= 1e-2, (n, i, e_x)
+            x_t = want_x  # teacher forcing: both paths continue from the reference path's x_{t-1}
+        print(f"persistent sampler, {n} rows: worst network-output deviation {worst_net:.2e} of range, worst x_(t-1) {worst_x:.2e}")
+        # all steps inside ONE launch == the same steps launched one at a time (same kernel, deterministic: bit-identical)
+        x_a = (torch.randn(n, D, generator=g) * 1.5).to(dev)
+        x_b = x_a.clone()
+        ops.mar_sampler(x_a, noise, tabs, mods, 0, steps, 0, 0.9, True, **args)
+        for i in reversed(range(steps)):
+            ops.mar_sampler(x_b, noise, tabs, mods, 0, i + 1, i, 0.9, True, **args)
+        assert torch.isfinite(x_a).all() and torch.equal(x_a, x_b)
