@@ -456,9 +456,12 @@ class MarEngine(Engine):
         ops.mar_p_sample(out, x, noise_i, tb, i, temperature, clip, x_next, x16_next)
 
     MOD_CHUNK_BYTES = 2 << 30
-    # True: the whole ancestral loop of a chunk of steps as one persistent kernel (csrc/mar_sampler.cu); False: the
-    # kernel-by-kernel loop (16 launches per ancestral step)
-    persistent_sampler = False
+    # True: the whole ancestral loop of a chunk of steps as one persistent kernel (csrc/mar_sampler.cu) when every GEMM stage
+    # is one tile per CTA (<= PERSISTENT_MAX_ROWS rows: 9-13 % faster than 16 launches per step, tools/ubench/sampler_call.py;
+    # with more rows each CTA re-reads its activation tile once per 32 output columns and the 64/128-wide tiles of the
+    # kernel-by-kernel GEMMs win); False: always the kernel-by-kernel loop
+    persistent_sampler = True
+    PERSISTENT_MAX_ROWS = 512
 
     def sample(self, p, z16: Tensor, x_init: Tensor, noise: Tensor, te_tab: Tensor, respacing: str, temperature: float,
                clip: bool) -> Tensor:
@@ -475,7 +478,7 @@ class MarEngine(Engine):
         sy_all = ops.mar_silu_steps(c, te_tab)
         ada_w, ada_b = self._pad["ada_w"], self._pad["ada_b"]
         per = max(1, min(steps, self.MOD_CHUNK_BYTES // max(1, n * ada_w.shape[0] * 2)))
-        if self.persistent_sampler and self.cfg.diffloss_d <= 8 and x_init.shape[1] <= 16:
+        if self.persistent_sampler and n <= self.PERSISTENT_MAX_ROWS and self.cfg.diffloss_d <= 8 and x_init.shape[1] <= 16:
             # the whole loop of a chunk of steps as ONE persistent launch (csrc/mar_sampler.cu): 16 launches per step -> 0
             x = x_init.contiguous().clone()
             dev, w = x.device, self.cfg.diffloss_w

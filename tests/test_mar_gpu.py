@@ -628,7 +628,6 @@ def test_mar_edge_cases_against_oracle():
             assert o.loss.item() == 0.0 == want.item() and gmax == 0.0
 
 
-@pytest.mark.skipif(__import__("os").environ.get("HMA_B200_TEST_PERSISTENT") != "1", reason="opt-in until validated on the GPU")
 def test_persistent_sampler_kernel_matches_the_kernel_by_kernel_steps():
     """csrc/mar_sampler.cu (the whole ancestral loop as one persistent kernel, stages separated by a grid barrier) against the
     kernel-by-kernel path it replaces, step by step and teacher-forced (both are fed the same x_t): network output (eps | v)

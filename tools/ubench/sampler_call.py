@@ -33,6 +33,7 @@ for n in [int(a) for a in sys.argv[1:]] or [64, 512, 4096]:
     res = {}
     for persistent in (False, True):
         eng.persistent_sampler = persistent
+        eng.PERSISTENT_MAX_ROWS = 1 << 30
         eng.sample(p, z16, x0, noise, te_tab, cfg.num_sampling_steps, 1.0, True)
         torch.cuda.synchronize()
         g = torch.cuda.CUDAGraph()
