@@ -261,3 +261,31 @@ def test_prefill_carrying_the_first_step_matches_a_separate_step(setup):
         assert torch.equal(out[True][1], out[False][1])
     finally:
         model._sessions.clear()
+
+
+def test_generate_without_actions_incremental_vs_full_window(setup):
+    """No action conditioning (n = S = 256 tokens per frame, no adaLN): the merged decode passes (prefill + first step,
+    commit + next first step) against the full-window recompute of the reference algorithm."""
+    rec, cfg, sd, model = setup
+    r = rec[rec["domains"][0]]
+    kw = dict(maskgit_steps=2, temperature=0.0, h=[16], w=[16])
+    inp = r["labels"][:, : 2 * 256].cuda()
+    model._sessions.clear()
+    try:
+        model.decode_algorithm = "full"
+        torch.manual_seed(9)  # (the re-masking keys of unmask_mode "random" come from torch's generator)
+        full = model.generate(inp, None, 2 * 256, **kw)
+        model.decode_algorithm = "incremental"
+        runs = []
+        for graphs in (False, True, True):
+            model.decode_cuda_graphs = graphs
+            torch.manual_seed(9)
+            runs.append(model.generate(inp, None, 2 * 256, **kw))
+        assert torch.equal(runs[0], runs[1]) and torch.equal(runs[1], runs[2])
+        assert (runs[0] != cfg.mask_token_id).all() and torch.equal(runs[0][:, : 2 * 256], inp)
+        agree = (runs[0] == full).float().mean().item()
+        assert agree > 0.95, agree
+    finally:
+        model.decode_algorithm = "incremental"
+        model.decode_cuda_graphs = True
+        model._sessions.clear()
