@@ -15,6 +15,8 @@ KERNELS = {
                                     15: "i:Pb_seen"}, single=(0, 10, 11)),
     "gemm_nt": dict(single=(0, 10), names={0: "start", 10: "end", 1: "mma:top", 2: "mma:tmem_free", 3: "mma:committed", 4: "epi:top",
                                            5: "epi:acc_ready", 6: "epi:done", 7: "ln:sent", 8: "ln:wait", 9: "ln:got", 11: "ln:done"}),
+    "mar_sampler": dict(single=(), names={0: "sync_exit(e)", 7: "sync_enter(e)", 1: "P:first", 2: "P:last", 3: "M:full0", 8: "M:full1",
+                                           4: "M:full15", 5: "E:tfull", 6: "E:done"}),
     "gemm_wgrad": dict(single=(0, 3, 4, 5), names={0: "start", 3: "mma_done", 4: "red_issued", 5: "end", 1: "tma_issued", 2: "full"}),
     "attn_spatial_bwd": dict(names={0: "start", 11: "loaded", 1: "SdP_issued", 5: "A0:P", 6: "A3:P", 7: "A4:P", 8: "A7:P",
                                     12: "B8:dS", 13: "B9:dS", 14: "B12:dS", 15: "B15:dS",
@@ -29,6 +31,13 @@ def run_attn_spatial_bwd():
     deltas = [(d.float() * o[0].float()).view(frames * n, H, 32).sum(-1).contiguous() for d, o in zip(douts, outs)]
     for i in range(4):
         ops.attn_spatial_bwd(qkvs[i], None, douts[i], outs[i][1], frames, n, H, 0.17, delta=deltas[i])
+
+def run_mar_sampler():  # tools/instr/mar_sampler.py first; stamps of the last persistent launch (64 rows)
+    import runpy
+    sys.argv = [sys.argv[0], "64"]
+    runpy.run_path(os.path.join(os.path.dirname(os.path.abspath(__file__)), "ubench", "sampler_call.py"), run_name="__main__")
+    sys.argv = [sys.argv[0], "mar_sampler"]
+
 
 def run_gemm_wgrad():
     N = 40960
@@ -71,7 +80,7 @@ def main():
     assert fn(buf) == 0
     a = np.array(buf).reshape(16, 64)
     names = KERNELS[name]["names"]
-    t0 = a[0, 0]
+    t0 = a[0, 0] or a[0, 1]
     single = [e for e in names if e in KERNELS[name].get('single', (0, 9, 10, 11))]
     print(" ".join(f"{names[e]}={a[e, 0] - t0}" for e in single))
     print("event-0 sub-stamps:", " ".join(f"[{i}]={a[0, i] - t0}" for i in range(1, 8) if a[0, i]))
