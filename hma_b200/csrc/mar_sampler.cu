@@ -341,6 +341,8 @@ __global__ void __launch_bounds__(kSThreads, 1) mar_sampler_kernel(const __grid_
   }
   grid_sync(p.barrier, epoch);
 
+  // development switches (bits 1-3 of `clip`, set through HMA_SAMPLER_DBG by hma_b200.ops; results are then meaningless): leave
+  // out the GEMM stages / the row stages / the grid barriers, to time what remains (tools/ubench/sampler_call.py)
   const bool dbg_no_gemm = (p.clip & 2) != 0, dbg_no_row = (p.clip & 4) != 0, dbg_no_sync = (p.clip & 8) != 0;
   for (int step = p.step_hi - 1; step >= p.step_lo; --step) {
     for (int blk = 0; blk < p.depth; ++blk) {
