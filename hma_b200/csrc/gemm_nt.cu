@@ -756,6 +756,14 @@ static int gemm_nt_impl(const void* A, long long lda, const void* B, long long l
   HMA_REQUIRE(N % 128 == 0, "gemm_nt: N=%d must be a multiple of 128", N);
   HMA_REQUIRE(out != nullptr, "gemm_nt: out is null");
   HMA_REQUIRE(ldo % 8 == 0 && ldo2 % 8 == 0 && ldr % 4 == 0 && ldaux % 4 == 0, "gemm_nt: leading dimensions must keep rows 16-byte aligned");
+  if (ln != nullptr) {  // (argument checks come before anything that needs the driver)
+    HMA_REQUIRE(epi == HMA_EPI_RESID_F32 && N == 256 && out2 == nullptr && colsum == nullptr,
+                "gemm_nt_ln: the LayerNorm epilogue needs the fp32 residual epilogue and N == 256 (a row = one 2-CTA cluster)");
+    HMA_REQUIRE(ln->ln_mode == 1 || ln->ln_mode == 2, "gemm_nt_ln: bad LayerNorm mode %d", ln->ln_mode);
+    HMA_REQUIRE(ln->ln_mode != 1 || (ln->ln_gamma && ln->ln_beta), "gemm_nt_ln: affine mode needs gamma/beta");
+    HMA_REQUIRE(ln->ln_mode != 2 || (ln->ln_mod && ln->ln_rpg > 0), "gemm_nt_ln: modulate mode needs shift/scale");
+    HMA_REQUIRE(ln->ln_out != nullptr && ln->ln_ldo % 4 == 0, "gemm_nt_ln: bad LayerNorm output");
+  }
   int bn = (N % 256 == 0 && N >= 512) ? 256 : 128;
   // Few rows (decode / sampler shapes, M <= a few hundred): 256-wide tiles would occupy a fraction of the SMs and each
   // CTA's k-loop is latency-bound, so halve the tile width to double the CTAs in flight.
@@ -793,12 +801,6 @@ static int gemm_nt_impl(const void* A, long long lda, const void* B, long long l
                   (epi == HMA_EPI_RESID_F32 && out2 != nullptr),
               "gemm_nt: colsum is produced by the d-activation epilogues and by the residual epilogue with a bf16 copy");
   if (ln != nullptr) {
-    HMA_REQUIRE(epi == HMA_EPI_RESID_F32 && N == 256 && out2 == nullptr && colsum == nullptr,
-                "gemm_nt_ln: the LayerNorm epilogue needs the fp32 residual epilogue and N == 256 (a row = one 2-CTA cluster)");
-    HMA_REQUIRE(ln->ln_mode == 1 || ln->ln_mode == 2, "gemm_nt_ln: bad LayerNorm mode %d", ln->ln_mode);
-    HMA_REQUIRE(ln->ln_mode != 1 || (ln->ln_gamma && ln->ln_beta), "gemm_nt_ln: affine mode needs gamma/beta");
-    HMA_REQUIRE(ln->ln_mode != 2 || (ln->ln_mod && ln->ln_rpg > 0), "gemm_nt_ln: modulate mode needs shift/scale");
-    HMA_REQUIRE(ln->ln_out != nullptr && ln->ln_ldo % 4 == 0, "gemm_nt_ln: bad LayerNorm output");
     p.ln_mode = ln->ln_mode; p.ln_gamma = ln->ln_gamma; p.ln_beta = ln->ln_beta; p.ln_mod = ln->ln_mod; p.ln_rpg = ln->ln_rpg;
     p.ln_eps = ln->ln_eps; p.ln_out = ln->ln_out; p.ln_ldo = ln->ln_ldo; p.ln_stats = ln->ln_stats;
     const bool stat = smem_need<128, HMA_EPI_RESID_F32>(p.K / kBK, true, 3) + kLnStash + kLnStatic <= (size_t)kSmemLimit;

@@ -71,3 +71,34 @@ def test_python_binding_raises_with_the_library_message():
     with pytest.raises(_lib.HmaError, match="multiple of 64"):
         _lib.call("hma_gemm_nt", P, 256, P, 256, 128, 256, 100, 0, P, 256, None, 0, None, None, 0, None, 0, 1.0, None, None, None)
     assert isinstance(_lib.lib(), ctypes.CDLL)
+
+
+def test_round2_entry_points_reject_bad_arguments():
+    # residual GEMM + LayerNorm epilogue: whole rows only (N == 256), a valid mode, its operands
+    ln = lambda N, mode, gamma, out: _call("hma_gemm_nt_ln", P, 256, P, 256, 128, N, 256, P, N, None, None, 0, 1.0, mode, gamma, gamma,  # noqa: E731
+                                           None, 0, 1e-5, out, 256, None, None)
+    rc, msg = ln(512, 1, P, P)
+    assert rc < 0 and "N == 256" in msg
+    rc, msg = ln(256, 3, P, P)
+    assert rc < 0 and "mode" in msg
+    rc, msg = ln(256, 1, None, P)
+    assert rc < 0 and "gamma/beta" in msg
+    rc, msg = ln(256, 2, None, P)
+    assert rc < 0 and "shift/scale" in msg
+    # cached temporal attention with several frames per sample: rows must be whole samples
+    rc, msg = _call("hma_attn_temporal_cached", P, 768, 0, 256, 512, P, 4096, 100, 3, 8, 0.17, P, 256, 2, 32, None)
+    assert rc < 0 and "whole number" in msg
+    # persistent sampler: token dimension, depth, modulation range
+    vp = (ctypes.c_void_p * 4)(P, P, P, P)
+    arr = ctypes.cast(vp, ctypes.c_void_p)
+    smp = lambda D, depth, lo, m0: _call("hma_mar_sampler", 64, D, depth, 10, lo, 1.0, 1, P, P, P, P, 14336, m0, P, P, arr, arr, arr, arr,  # noqa: E731
+                                         arr, arr, P, P, P, P, P, P, None, P, None)
+    rc, msg = smp(40, 4, 0, 0)
+    assert rc < 0 and "token dimension" in msg
+    rc, msg = smp(16, 9, 0, 0)
+    assert rc < 0 and "depth" in msg
+    rc, msg = smp(16, 4, 2, 5)
+    assert rc < 0 and "modulations start" in msg
+    rc, msg = _call("hma_mar_sampler", 0, 16, 4, 10, 0, 1.0, 1, P, P, P, P, 14336, 0, P, P, arr, arr, arr, arr, arr, arr, P, P, P, P, P, P,
+                    None, P, None)
+    assert rc == 0  # no rows: a no-op
